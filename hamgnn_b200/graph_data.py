@@ -228,9 +228,21 @@ def build_graph(z: np.ndarray, pos_bohr: np.ndarray, cell_bohr: np.ndarray, pbc=
     dst = np.concatenate(dst)
     sh = np.concatenate(sh)
     E = len(src)
-    # inverse edge: (dst -> src, -shift)
-    lut = {(int(a), int(b), int(s[0]), int(s[1]), int(s[2])): e for e, (a, b, s) in enumerate(zip(src, dst, sh))}
-    inv = np.array([lut[(int(b), int(a), -int(s[0]), -int(s[1]), -int(s[2]))] for a, b, s in zip(src, dst, sh)], dtype=np.int64)
+    # inverse edge: (dst -> src, -shift), found by sorting a composite integer key
+    smax = int(np.abs(sh).max()) if E else 0
+    base = 2 * smax + 1
+
+    def _key(a, b, s):
+        k = a.astype(np.int64) * n + b.astype(np.int64)
+        for c in range(3):
+            k = k * base + (s[:, c] + smax)
+        return k
+
+    key = _key(src, dst, sh)
+    order = np.argsort(key, kind="stable")
+    pos_in_sorted = np.searchsorted(key[order], _key(dst, src, -sh))
+    inv = order[pos_in_sorted].astype(np.int64)
+    assert np.array_equal(key[inv], _key(dst, src, -sh)), "graph is not closed under edge inversion"
     nbr_shift = sh.astype(np.float64) @ cell
     d = Data(
         z=torch.from_numpy(z), pos=torch.from_numpy(pos).to(dtype), cell=torch.from_numpy(cell).to(dtype)[None],

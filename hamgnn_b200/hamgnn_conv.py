@@ -1,0 +1,353 @@
+"""`HamGNNConvE3` ("HamGNN_pre") on the B200 kernels -- host-side mirror of
+/root/reference/hamgnn/models/hamgnn_conv.py:88-284.
+
+Same constructor contract (`config.HamGNN_pre.*`), same `.irreps_node_features`, same
+`forward(data) -> {'node_attr': [N, D], 'edge_attr': [E, D]}` with the same in-place writes on `data`
+(node_attrs, node_features, edge_attrs, edge_embedding, edge_vectors, edge_lengths, edge_features),
+and the same parameter names / e3nn flat layouts, so a reference state_dict loads with
+`load_state_dict(sd, strict=False)` (the e3nn constant buffers are ignored).
+
+All arithmetic runs in libhamgnn_b200.so (hgb_edge_embed, hgb_msgpack_forward, hgb_linear_forward,
+hgb_resblock_forward).  Inference only in this round: the kernels are forward-only and the module
+raises if autograd is requested through it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import lib as L
+from .irreps import Ir, Irreps, MulIr
+from .plan import Branch, GateLayout, LinearOp, MessagePackOp, linear_forward
+
+
+class AttrDict(dict):
+    """EasyDict stand-in (the reference returns an EasyDict from forward, hamgnn_conv.py:278-284)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class _W(nn.Module):
+    """Holder of one flat e3nn-layout `weight` parameter (TensorProduct / Linear)."""
+
+    def __init__(self, numel: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(numel))
+
+
+class _FC(nn.Module):
+    """e3nn FullyConnectedNet parameter layout: layer{i}.weight [h_in, h_out]."""
+
+    def __init__(self, hs):
+        super().__init__()
+        for i, (a, b) in enumerate(zip(hs, hs[1:])):
+            lay = nn.Module()
+            lay.weight = nn.Parameter(torch.randn(a, b))
+            self.add_module(f"layer{i}", lay)
+        self.n = len(hs) - 1
+
+    def weights(self):
+        return [getattr(self, f"layer{i}").weight for i in range(self.n)]
+
+
+class _LinearScaler(nn.Module):
+    def __init__(self, numel):
+        super().__init__()
+        self.linear_out = _W(numel)
+
+
+class MessagePackBlock(nn.Module):
+    """Parameters of hamgnn/nn/message_passing.py:26-134 (non-lite) + the fused kernel plan."""
+
+    def __init__(self, irreps_node, irreps_edge, irreps_sh, irreps_out, num_radial, radial_MLP, skip_edge=False):
+        super().__init__()
+        irreps_node, irreps_edge, irreps_out = Irreps(irreps_node), Irreps(irreps_edge), Irreps(irreps_out)
+        self.op = MessagePackOp(
+            [Branch(irreps_node, 2, 0), Branch(irreps_edge, 1, 2)], irreps_sh, irreps_out, num_radial, radial_MLP,
+            src_dims=[irreps_node.dim, irreps_node.dim, irreps_edge.dim], direct_src=2 if skip_edge else None)
+        op = self.op
+        self.node_tensor_product = _W(op.tp_numel[0])
+        self.edge_tensor_product = _W(op.tp_numel[1])
+        self.node_linear_scaler = _LinearScaler(op.lin_mid_blocks[0][1])
+        self.edge_linear_scaler = _LinearScaler(op.lin_mid_blocks[1][1])
+        hs = [num_radial] + list(radial_MLP)
+        self.node_weight_generator = _FC(hs + [op.n_channels[0]])
+        self.edge_weight_generator = _FC(hs + [op.n_channels[1]])
+        self.node_linear_out = _W(op.lin_out_blocks[0][1])
+        self.edge_linear_out = _W(op.lin_out_blocks[1][1])
+
+    def weights(self, direct: Optional[torch.Tensor] = None) -> dict:
+        return {"tp": [self.node_tensor_product.weight, self.edge_tensor_product.weight],
+                "fc": [self.node_weight_generator.weights(), self.edge_weight_generator.weights()],
+                "lin_mid": [self.node_linear_scaler.linear_out.weight, self.edge_linear_scaler.linear_out.weight],
+                "lin_out": [self.node_linear_out.weight, self.edge_linear_out.weight], "direct": direct}
+
+
+class ResidualBlock(nn.Module):
+    """hamgnn/nn/interaction_blocks.py:264-358 (gate nonlinearity)."""
+
+    def __init__(self, irreps_in, hidden):
+        super().__init__()
+        irreps_in = Irreps(irreps_in)
+        self.gate = GateLayout(Irreps(hidden))
+        self.op1 = LinearOp(irreps_in, self.gate.irreps_in)
+        self.op2 = LinearOp(self.gate.irreps_out, irreps_in)
+        self.linear1 = _W(self.op1.weight_numel)
+        self.linear2 = _W(self.op2.weight_numel)
+
+    def forward_cuda(self, x, extra=None, post: Optional[LinearOp] = None, post_w=None):
+        L.require_cuda(x)
+        x = L.f32c(x)
+        n = x.shape[0]
+        out_dim = post.irreps_out.dim if post is not None else x.shape[1]
+        y = torch.empty(n, out_dim, device=x.device, dtype=torch.float32)
+        p1, p2 = self.op1.plan(self.linear1.weight), self.op2.plan(self.linear2.weight)
+        pp = post.plan(post_w) if post is not None else None
+        rc = L.load().hgb_resblock_forward(C.byref(p1), C.byref(self.gate.desc), C.byref(p2),
+                                           C.byref(pp) if pp is not None else None, x.data_ptr(), L.ptr(extra), n,
+                                           y.data_ptr(), L.stream_ptr(x.device))
+        L.check(rc, "hgb_resblock_forward")
+        return y
+
+
+class ConvBlockE3(nn.Module):
+    """hamgnn/nn/convolution.py:23-160."""
+
+    def __init__(self, D, irreps_sh, num_radial, radial_MLP):
+        super().__init__()
+        self.D = Irreps(D)
+        self.residual = ResidualBlock(D, D)
+        self.conv_tp = MessagePackBlock(D, D, irreps_sh, D, num_radial, radial_MLP)
+        self.skip_op = LinearOp(D, D)
+        self.skip_linear = _W(self.skip_op.weight_numel)
+
+    def forward(self, data):
+        sender, receiver = data["edge_index"][0], data["edge_index"][1]
+        x, e = data["node_features"], data["edge_features"]
+        skip = linear_forward(self.skip_op, self.skip_linear.weight, x)
+        agg = torch.zeros_like(x)
+        self.conv_tp.op.forward(self.conv_tp.weights(), [x, x, e], [sender, receiver, None], data["edge_attrs"],
+                                data["edge_embedding"], e.shape[0], agg, out_index=receiver)
+        out = self.residual.forward_cuda(agg, extra=skip)
+        data["node_features"] = out
+        return out
+
+
+class PairInteractionBlock(nn.Module):
+    """hamgnn/nn/interaction_blocks.py:30-164."""
+
+    def __init__(self, D, irreps_sh, num_radial, radial_MLP, use_skip_connections, legacy_edge_update):
+        super().__init__()
+        self.use_skip_connections, self.legacy_edge_update = use_skip_connections, legacy_edge_update
+        self.up_op = LinearOp(D, D)
+        self.linear_up_src = _W(self.up_op.weight_numel)
+        self.linear_up_tar = _W(self.up_op.weight_numel)
+        self.conv_tp = MessagePackBlock(D, D, irreps_sh, D, num_radial, radial_MLP, skip_edge=use_skip_connections)
+        if use_skip_connections:
+            self.skip_linear = _W(self.up_op.weight_numel)
+
+    def forward(self, data):
+        src, dst = data["edge_index"][0], data["edge_index"][1]
+        x, e = data["node_features"], data["edge_features"]
+        if not self.use_skip_connections and self.legacy_edge_update:
+            return e  # legacy: the mixed features are discarded (interaction_blocks.py:156-158)
+        xs = linear_forward(self.up_op, self.linear_up_src.weight, x)
+        xt = linear_forward(self.up_op, self.linear_up_tar.weight, x)
+        out = torch.empty_like(e)
+        direct = self.skip_linear.weight if self.use_skip_connections else None
+        self.conv_tp.op.forward(self.conv_tp.weights(direct), [xs, xt, e], [src, dst, None], data["edge_attrs"],
+                                data["edge_embedding"], e.shape[0], out)
+        data["edge_features"] = out
+        return out
+
+
+class _EmbeddingTP(nn.Module):
+    """TensorProductWithMemoryOptimizationWithWeight parameters (tensor_products.py:51-167)."""
+
+    def __init__(self, irreps_in, irreps_sh, irreps_out, num_radial, radial_MLP):
+        super().__init__()
+        irreps_in = Irreps(irreps_in)
+        self.op = MessagePackOp([Branch(irreps_in, 1, 0, has_out_linear=False)], irreps_sh, irreps_out, num_radial,
+                                radial_MLP, src_dims=[irreps_in.dim])
+        self.tensor_product = _W(self.op.tp_numel[0])
+        self.linear_scaler = _LinearScaler(self.op.lin_mid_blocks[0][1])
+        self.weight_generator = _FC([num_radial] + list(radial_MLP) + [self.op.n_channels[0]])
+
+    def weights(self):
+        return {"tp": [self.tensor_product.weight], "fc": [self.weight_generator.weights()],
+                "lin_mid": [self.linear_scaler.linear_out.weight], "lin_out": [None], "direct": None}
+
+
+class PairInteractionEmbeddingBlock(nn.Module):
+    """hamgnn/nn/embeddings.py:215-337."""
+
+    def __init__(self, irreps_attr, irreps_sh, D, num_radial, radial_MLP):
+        super().__init__()
+        self.up_op = LinearOp(irreps_attr, irreps_attr)
+        self.linear_up_src = _W(self.up_op.weight_numel)
+        self.linear_up_dst = _W(self.up_op.weight_numel)
+        self.conv_tp = _EmbeddingTP(irreps_attr, irreps_sh, D, num_radial, radial_MLP)
+        self.out_dim = Irreps(D).dim
+
+    def forward(self, data):
+        src, dst = data["edge_index"][0], data["edge_index"][1]
+        x = data["node_features"]
+        E = src.shape[0]
+        h = linear_forward(self.up_op, self.linear_up_src.weight, x, rows=src)
+        linear_forward(self.up_op, self.linear_up_dst.weight, x, rows=dst, out=h, accumulate=True)
+        out = torch.empty(E, self.out_dim, device=x.device, dtype=torch.float32)
+        self.conv_tp.op.forward(self.conv_tp.weights(), [h], [None], data["edge_attrs"], data["edge_embedding"], E, out)
+        data["edge_features"] = out
+        return out
+
+
+class _Atomwise(nn.Module):
+    def __init__(self, numel):
+        super().__init__()
+        self.linear = _W(numel)
+
+
+class _Bessel(nn.Module):
+    def __init__(self, cutoff, n_rbf):
+        super().__init__()
+        self.register_buffer("freqs", torch.arange(1, n_rbf + 1) * math.pi / cutoff)
+
+
+class _Cutoff(nn.Module):
+    def __init__(self, cutoff):
+        super().__init__()
+        self.register_buffer("cutoff", torch.FloatTensor([cutoff]))
+
+
+class _RadialBasis(nn.Module):
+    def __init__(self, basis, cutoff):
+        super().__init__()
+        self.basis, self.cutoff = basis, cutoff
+
+
+DEFAULTS = dict(cutoff=26.0, radius_type="openmx", edge_sh_normalization="component", edge_sh_normalize=True,
+                irreps_edge_sh="0e + 1o + 2e + 3o + 4e + 5o",
+                irreps_node_features="64x0e+64x0o+32x1o+16x1e+12x2o+25x2e+18x3o+9x3e+4x4o+9x4e+4x5o+4x5e+2x6e",
+                num_layers=3, num_radial=64, num_types=96, rbf_func="bessel", radial_MLP=[64, 64], use_corr_prod=False,
+                use_kan=False, build_internal_graph=False, use_gradient_checkpointing=False, legacy_edge_update=False,
+                lite_mode=False, apply_charge_doping=False)
+
+
+class HamGNNConvE3(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        pre = _get(config, "HamGNN_pre", config)
+        c = dict(DEFAULTS)
+        for k in list(DEFAULTS) + ["radius_scale", "correlation", "num_hidden_features"]:
+            v = _get(pre, k, None)
+            if v is not None:
+                c[k] = v
+        if _get(pre, "radius_scale", None) is not None:
+            assert c["radius_scale"] > 1.0, "The radius scaling factor must be greater than 1.0."
+        if str(c["rbf_func"]).lower() != "bessel":
+            if str(c["rbf_func"]).lower() in ("gaussian", "exp-gaussian", "exp-bernstein", "bernstein"):
+                raise NotImplementedError(f"rbf_func={c['rbf_func']} is a config variant outside the B200 hot path "
+                                          "(SURVEY.md section 2 row 8); only 'bessel' is implemented")
+            raise ValueError(f"Unsupported radial basis function: {c['rbf_func']}")
+        for flag in ("use_corr_prod", "use_kan", "build_internal_graph", "lite_mode", "apply_charge_doping"):
+            if c[flag]:
+                raise NotImplementedError(f"HamGNN_pre.{flag}=True is outside the B200 hot path of this round "
+                                          "(SURVEY.md section 8f)")
+        if c["edge_sh_normalization"] != "component" or not c["edge_sh_normalize"]:
+            raise NotImplementedError("only edge_sh_normalization='component', edge_sh_normalize=True is implemented")
+        self.cfg = c
+        self.num_types = int(c["num_types"])
+        self.cutoff = float(c["cutoff"])
+        self.num_radial = int(c["num_radial"])
+        self.num_layers = int(c["num_layers"])
+        self.radial_MLP = list(c["radial_MLP"])
+        self.legacy_edge_update = bool(c["legacy_edge_update"])
+        self.irreps_edge_sh = Irreps(c["irreps_edge_sh"])
+        self.irreps_node_features = Irreps(c["irreps_node_features"])
+        for m in self.irreps_edge_sh:
+            if m.mul != 1 or m.ir.p != (-1) ** m.ir.l:
+                raise NotImplementedError("irreps_edge_sh must be spherical-harmonic irreps (1 x l with parity (-1)^l)")
+        self._sh_ls = (C.c_int32 * len(self.irreps_edge_sh))(*[m.ir.l for m in self.irreps_edge_sh])
+
+        D = self.irreps_node_features
+        ir_attr = Irreps([MulIr(self.num_types, Ir(0, 1))])
+        # buffers registered under the reference's names (hamgnn_conv.py:127,165-167)
+        self.radial_basis_functions = _Bessel(self.cutoff, self.num_radial)
+        self.cutoff_func = _Cutoff(self.cutoff)
+        self.radial_basis = _RadialBasis(self.radial_basis_functions, self.cutoff_func)
+        self.pair_embedding = PairInteractionEmbeddingBlock(ir_attr, self.irreps_edge_sh, D, self.num_radial, self.radial_MLP)
+        self.chem_op = LinearOp(ir_attr, D)
+        self.chemical_embedding = _Atomwise(self.chem_op.weight_numel)
+        self.convolutions = nn.ModuleList()
+        self.pair_interactions = nn.ModuleList()
+        for i in range(self.num_layers):
+            self.convolutions.append(ConvBlockE3(D, self.irreps_edge_sh, self.num_radial, self.radial_MLP))
+            skip = ((i > 0) if self.legacy_edge_update else True)
+            self.pair_interactions.append(PairInteractionBlock(D, self.irreps_edge_sh, self.num_radial, self.radial_MLP,
+                                                               use_skip_connections=skip,
+                                                               legacy_edge_update=self.legacy_edge_update))
+
+    @property
+    def num_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    # -- a1 + a2
+    def edge_embed(self, data):
+        pos, shift, ei = L.f32c(data["pos"]), L.f32c(data["nbr_shift"]), L.i64c(data["edge_index"])
+        L.require_cuda(pos, shift, ei)
+        E = ei.shape[1]
+        dev = pos.device
+        S = self.irreps_edge_sh.dim
+        sh = torch.empty(E, S, device=dev, dtype=torch.float32)
+        rbf = torch.empty(E, self.num_radial, device=dev, dtype=torch.float32)
+        vec = torch.empty(E, 3, device=dev, dtype=torch.float32)
+        ln = torch.empty(E, device=dev, dtype=torch.float32)
+        freqs = self.radial_basis_functions.freqs.detach().float().cpu().contiguous()
+        fptr = C.cast(freqs.data_ptr(), C.POINTER(C.c_float))
+        rc = L.load().hgb_edge_embed(pos.data_ptr(), shift.data_ptr(), ei.data_ptr(), E, self._sh_ls, len(self._sh_ls),
+                                     self.cutoff, fptr,
+                                     self.num_radial, sh.data_ptr(), rbf.data_ptr(), vec.data_ptr(), ln.data_ptr(),
+                                     L.stream_ptr(dev))
+        L.check(rc, "hgb_edge_embed")
+        data["edge_attrs"], data["edge_embedding"] = sh, rbf
+        data["edge_vectors"], data["edge_lengths"] = vec, ln
+
+    def forward(self, data):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # forward-only kernels: make the contract explicit instead of silently returning detached tensors
+            raise RuntimeError("hamgnn_b200.HamGNNConvE3 is inference-only in this round: call it under "
+                               "torch.no_grad() (backward kernels are the first 'next' row, SURVEY.md section 8f)")
+        if torch.get_default_dtype() != torch.float32:
+            raise NotImplementedError("the B200 path computes in fp32 (reference default precision: 32)")
+        z = data["z"]
+        L.require_cuda(z)
+        if int(z.max()) >= self.num_types or int(z.min()) < 0:
+            raise IndexError("atomic number outside [0, num_types)")
+        onehot = torch.nn.functional.one_hot(z, num_classes=self.num_types).to(torch.float32)
+        data["node_attrs"] = onehot
+        data["node_features"] = onehot
+        self.edge_embed(data)
+        self.pair_embedding(data)
+        data["node_features"] = linear_forward(self.chem_op, self.chemical_embedding.linear.weight, onehot)
+        for i in range(self.num_layers):
+            self.convolutions[i](data)
+            self.pair_interactions[i](data)
+        return AttrDict(node_attr=data["node_features"], edge_attr=data["edge_features"])

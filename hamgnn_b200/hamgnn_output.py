@@ -1,0 +1,235 @@
+"""`HamGNNPlusPlusOut` ("HamGNN_out") on the B200 kernels -- host-side mirror of the non-SOC, non-magnetic
+branch of /root/reference/hamgnn/models/hamgnn_output.py (ctor :96-256, forward :2916-2990, 3771-3799,
+3966-4021) for the OpenMX basis tables (:345-526).
+
+Kernels: hgb_resblock_forward (HamLayer = ResidualBlock + o3.Linear, :38-58), hgb_ham_assemble
+(merge_tensor_components :851-891 + reorder_matrix :1056-1096 as one CSR product), hgb_ham_finalize
+(symmetrize :1231-1285, +H0 :3782-3795, orbital masks :2288-2365, per-crystal interleave :1187-1229).
+SOC (su2/so3), spin-constrained, band-energy and overlap heads are outside this round's scope and raise
+NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import lib as L
+from .hamgnn_conv import ResidualBlock, _W
+from .irreps import Irreps
+from .plan import HamAssembly, LinearOp
+
+
+def openmx_basis(nao_max: int):
+    """(index_change, row irreps, basis_def) of hamgnn_output.py:367-526."""
+    s1, s2, s3 = [0], [1], [2]
+    p1, p2 = [3, 4, 5], [6, 7, 8]
+    d1, d2 = [9, 10, 11, 12, 13], [14, 15, 16, 17, 18]
+    f1 = list(range(19, 26))
+    sp = s1 + s2 + p1
+    if nao_max in (14, 19):
+        base = {1: sp, 2: sp, 3: s1 + s2 + s3 + p1 + p2, 4: s1 + s2 + p1 + p2}
+        spd = s1 + s2 + p1 + p2 + d1
+        for Z in (5, 6, 7, 8, 9, 10, 13, 14, 15, 16, 17, 18):
+            base[Z] = spd
+        full14 = list(range(14))
+        for Z in (11, 12, 19, 20):
+            base[Z] = full14
+        if nao_max == 14:
+            for Z in (35, 23, 25):
+                base[Z] = full14
+            return [0, 1, 2, 5, 3, 4, 8, 6, 7, 11, 13, 9, 12, 10], Irreps("1x0e+1x0e+1x0e+1x1o+1x1o+1x2e"), base
+        full19 = list(range(19))
+        for Z in (25, 24, 28, 26, 23):
+            base[Z] = full14
+        for Z in (42, 83, 34, 53, 35, 77, 52, 51):
+            base[Z] = full19
+        return ([0, 1, 2, 5, 3, 4, 8, 6, 7, 11, 13, 9, 12, 10, 16, 18, 14, 17, 15],
+                Irreps("1x0e+1x0e+1x0e+1x1o+1x1o+1x2e+1x2e"), base)
+    if nao_max == 13:
+        full = list(range(13))
+        return ([0, 1, 4, 2, 3, 7, 5, 6, 10, 12, 8, 11, 9], Irreps("1x0e+1x0e+1x1o+1x1o+1x2e"),
+                {1: [0, 1, 2, 3, 4], 5: full, 6: full, 7: full, 8: full})
+    if nao_max == 26:
+        a = s1 + s2 + p1
+        b = s1 + s2 + s3 + p1 + p2
+        c = s1 + s2 + p1 + p2
+        d = c + d1
+        e = b + d1
+        f = b + d1 + d2
+        g = f + f1
+        base = {1: a, 2: a, 3: b, 4: c}
+        for Z in (5, 6, 7, 8, 9, 10, 13, 14, 15, 16, 17, 18):
+            base[Z] = d
+        for Z in (11, 12) + tuple(range(19, 31)):
+            base[Z] = e
+        for Z in tuple(range(31, 52)) + (54, 55, 56):
+            base[Z] = f
+        for Z in (52, 53, 57, 58, 59, 60, 61, 62, 66, 67, 71) + tuple(range(72, 84)):
+            base[Z] = g
+        return ([0, 1, 2, 5, 3, 4, 8, 6, 7, 11, 13, 9, 12, 10, 16, 18, 14, 17, 15, 22, 23, 21, 24, 20, 25, 19],
+                Irreps("1x0e+1x0e+1x0e+1x1o+1x1o+1x2e+1x2e+1x3o"), base)
+    raise NotImplementedError(f"NAO max '{nao_max}' not supported for 'openmx'.")
+
+
+class HamLayer(nn.Module):
+    """hamgnn_output.py:38-58."""
+
+    def __init__(self, irreps_in, irreps_out):
+        super().__init__()
+        self.residual_block = ResidualBlock(irreps_in, irreps_in)
+        self.op = LinearOp(irreps_in, irreps_out)
+        self.linear_transform = _W(self.op.weight_numel)
+
+    def forward_cuda(self, x):
+        return self.residual_block.forward_cuda(x, post=self.op, post_w=self.linear_transform.weight)
+
+
+class HamGNNPlusPlusOut(nn.Module):
+    def __init__(self, irreps_in_node=None, irreps_in_edge=None, nao_max: int = 14, return_forces: bool = False,
+                 create_graph: bool = False, ham_type: str = "openmx", ham_only: bool = False, symmetrize: bool = True,
+                 include_triplet: bool = False, calculate_band_energy: bool = False, num_k: int = 8, k_path=None,
+                 band_num_control=None, soc_switch: bool = True, nonlinearity_type: str = "gate",
+                 export_reciprocal_values: bool = False, add_H0: bool = False, soc_basis: str = "so3",
+                 spin_constrained: bool = False, use_learned_weight: bool = True, minMagneticMoment: float = 0.5,
+                 collinear_spin: bool = False, zero_point_shift: bool = False, add_H_nonsoc: bool = False,
+                 get_nonzero_mask_tensor: bool = False, calculate_sparsity: bool = True):
+        super().__init__()
+        self.derivative = return_forces
+        self.create_graph = create_graph
+        self.nao_max = nao_max
+        self.ham_type = ham_type.lower()
+        self.ham_only, self.symmetrize, self.add_H0 = ham_only, symmetrize, add_H0
+        self.soc_switch, self.spin_constrained, self.collinear_spin = soc_switch, spin_constrained, collinear_spin
+        self.zero_point_shift, self.calculate_sparsity = zero_point_shift, calculate_sparsity
+        self.calculate_band_energy = calculate_band_energy
+        if self.ham_type != "openmx":
+            if self.ham_type in ("siesta", "abacus", "pasp"):
+                raise NotImplementedError(f"ham_type '{ham_type}' basis tables are not part of this round's hot path")
+            raise NotImplementedError(f"Hamiltonian type '{self.ham_type}' is not supported.")
+        for flag, name in ((soc_switch, "soc_switch"), (spin_constrained, "spin_constrained"),
+                           (calculate_band_energy, "calculate_band_energy"), (return_forces, "return_forces"),
+                           (not ham_only, "ham_only=False"), (nonlinearity_type != "gate", "nonlinearity_type!='gate'"),
+                           (get_nonzero_mask_tensor, "get_nonzero_mask_tensor"),
+                           (export_reciprocal_values, "export_reciprocal_values")):
+            if flag:
+                raise NotImplementedError(f"HamGNN_out option {name} is outside the B200 hot path of this round "
+                                          "(SURVEY.md section 8f)")
+        idx, self.row, self.basis_def = openmx_basis(nao_max)
+        self.col = self.row
+        self.index_change = torch.tensor(idx, dtype=torch.long)
+        self.assembly = HamAssembly(self.row, self.col, idx, self.basis_def)
+        self.hamiltonian_irreps = self.assembly.hamiltonian_irreps
+        self.onsite_hamiltonian_network = HamLayer(Irreps(irreps_in_node), self.hamiltonian_irreps)
+        self.offsite_hamiltonian_network = HamLayer(Irreps(irreps_in_edge), self.hamiltonian_irreps)
+        self._tables: Dict[str, tuple] = {}
+
+    # ---------------------------------------------------------------------------------------------
+    def _lookup(self, device):
+        key = str(device)
+        if key not in self._tables:
+            n_orb = torch.full((256,), self.nao_max, dtype=torch.long)
+            defined = torch.zeros(256, dtype=torch.bool)
+            for Z, orbs in self.basis_def.items():
+                n_orb[Z] = len(orbs)
+                defined[Z] = True
+            self._tables[key] = (n_orb.to(device), defined.to(device))
+        return self._tables[key]
+
+    def validate_elements_in_basis_def(self, data):
+        zs = data["z"].unique().cpu().tolist()
+        missing = [z for z in zs if z not in self.basis_def]
+        if missing:
+            raise ValueError("The following elements are missing from basis_def: " + ", ".join(f"Z={m}" for m in missing))
+        return True
+
+    def calculate_sparsity_ratio(self, data):
+        """hamgnn_output.py:2784-2872."""
+        if "sparsity_ratio" in data:
+            c = data["sparsity_ratio"]
+            return c.to(device=data["z"].device, dtype=torch.float32) if torch.is_tensor(c) else \
+                torch.tensor(float(c), device=data["z"].device, dtype=torch.float32)
+        z = data["z"]
+        n_orb, defined = self._lookup(z.device)
+        nn2 = self.nao_max ** 2
+        total = z.new_zeros((), dtype=torch.long)
+        eff = z.new_zeros((), dtype=torch.long)
+        if "Hon" in data:
+            total = total + z.numel() * nn2
+            eff = eff + (n_orb[z] ** 2).sum()
+        if "Hoff" in data and "edge_index" in data:
+            src, dst = data["edge_index"][0], data["edge_index"][1]
+            total = total + src.numel() * nn2
+            both = defined[z[src]] & defined[z[dst]]
+            eff = eff + torch.where(both, n_orb[z[src]] * n_orb[z[dst]], torch.full_like(src, nn2)).sum()
+        t, e = total.double(), eff.double()
+        return torch.where(e > 0, t / e, torch.full_like(t, float("inf"))).float()
+
+    def _row_maps(self, data):
+        """Row of every on-site / off-site block in the per-crystal interleaved output
+        (concatenate_hamiltonians_by_crystal :1187-1229) and the batch-global inverse edge (:2985-2990)."""
+        src = data["edge_index"][0]
+        batch = data["batch"]
+        counts = data["node_counts"]
+        B = counts.shape[0]
+        eb = batch[src]
+        epc = torch.zeros(B, dtype=torch.long, device=src.device).index_add_(0, eb, torch.ones_like(src))
+        e_off = torch.cumsum(epc, 0) - epc
+        n_off = torch.cumsum(counts, 0) - counts
+        N, E = batch.shape[0], src.shape[0]
+        on_row = torch.arange(N, device=src.device) + e_off[batch]
+        off_row = torch.arange(E, device=src.device) + (n_off + counts)[eb]
+        inv = data["inv_edge_idx"] + e_off[eb]
+        return on_row, off_row, inv
+
+    def concatenate_hamiltonians_by_crystal(self, data, on, off):
+        on_row, off_row, _ = self._row_maps(data)
+        out = on.new_empty((on.shape[0] + off.shape[0],) + tuple(on.shape[1:]))
+        out[on_row] = on
+        out[off_row] = off
+        return out
+
+    def forward(self, data, graph_representation: dict = None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("hamgnn_b200.HamGNNPlusPlusOut is inference-only in this round: call it under torch.no_grad()")
+        self.validate_elements_in_basis_def(data)
+        if "hamiltonian" not in data and "Hon" in data:
+            data["hamiltonian"] = self.concatenate_hamiltonians_by_crystal(data, data["Hon"], data["Hoff"])
+        if "overlap" not in data and "Son" in data:
+            data["overlap"] = self.concatenate_hamiltonians_by_crystal(data, data["Son"], data["Soff"])
+        node_attr, edge_attr = graph_representation["node_attr"], graph_representation["edge_attr"]
+        L.require_cuda(node_attr, edge_attr)
+        dev = node_attr.device
+        src, dst = L.i64c(data["edge_index"][0]), L.i64c(data["edge_index"][1])
+        z = L.i64c(data["z"])
+        on_row, off_row, inv = self._row_maps(data)
+        N, E, nn2 = node_attr.shape[0], edge_attr.shape[0], self.nao_max ** 2
+        plan = self.assembly.plan(dev)
+        lib, st = L.load(), L.stream_ptr(dev)
+        H = torch.empty(N + E, nn2, device=dev, dtype=torch.float32)
+
+        coef_on = self.onsite_hamiltonian_network.forward_cuda(node_attr)
+        raw_on = torch.empty(N, nn2, device=dev, dtype=torch.float32)
+        L.check(lib.hgb_ham_assemble(C.byref(plan), coef_on.data_ptr(), N, raw_on.data_ptr(), st), "hgb_ham_assemble")
+        h0 = L.f32c(data["Hon0"]) if self.add_H0 else None
+        L.check(lib.hgb_ham_finalize(C.byref(plan), raw_on.data_ptr(), None, L.ptr(h0), z.data_ptr(), None, None,
+                                     on_row.data_ptr(), N, int(self.symmetrize), H.data_ptr(), st), "hgb_ham_finalize")
+
+        coef_off = self.offsite_hamiltonian_network.forward_cuda(edge_attr)
+        raw_off = torch.empty(E, nn2, device=dev, dtype=torch.float32)
+        L.check(lib.hgb_ham_assemble(C.byref(plan), coef_off.data_ptr(), E, raw_off.data_ptr(), st), "hgb_ham_assemble")
+        h0 = L.f32c(data["Hoff0"]) if self.add_H0 else None
+        L.check(lib.hgb_ham_finalize(C.byref(plan), raw_off.data_ptr(), inv.data_ptr(), L.ptr(h0), z.data_ptr(),
+                                     src.data_ptr(), dst.data_ptr(), off_row.data_ptr(), E, int(self.symmetrize),
+                                     H.data_ptr(), st), "hgb_ham_finalize")
+        if self.zero_point_shift:
+            S = data["overlap"]
+            sel = S > 1e-6
+            shift = ((H - data["hamiltonian"]) * sel).sum() / (S * sel).sum()
+            H = H - shift * S
+        result = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+        if self.calculate_sparsity:
+            result["sparsity_ratio"] = self.calculate_sparsity_ratio(data)
+        return result

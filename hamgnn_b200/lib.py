@@ -1,0 +1,132 @@
+"""ctypes binding of libhamgnn_b200.so -- the C ABI declared in include/hamgnn_b200.h.
+
+There is no CPU fallback: if the library is missing (or cannot be loaded) every op raises.
+`HGB_LIB` overrides the library path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("HGB_LIB", os.path.join(_HERE, "libhamgnn_b200.so"))
+
+EXPORTS = ["hgb_abi_version", "hgb_last_error", "hgb_launch_count", "hgb_edge_embed", "hgb_msgpack_forward",
+           "hgb_linear_forward", "hgb_resblock_forward", "hgb_ham_assemble", "hgb_ham_finalize"]
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class TypeT(C.Structure):
+    _fields_ = [("mul", i32), ("mpad", i32), ("l", i32), ("out_off", i32), ("path_begin", i32), ("path_end", i32),
+                ("pad0", i32), ("pad1", i32)]
+
+
+class PathT(C.Structure):
+    _fields_ = [("kind", i32), ("branch", i32), ("src0", i32), ("nsrc", i32), ("in_off", i32), ("mul_in", i32),
+                ("l1", i32), ("l2", i32), ("l3", i32), ("sh_off", i32), ("cg_off", i32), ("cg_kstart", i32),
+                ("w_off", i32), ("w3_off", i32), ("lf_off", i32), ("pad0", i32)]
+
+
+class MsgpackPlan(C.Structure):
+    _fields_ = [("n_types", i32), ("n_paths", i32), ("n_branches", i32), ("n_sources", i32),
+                ("sh_dim", i32), ("rbf_dim", i32), ("h1", i32), ("h2", i32), ("out_dim", i32),
+                ("src_dim", i32 * 4), ("fc1_off", i32 * 2), ("fc2_off", i32 * 2), ("act_const", f32),
+                ("types", vp), ("paths", vp), ("types_host", vp), ("paths_host", vp),
+                ("cg_ij", vp), ("cg_val", vp), ("cg_kstart", vp), ("wbuf", vp)]
+
+
+class LinBlockT(C.Structure):
+    _fields_ = [("in_off", i32), ("out_off", i32), ("mul_in", i32), ("mul_out", i32), ("dim", i32), ("w_off", i32)]
+
+
+class LinearPlan(C.Structure):
+    _fields_ = [("n_blocks", i32), ("in_dim", i32), ("out_dim", i32), ("pad", i32), ("blocks", vp), ("w", vp)]
+
+
+class GateDesc(C.Structure):
+    _fields_ = [("n_scalar_slots", i32), ("sc_in_off", i32 * 4), ("sc_out_off", i32 * 4), ("sc_n", i32 * 4),
+                ("sc_act", i32 * 4), ("n_gated", i32), ("gd_in_off", i32 * 16), ("gd_out_off", i32 * 16),
+                ("gd_mul", i32 * 16), ("gd_dim", i32 * 16), ("gd_gate_off", i32 * 16), ("c_ssp", f32), ("c_tanh", f32),
+                ("in_dim", i32), ("out_dim", i32)]
+
+
+class HamPlan(C.Structure):
+    _fields_ = [("nao", i32), ("n_coef", i32), ("nnz", i32), ("pad", i32), ("row_ptr", vp), ("col", vp), ("val", vp),
+                ("orb_mask", vp)]
+
+
+class HgbError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it is absent: the CUDA path is the only path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HgbError(f"{LIB_PATH} not found: build it with `python -m hamgnn_b200.build` "
+                       "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise HgbError(f"{LIB_PATH} does not export {name}")
+    lib.hgb_abi_version.restype = C.c_int
+    lib.hgb_last_error.restype = C.c_char_p
+    lib.hgb_launch_count.restype = i64
+    lib.hgb_edge_embed.argtypes = [vp, vp, vp, i64, C.POINTER(i32), i32, f32, C.POINTER(f32), i32, vp, vp, vp, vp, vp]
+    lib.hgb_msgpack_forward.argtypes = [C.POINTER(MsgpackPlan), C.POINTER(vp), C.POINTER(vp), vp, vp, i64, vp, vp, vp]
+    lib.hgb_linear_forward.argtypes = [C.POINTER(LinearPlan), vp, vp, i64, vp, i32, vp]
+    lib.hgb_resblock_forward.argtypes = [C.POINTER(LinearPlan), C.POINTER(GateDesc), C.POINTER(LinearPlan),
+                                         C.POINTER(LinearPlan), vp, vp, i64, vp, vp]
+    lib.hgb_ham_assemble.argtypes = [C.POINTER(HamPlan), vp, i64, vp, vp]
+    lib.hgb_ham_finalize.argtypes = [C.POINTER(HamPlan), vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp]
+    for name in EXPORTS[3:]:
+        getattr(lib, name).restype = C.c_int
+    if lib.hgb_abi_version() != 1:
+        raise HgbError(f"ABI version mismatch: library {lib.hgb_abi_version()} != binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise HgbError(f"{what}: {load().hgb_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().hgb_launch_count())
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise HgbError("hamgnn_b200 ops need CUDA tensors: the B200 kernels are the only implementation "
+                           "(no CPU fallback)")
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise HgbError(f"expected float32 tensor, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def i64c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        raise HgbError(f"expected int64 tensor, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()

@@ -1,0 +1,556 @@
+"""Host-side planners: turn irreps + e3nn-layout parameters into the constant tables and packed weight
+buffers that the kernels of libhamgnn_b200.so consume (include/hamgnn_b200.h).
+
+The instruction tables reproduce the reference's builders line for line in *behaviour*:
+  * `tp_paths`        <- MessagePackBlock._tp_out_irreps_with_instructions
+                         (/root/reference/hamgnn/nn/message_passing.py:136-171; identical copy at
+                         hamgnn/nn/tensor_products.py:116-149): 'uvw' paths, output slots sorted with
+                         e3nn's Irreps.sort(), instructions re-sorted by output slot.
+  * `linear_blocks`   <- e3nn o3.Linear instruction order
+  * `gate_layout`     <- irreps2gate (hamgnn/utils/irreps_utils.py:33-65) + e3nn Gate's sorted input row
+Flat weight layouts are e3nn's, so reference state_dicts load unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import so3
+from .irreps import Ir, Irreps, MulIr
+
+
+# ====================================================================================== TP paths
+@dataclass
+class TPPath:
+    i_in: int          # slot in the (combined) input irreps
+    i_sh: int          # slot in irreps_sh
+    ir_in: Ir
+    l2: int
+    ir_out: Ir
+    mul_in_total: int  # K (combined multiplicity)
+    mul_out: int
+    w_off: int         # offset in the flat TensorProduct.weight
+    ch_off: int        # first mid channel (== radial gate column)
+
+
+def tp_paths(irreps_in: Irreps, irreps_sh: Irreps, target: Irreps) -> Tuple[Irreps, List[TPPath]]:
+    """'uvw' instruction list in the reference's final (sorted) order, plus the sorted mid irreps."""
+    raw = []
+    out_list = []
+    for i, (mul_in, ir_in) in enumerate(irreps_in):
+        for j, (_, ir_sh) in enumerate(irreps_sh):
+            for (mul_out, ir_out) in target:
+                if ir_out in ir_in.product(ir_sh):
+                    raw.append((i, j, len(out_list)))
+                    out_list.append(MulIr(mul_out, ir_out))
+    mid, perm, _ = Irreps(out_list).sort()
+    instr = sorted(((i, j, perm[k]) for i, j, k in raw), key=lambda x: x[2])
+    paths, w_off, ch = [], 0, 0
+    for i, j, k in instr:
+        mul_out, ir_out = mid[k]
+        K = irreps_in[i].mul
+        paths.append(TPPath(i, j, irreps_in[i].ir, irreps_sh[j].ir.l, ir_out, K, mul_out, w_off, ch))
+        w_off += K * mul_out
+        ch += mul_out
+    return mid, paths
+
+
+# ====================================================================================== Linear
+@dataclass
+class LinBlock:
+    in_off: int
+    out_off: int
+    mul_in: int
+    mul_out: int
+    dim: int
+    w_off: int
+    scale: float
+    i_in: int
+    i_out: int
+
+
+def linear_blocks(irreps_in: Irreps, irreps_out: Irreps) -> Tuple[List[LinBlock], int]:
+    offs_in, offs_out = irreps_in.offsets(), irreps_out.offsets()
+    pairs = [(i, o) for i, (_, ii) in enumerate(irreps_in) for o, (_, io) in enumerate(irreps_out) if ii == io]
+    fan = {}
+    for i, o in pairs:
+        fan[o] = fan.get(o, 0) + irreps_in[i].mul
+    blocks, w = [], 0
+    for i, o in pairs:
+        mi, mo = irreps_in[i].mul, irreps_out[o].mul
+        blocks.append(LinBlock(offs_in[i], offs_out[o], mi, mo, irreps_in[i].ir.dim, w, 1.0 / math.sqrt(fan[o]), i, o))
+        w += mi * mo
+    return blocks, w
+
+
+class DeviceTables:
+    """Keeps ctypes structs, their host arrays and the device tensors they point to alive together."""
+
+    def __init__(self):
+        self.keep = []
+
+    def dev(self, arr: np.ndarray, device) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        self.keep.append(t)
+        return t
+
+
+class LinearOp:
+    """One o3.Linear evaluated by hgb_linear_forward / as a stage of hgb_resblock_forward."""
+
+    def __init__(self, irreps_in, irreps_out):
+        self.irreps_in, self.irreps_out = Irreps(irreps_in), Irreps(irreps_out)
+        self.blocks, self.weight_numel = linear_blocks(self.irreps_in, self.irreps_out)
+        sc = np.zeros(self.weight_numel, dtype=np.float32)
+        for b in self.blocks:
+            sc[b.w_off:b.w_off + b.mul_in * b.mul_out] = b.scale
+        self._scale_np = sc
+        self._dev: Dict[str, tuple] = {}
+
+    def plan(self, weight: torch.Tensor) -> L.LinearPlan:
+        """Device plan for the given flat parameter (cached per device and parameter version)."""
+        dev = weight.device
+        key = str(dev)
+        ent = self._dev.get(key)
+        if ent is None:
+            arr = (L.LinBlockT * max(1, len(self.blocks)))()
+            for q, b in enumerate(self.blocks):
+                arr[q] = L.LinBlockT(b.in_off, b.out_off, b.mul_in, b.mul_out, b.dim, b.w_off)
+            raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+            d_blocks = torch.from_numpy(raw).to(dev)
+            scale = torch.from_numpy(self._scale_np).to(dev)
+            ent = {"blocks": d_blocks, "scale": scale, "ver": None, "w": None, "plan": None}
+            self._dev[key] = ent
+        ver = (weight._version, weight.data_ptr())
+        if ent["ver"] != ver:
+            ent["w"] = (weight.detach() * ent["scale"]).contiguous()
+            ent["ver"] = ver
+            ent["plan"] = L.LinearPlan(len(self.blocks), self.irreps_in.dim, self.irreps_out.dim, 0,
+                                       ent["blocks"].data_ptr(), ent["w"].data_ptr())
+        return ent["plan"]
+
+
+def linear_forward(op: LinearOp, weight: torch.Tensor, x: torch.Tensor, rows: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None, accumulate: bool = False, n_rows: Optional[int] = None):
+    L.require_cuda(x, weight)
+    x = L.f32c(x)
+    n = int(n_rows if n_rows is not None else (rows.shape[0] if rows is not None else x.shape[0]))
+    if out is None:
+        out = torch.empty(n, op.irreps_out.dim, device=x.device, dtype=torch.float32)
+        accumulate = False
+    plan = op.plan(weight)
+    rc = L.load().hgb_linear_forward(C.byref(plan), x.data_ptr(), L.ptr(rows), n, out.data_ptr(), int(accumulate),
+                                     L.stream_ptr(x.device))
+    L.check(rc, "hgb_linear_forward")
+    return out
+
+
+# ====================================================================================== Gate / ResidualBlock
+def irreps2gate(irreps: Irreps):
+    """hamgnn/utils/irreps_utils.py:33-65."""
+    scal = Irreps([m for m in irreps if m.ir.l == 0]).simplify()
+    gated = Irreps([m for m in irreps if m.ir.l != 0]).simplify()
+    gates = Irreps([MulIr(m.mul, Ir(0, 1)) for m in gated]).simplify() if gated.dim > 0 else Irreps()
+    return scal, gates, gated
+
+
+class GateLayout:
+    """e3nn Gate(irreps_scalars, [ssp|tanh], irreps_gates, [ssp], irreps_gated): input row is the sorted +
+    simplified concatenation (e3nn `_Sortcut`), output row is scalars + gated."""
+
+    def __init__(self, hidden: Irreps):
+        scal, gates, gated = irreps2gate(Irreps(hidden))
+        if len(gates) > 1 or any(g.ir != Ir(0, 1) for g in gates):
+            raise NotImplementedError("only even scalar gates are supported")
+        if len(scal) > 4 or len(gated) > 16:
+            raise NotImplementedError("too many gate slots")
+        cat = scal + gates + gated
+        sorted_irreps, perm, _ = cat.sort()
+        self.irreps_in = sorted_irreps.simplify()
+        self.irreps_out = scal + gated
+        in_offs = sorted_irreps.offsets()
+        out_offs = self.irreps_out.offsets()
+        d = L.GateDesc()
+        d.n_scalar_slots = len(scal)
+        for q, m in enumerate(scal):
+            d.sc_in_off[q] = in_offs[perm[q]]
+            d.sc_out_off[q] = out_offs[q]
+            d.sc_n[q] = m.mul
+            d.sc_act[q] = 0 if m.ir.p == 1 else 1
+        ns, ng = len(scal), len(gates)
+        gate_col = in_offs[perm[ns]] if ng else 0
+        d.n_gated = len(gated)
+        gch = 0
+        for q, m in enumerate(gated):
+            d.gd_in_off[q] = in_offs[perm[ns + ng + q]]
+            d.gd_out_off[q] = out_offs[ns + q]
+            d.gd_mul[q] = m.mul
+            d.gd_dim[q] = m.ir.dim
+            d.gd_gate_off[q] = gate_col + gch
+            gch += m.mul
+        d.c_ssp = so3.normalize2mom_const("ssp")
+        d.c_tanh = so3.normalize2mom_const("tanh")
+        d.in_dim = self.irreps_in.dim
+        d.out_dim = self.irreps_out.dim
+        self.desc = d
+
+
+# ====================================================================================== MessagePack
+@dataclass
+class Branch:
+    """One tensor-product branch of a MessagePackBlock: `nsrc` input sources sharing `irreps_in`
+    (nsrc == 2 is the fused (src|dst) node input), its own radial MLP and its own Linear pair."""
+    irreps_in: Irreps
+    nsrc: int
+    src0: int
+    has_out_linear: bool = True
+
+
+_CG_CACHE: Dict[Tuple[int, int, int], Tuple[np.ndarray, np.ndarray, np.ndarray]] = {}
+
+
+def _cg_table(l1, l2, l3):
+    key = (l1, l2, l3)
+    if key not in _CG_CACHE:
+        i, j, k, v = so3.cg_nnz(l1, l2, l3)
+        kstart = np.zeros(2 * l3 + 2, dtype=np.int32)
+        for kk in range(2 * l3 + 1):
+            kstart[kk + 1] = kstart[kk] + int((k == kk).sum())
+        _CG_CACHE[key] = ((i | (j << 8)).astype(np.int32), v.astype(np.float32), kstart)
+    return _CG_CACHE[key]
+
+
+class MessagePackOp:
+    """Static structure of one fused message kernel call (hgb_msgpack_forward).
+
+    weights per branch b (e3nn layouts):
+        tp[b]      flat TensorProduct.weight
+        fc[b]      [layer0 (R,h1), layer1 (h1,h2), layer2 (h2, n_channels)]
+        lin_mid[b] flat weight of Linear(mid.simplify() -> irreps_out)
+        lin_out[b] flat weight of Linear(irreps_out -> irreps_out) or None
+    direct (optional): (source index, flat weight of Linear(irreps_out -> irreps_out)) added un-gated
+    (PairInteractionBlock's skip_linear on the edge features).
+    """
+
+    def __init__(self, branches: Sequence[Branch], irreps_sh, irreps_out, rbf_dim: int, radial_mlp: Sequence[int],
+                 src_dims: Sequence[int], direct_src: Optional[int] = None):
+        self.branches = list(branches)
+        self.irreps_sh = Irreps(irreps_sh)
+        self.irreps_out = Irreps(irreps_out)
+        if len({m.ir for m in self.irreps_out}) != len(self.irreps_out):
+            raise NotImplementedError("irreps_out with repeated irreps is not supported by the fused kernel")
+        if any(m.mul != 1 for m in self.irreps_sh):
+            raise NotImplementedError("irreps_edge_sh must have multiplicity 1 per irrep")
+        if len(radial_mlp) != 2:
+            raise NotImplementedError("radial_MLP must have exactly two hidden layers (reference default [64, 64])")
+        self.rbf_dim, self.h1, self.h2 = int(rbf_dim), int(radial_mlp[0]), int(radial_mlp[1])
+        self.src_dims = list(src_dims)
+        self.direct_src = direct_src
+        sh_offs = self.irreps_sh.offsets()
+        out_offs = self.irreps_out.offsets()
+        slot_of = {m.ir: t for t, m in enumerate(self.irreps_out)}
+
+        self.mid: List[Irreps] = []
+        self.paths_by_branch: List[List[TPPath]] = []
+        self.lin_mid_blocks = []
+        self.lin_out_blocks = []
+        for br in self.branches:
+            comb = br.irreps_in.scaled(br.nsrc) if br.nsrc > 1 else br.irreps_in
+            mid, paths = tp_paths(comb, self.irreps_sh, self.irreps_out)
+            self.mid.append(mid)
+            self.paths_by_branch.append(paths)
+            self.lin_mid_blocks.append(linear_blocks(mid.simplify(), self.irreps_out))
+            self.lin_out_blocks.append(linear_blocks(self.irreps_out, self.irreps_out))
+        self.direct_blocks = linear_blocks(self.irreps_out, self.irreps_out) if direct_src is not None else None
+
+        # ---- per-type path lists and packed-weight offsets
+        wcur = 0
+        self.fc1_off, self.fc2_off = [], []
+        for _ in self.branches:
+            self.fc1_off.append(wcur); wcur += self.rbf_dim * self.h1
+            self.fc2_off.append(wcur); wcur += self.h1 * self.h2
+        cg_ij, cg_val, cg_ks = [], [], []
+        cg_index: Dict[Tuple[int, int, int], Tuple[int, int]] = {}
+
+        def cg_offsets(l1, l2, l3):
+            key = (l1, l2, l3)
+            if key not in cg_index:
+                ij, v, ks = _cg_table(l1, l2, l3)
+                cg_index[key] = (sum(len(a) for a in cg_ij), sum(len(a) for a in cg_ks))
+                cg_ij.append(ij); cg_val.append(v); cg_ks.append(ks)
+            return cg_index[key]
+
+        types = (L.TypeT * len(self.irreps_out))()
+        plist: List[L.PathT] = []
+        self.pack_items = []   # (kind, branch, path/blk info ...) consumed by pack()
+        in_offs_by_branch = [br.irreps_in.offsets() for br in self.branches]
+        for t, m in enumerate(self.irreps_out):
+            mpad = (m.mul + 3) // 4 * 4
+            begin = len(plist)
+            for b, br in enumerate(self.branches):
+                tpaths = [p for p in self.paths_by_branch[b] if p.ir_out == m.ir]
+                ch_type0 = tpaths[0].ch_off if tpaths else 0
+                for p in tpaths:
+                    K = p.mul_in_total
+                    mul_in = K // br.nsrc
+                    co, ks = cg_offsets(p.ir_in.l, p.l2, p.ir_out.l)
+                    pt = L.PathT(0, b, br.src0, br.nsrc, in_offs_by_branch[b][p.i_in], mul_in, p.ir_in.l, p.l2, p.ir_out.l,
+                                 sh_offs[p.i_sh], co, ks, wcur, wcur + K * mpad, wcur + K * mpad + self.h2 * mpad, 0)
+                    self.pack_items.append(("tp", b, p, t, mpad, wcur, p.ch_off - ch_type0))
+                    wcur += K * mpad + self.h2 * mpad + mpad * mpad
+                    plist.append(pt)
+            if direct_src is not None:
+                d1 = m.ir.dim
+                pt = L.PathT(1, 0, direct_src, 1, out_offs[t], m.mul, m.ir.l, 0, m.ir.l, 0, 0, 0, 0, 0, wcur, 0)
+                self.pack_items.append(("direct", t, mpad, wcur))
+                wcur += m.mul * mpad
+                plist.append(pt)
+            types[t] = L.TypeT(m.mul, mpad, m.ir.l, out_offs[t], begin, len(plist), 0, 0)
+        self.w_total = wcur
+        self.types_c = types
+        self.paths_c = (L.PathT * max(1, len(plist)))(*plist)
+        self.n_paths = len(plist)
+        self.cg_ij = np.concatenate(cg_ij) if cg_ij else np.zeros(1, np.int32)
+        self.cg_val = np.concatenate(cg_val) if cg_val else np.zeros(1, np.float32)
+        self.cg_ks = np.concatenate(cg_ks) if cg_ks else np.zeros(2, np.int32)
+        self.n_channels = [mid.num_irreps for mid in self.mid]
+        self.tp_numel = [sum(p.mul_in_total * p.mul_out for p in ps) for ps in self.paths_by_branch]
+        self._build_pack_program()
+        self._dev: Dict[str, dict] = {}
+
+    # -------------------------------------------------------------------------------- packing program
+    def _build_pack_program(self):
+        """Index program so that  wbuf[dst] = cat(sources)[src] * scale  packs everything in one gather.
+
+        sources (concatenated flat): per branch [tp, fc0, fc1, fc2, F] then direct weight; F = per-type folded
+        (Lmid_t / sqrt(fan_mid)) @ (Lout_t / sqrt(fan_out)) laid out [P_t*M, M] in out-slot order."""
+        dst, src, scale = [], [], []
+        self.src_layout = []  # (name, branch, numel)
+        cur = 0
+        base = {}
+        self.f_slices = {}
+        for b, br in enumerate(self.branches):
+            nchan = self.n_channels[b]
+            for name, n in (("tp", self.tp_numel[b]), ("fc0", self.rbf_dim * self.h1), ("fc1", self.h1 * self.h2),
+                            ("fc2", self.h2 * nchan)):
+                base[(name, b)] = cur
+                self.src_layout.append((name, b, n))
+                cur += n
+            # folded F: one [rows_t, M] block per out slot that has paths
+            fsz = 0
+            for t, m in enumerate(self.irreps_out):
+                rows = sum(p.mul_out for p in self.paths_by_branch[b] if p.ir_out == m.ir)
+                self.f_slices[(b, t)] = (fsz, rows, m.mul)
+                fsz += rows * m.mul
+            base[("F", b)] = cur
+            self.src_layout.append(("F", b, fsz))
+            cur += fsz
+        if self.direct_src is not None:
+            base[("direct", 0)] = cur
+            self.src_layout.append(("direct", 0, self.direct_blocks[1]))
+            cur += self.direct_blocks[1]
+        self.src_total = cur
+
+        def add(d, s, sc):
+            dst.append(np.asarray(d, dtype=np.int64).ravel())
+            src.append(np.asarray(s, dtype=np.int64).ravel())
+            scale.append(np.broadcast_to(np.asarray(sc, dtype=np.float32), dst[-1].shape).ravel())
+
+        for b in range(len(self.branches)):
+            n1, n2 = self.rbf_dim * self.h1, self.h1 * self.h2
+            add(self.fc1_off[b] + np.arange(n1), base[("fc0", b)] + np.arange(n1), 1.0 / math.sqrt(self.rbf_dim))
+            add(self.fc2_off[b] + np.arange(n2), base[("fc1", b)] + np.arange(n2), 1.0 / math.sqrt(self.h1))
+        for item in self.pack_items:
+            if item[0] == "tp":
+                _, b, p, t, mpad, w0, row_in_type = item
+                K, M = p.mul_in_total, p.mul_out
+                u, w = np.meshgrid(np.arange(K), np.arange(M), indexing="ij")
+                coef = math.sqrt(p.ir_out.dim / K)
+                add(w0 + u * mpad + w, base[("tp", b)] + p.w_off + u * M + w, coef)
+                h, w = np.meshgrid(np.arange(self.h2), np.arange(M), indexing="ij")
+                add(w0 + K * mpad + h * mpad + w, base[("fc2", b)] + h * self.n_channels[b] + p.ch_off + w,
+                    1.0 / math.sqrt(self.h2))
+                f0, rows, Mt = self.f_slices[(b, t)]
+                r, c = np.meshgrid(np.arange(M), np.arange(Mt), indexing="ij")
+                add(w0 + K * mpad + self.h2 * mpad + r * mpad + c, base[("F", b)] + f0 + (row_in_type + r) * Mt + c, 1.0)
+            else:
+                _, t, mpad, w0 = item
+                blk = [x for x in self.direct_blocks[0] if x.i_out == t]
+                assert len(blk) == 1
+                bl = blk[0]
+                u, w = np.meshgrid(np.arange(bl.mul_in), np.arange(bl.mul_out), indexing="ij")
+                add(w0 + u * mpad + w, base[("direct", 0)] + bl.w_off + u * bl.mul_out + w, bl.scale)
+        self._dst = np.concatenate(dst)
+        self._src = np.concatenate(src)
+        self._scale = np.concatenate(scale)
+
+    # -------------------------------------------------------------------------------- device side
+    def _device_state(self, device) -> dict:
+        key = str(device)
+        st = self._dev.get(key)
+        if st is None:
+            st = {}
+            st["types"] = torch.from_numpy(np.frombuffer(bytes(self.types_c), dtype=np.uint8).copy()).to(device)
+            st["paths"] = torch.from_numpy(np.frombuffer(bytes(self.paths_c), dtype=np.uint8).copy()).to(device)
+            st["cg_ij"] = torch.from_numpy(self.cg_ij).to(device)
+            st["cg_val"] = torch.from_numpy(self.cg_val).to(device)
+            st["cg_ks"] = torch.from_numpy(self.cg_ks).to(device)
+            st["dst"] = torch.from_numpy(self._dst).to(device)
+            st["src"] = torch.from_numpy(self._src).to(device)
+            st["scale"] = torch.from_numpy(self._scale).to(device)
+            st["ver"] = None
+            self._dev[key] = st
+        return st
+
+    def _fold(self, b: int, lin_mid: torch.Tensor, lin_out: Optional[torch.Tensor]) -> torch.Tensor:
+        """F_t = (Lmid_t / sqrt(fan_mid)) @ (Lout_t / sqrt(fan_out)) for every out slot (weights-only prep)."""
+        blocks_mid, _ = self.lin_mid_blocks[b]
+        blocks_out, _ = self.lin_out_blocks[b]
+        outs = []
+        for t, m in enumerate(self.irreps_out):
+            f0, rows, M = self.f_slices[(b, t)]
+            if rows == 0:
+                continue
+            bm = [x for x in blocks_mid if x.i_out == t]
+            assert len(bm) == 1 and bm[0].mul_in == rows
+            Wm = lin_mid[bm[0].w_off:bm[0].w_off + rows * M].view(rows, M) * bm[0].scale
+            if lin_out is not None:
+                bo = [x for x in blocks_out if x.i_out == t][0]
+                Wo = lin_out[bo.w_off:bo.w_off + M * M].view(M, M) * bo.scale
+                Wm = Wm @ Wo
+            outs.append(Wm.reshape(-1))
+        return torch.cat(outs) if outs else lin_mid.new_zeros(0)
+
+    def pack(self, weights: dict) -> Tuple[dict, torch.Tensor]:
+        """weights: {'tp': [..], 'fc': [[w0,w1,w2],..], 'lin_mid': [..], 'lin_out': [..|None], 'direct': w|None}"""
+        dev = weights["tp"][0].device
+        st = self._device_state(dev)
+        allp = [*weights["tp"], *[w for fc in weights["fc"] for w in fc], *weights["lin_mid"],
+                *[w for w in weights["lin_out"] if w is not None]]
+        if weights.get("direct") is not None:
+            allp.append(weights["direct"])
+        ver = tuple((p._version, p.data_ptr()) for p in allp)
+        if st["ver"] != ver:
+            with torch.no_grad():
+                parts = []
+                for b in range(len(self.branches)):
+                    parts += [weights["tp"][b].reshape(-1), weights["fc"][b][0].reshape(-1), weights["fc"][b][1].reshape(-1),
+                              weights["fc"][b][2].reshape(-1), self._fold(b, weights["lin_mid"][b], weights["lin_out"][b])]
+                if self.direct_src is not None:
+                    parts.append(weights["direct"].reshape(-1))
+                cat = torch.cat(parts).float()
+                assert cat.numel() == self.src_total, (cat.numel(), self.src_total)
+                wbuf = torch.zeros(self.w_total, device=dev, dtype=torch.float32)
+                wbuf.index_copy_(0, st["dst"], cat[st["src"]] * st["scale"])
+            st["wbuf"] = wbuf
+            st["ver"] = ver
+            plan = L.MsgpackPlan()
+            plan.n_types, plan.n_paths = len(self.irreps_out), self.n_paths
+            plan.n_branches, plan.n_sources = len(self.branches), len(self.src_dims)
+            plan.sh_dim, plan.rbf_dim, plan.h1, plan.h2 = self.irreps_sh.dim, self.rbf_dim, self.h1, self.h2
+            plan.out_dim = self.irreps_out.dim
+            for q, d in enumerate(self.src_dims):
+                plan.src_dim[q] = d
+            for b in range(len(self.branches)):
+                plan.fc1_off[b] = self.fc1_off[b]
+                plan.fc2_off[b] = self.fc2_off[b]
+            plan.act_const = so3.normalize2mom_const("silu")
+            plan.types, plan.paths = st["types"].data_ptr(), st["paths"].data_ptr()
+            plan.types_host = C.cast(self.types_c, C.c_void_p).value
+            plan.paths_host = C.cast(self.paths_c, C.c_void_p).value
+            plan.cg_ij, plan.cg_val, plan.cg_kstart = st["cg_ij"].data_ptr(), st["cg_val"].data_ptr(), st["cg_ks"].data_ptr()
+            plan.wbuf = wbuf.data_ptr()
+            st["plan"] = plan
+        return st, st["wbuf"]
+
+    def forward(self, weights: dict, sources: Sequence[torch.Tensor], rows: Sequence[Optional[torch.Tensor]],
+                sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
+                out_index: Optional[torch.Tensor] = None):
+        L.require_cuda(sh, rbf, out, *sources)
+        st, _ = self.pack(weights)
+        ns = len(self.src_dims)
+        assert len(sources) == ns and len(rows) == ns
+        srcs = (C.c_void_p * 4)(*[L.f32c(s).data_ptr() for s in sources] + [None] * (4 - ns))
+        rws = (C.c_void_p * 4)(*[L.ptr(r) for r in rows] + [None] * (4 - ns))
+        for s, d in zip(sources, self.src_dims):
+            assert s.shape[-1] == d and s.is_contiguous(), (s.shape, d)
+        rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
+                                          int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
+        L.check(rc, "hgb_msgpack_forward")
+        return out
+
+    # FLOP / byte accounting for bench.py (per edge, algorithmic minimum of this formulation)
+    def flops_per_edge(self) -> int:
+        fl = 0
+        for b, br in enumerate(self.branches):
+            fl += 2 * (self.rbf_dim * self.h1 + self.h1 * self.h2 + self.h2 * self.n_channels[b])
+            for p in self.paths_by_branch[b]:
+                d1, d3, K, M = p.ir_in.dim, p.ir_out.dim, p.mul_in_total, p.mul_out
+                nnz = len(_cg_table(p.ir_in.l, p.l2, p.ir_out.l)[0])
+                fl += 2 * K * min(nnz, d1 * d3) + 2 * K * M * d3 + M * d3 + 2 * M * M * d3
+        if self.direct_src is not None:
+            fl += sum(2 * m.mul * m.mul * m.ir.dim for m in self.irreps_out)
+        return fl
+
+
+# ====================================================================================== Hamiltonian assembly
+class HamAssembly:
+    """CSR form of merge_tensor_components + reorder_matrix (hamgnn_output.py:851-891, 1056-1096)."""
+
+    def __init__(self, row: Irreps, col: Irreps, index_change: Sequence[int], basis_def: Dict[int, Sequence[int]],
+                 minus_index: Optional[Sequence[int]] = None):
+        nao = row.dim
+        assert col.dim == nao
+        self.nao = nao
+        dense = {}
+        coef_off, k, r0 = 0, 0, 0
+        irs = []
+        for _, li in row:
+            c0 = 0
+            for _, lj in col:
+                for Lq in range(abs(li.l - lj.l), li.l + lj.l + 1):
+                    irs.append(MulIr(1, Ir(Lq, (-1) ** (li.l + lj.l))))
+                    w = math.sqrt(2 * Lq + 1) * so3.wigner_3j(li.l, lj.l, Lq)
+                    ii, jj, mm = np.nonzero(w)
+                    for a, b_, m in zip(ii, jj, mm):
+                        dense.setdefault((r0 + a, c0 + b_), []).append((coef_off + m, w[a, b_, m]))
+                    coef_off += 2 * Lq + 1
+                    k += 1
+                c0 += lj.dim
+            r0 += li.dim
+        self.hamiltonian_irreps = Irreps(irs)
+        self.n_coef = coef_off
+        idx = list(index_change) if index_change is not None else list(range(nao))
+        sign = np.ones(nao)
+        if minus_index is not None:
+            sign[list(minus_index)] = -1
+        row_ptr, colv, valv = [0], [], []
+        for a in range(nao):
+            for b_ in range(nao):
+                for c, v in dense.get((idx[a], idx[b_]), []):
+                    colv.append(c)
+                    valv.append(v * sign[a] * sign[b_])
+                row_ptr.append(len(colv))
+        self.row_ptr = np.asarray(row_ptr, dtype=np.int32)
+        self.col = np.asarray(colv, dtype=np.int32)
+        self.val = np.asarray(valv, dtype=np.float32)
+        mask = np.zeros((128, nao), dtype=np.uint8)
+        for Z, orbs in basis_def.items():
+            mask[int(Z), list(orbs)] = 1
+        self.mask = mask
+        self._dev = {}
+
+    def plan(self, device) -> L.HamPlan:
+        key = str(device)
+        if key not in self._dev:
+            t = {k: torch.from_numpy(getattr(self, k)).to(device) for k in ("row_ptr", "col", "val", "mask")}
+            p = L.HamPlan(self.nao, self.n_coef, len(self.col), 0, t["row_ptr"].data_ptr(), t["col"].data_ptr(),
+                          t["val"].data_ptr(), t["mask"].data_ptr())
+            self._dev[key] = (p, t)
+        return self._dev[key][0]

@@ -1,0 +1,173 @@
+/* hamgnn_b200.h -- C ABI of the B200-native HamGNN hot path (libhamgnn_b200.so).
+ *
+ * The reference (QuantumLab-ZY/HamGNN) has no FFI: its hot path is Python calling e3nn / torch_scatter.
+ * Each entry point below replaces the arithmetic of the cited reference function(s); a maintainer binds
+ * them with ctypes from inside the two nn.Modules `HamGNNConvE3` / `HamGNNPlusPlusOut`.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; row-major, contiguous;
+ *     float = fp32, indices int64 (edge_index, inv_edge_idx, z) exactly as the reference's Data fields.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 on success, non-zero on failure; hgb_last_error() gives the message
+ *     (thread-local).  No entry point synchronises the stream.
+ *   - plans (`hgb_*_plan`) are plain structs of device pointers to constant tables built by the host
+ *     (irreps instruction tables, sparse Clebsch-Gordan lists, packed weights); the library never
+ *     allocates or frees device memory.
+ */
+#ifndef HAMGNN_B200_H
+#define HAMGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGB_ABI_VERSION 1
+#define HGB_MAX_L 8
+
+int hgb_abi_version(void);
+const char* hgb_last_error(void);
+/* number of kernels launched by this library in the calling process (for bench.py's gpu_launches) */
+int64_t hgb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1+a2: edge geometry, spherical harmonics, Bessel x cosine-cutoff radial embedding.
+ * Replaces SphericalHarmonicEdgeAttrs.forward (hamgnn/toolbox/nequip/nn/embedding/_edge.py:59-67),
+ * RadialBasisEdgeEncoding.forward (hamgnn/nn/embeddings.py:73-100), BesselBasis.forward
+ * (hamgnn/utils/basis_functions.py:193-208), CosineCutoff.forward (hamgnn/utils/cutoff_functions.py:50-61).
+ *   edge_index [2,E] (row 0 = j, row 1 = i): vec = pos[i] + nbr_shift - pos[j]
+ *   sh_ls[n_ls]: the l of every irrep of irreps_edge_sh (mul 1 each), output sh [E, sum(2l+1)],
+ *   'component' normalisation of the unit vector (||Y_l||^2 = 2l+1), reference axis order (y,z,x).
+ *   rbf [E,num_radial] = sin(freq_n r)/r * 0.5(cos(pi r/rc)+1) [r<rc], freq = the reference's BesselBasis.freqs
+ *   buffer (HOST pointer, num_radial floats);  edge_vec [E,3] unit; edge_len [E].
+ */
+int hgb_edge_embed(const float* pos, const float* nbr_shift, const int64_t* edge_index, int64_t n_edges,
+                   const int32_t* sh_ls_host, int32_t n_ls, float cutoff, const float* bessel_freqs_host,
+                   int32_t num_radial, float* sh, float* rbf, float* edge_vec, float* edge_len, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5-a8 (+a9 scatter, +a11 skip): fused MessagePackBlock.
+ * Replaces MessagePackBlock.forward (hamgnn/nn/message_passing.py:216-231), LinearScaleWithWeights
+ * (hamgnn/nn/tensor_products.py:25-47), the FullyConnectedNet radial weight generators
+ * (message_passing.py:173-189), AttentionHeadsToVector (hamgnn/nn/attention_utils.py:85-120),
+ * torch_scatter.scatter in ConvBlockE3.forward (hamgnn/nn/convolution.py:147-149) and the
+ * `edge_feats_mix + skip_linear(edge_feats)` of PairInteractionBlock.forward
+ * (hamgnn/nn/interaction_blocks.py:154-155).  The same kernel with one branch evaluates
+ * TensorProductWithMemoryOptimizationWithWeight.forward (hamgnn/nn/tensor_products.py:170-189).
+ */
+typedef struct {
+  int32_t mul;      /* multiplicity of the output slot                              */
+  int32_t mpad;     /* mul rounded up to a multiple of 4 (weight tables are padded) */
+  int32_t l;        /* l of the output irrep                                        */
+  int32_t out_off;  /* first column of the slot in the output row                   */
+  int32_t path_begin, path_end; /* paths feeding this slot: [begin, end)            */
+  int32_t pad0, pad1;
+} hgb_type_t;
+
+typedef struct {
+  int32_t kind;      /* 0: CG path (A W) * gate -> L';  1: direct linear (no SH, no gate)           */
+  int32_t branch;    /* which radial MLP / input group the path belongs to                         */
+  int32_t src0;      /* index of the first input source                                            */
+  int32_t nsrc;      /* 1, or 2 for the fused (src|dst) node input: channel u -> source src0+u/mul  */
+  int32_t in_off;    /* first column of the input irrep block inside its source row                */
+  int32_t mul_in;    /* multiplicity per source; K = nsrc * mul_in                                 */
+  int32_t l1, l2, l3;
+  int32_t sh_off;    /* first column of Y_l2 in the SH row                                          */
+  int32_t cg_off;    /* offset into cg_ij / cg_val (entries sorted by k)                            */
+  int32_t cg_kstart; /* offset into cg_kstart table (2*l3+2 entries)                                */
+  int32_t w_off;     /* packed TP weight  [K][mpad]   (scaled by the path coefficient)              */
+  int32_t w3_off;    /* packed radial last layer [H2][mpad] (scaled by 1/sqrt(H2))                   */
+  int32_t lf_off;    /* packed folded (mid->D Linear) x (out Linear): [mpad][mpad]; kind 1: [K][mpad] */
+  int32_t pad0;
+} hgb_path_t;
+
+typedef struct {
+  int32_t n_types, n_paths, n_branches, n_sources;
+  int32_t sh_dim, rbf_dim, h1, h2;   /* radial MLP sizes [rbf_dim, h1, h2, *]                   */
+  int32_t out_dim;
+  int32_t src_dim[4];                /* row length of every input source                          */
+  int32_t fc1_off[2], fc2_off[2];    /* per branch: packed [rbf_dim][h1] and [h1][h2] (pre-scaled) */
+  float act_const;                   /* normalize2mom constant of silu                             */
+  const hgb_type_t* types;           /* device copies (read by the kernel)                         */
+  const hgb_path_t* paths;
+  const hgb_type_t* types_host;      /* host copies of the same tables (validated on every call)   */
+  const hgb_path_t* paths_host;
+  const int32_t* cg_ij;              /* i | (j << 8)                                               */
+  const float* cg_val;
+  const int32_t* cg_kstart;
+  const float* wbuf;                 /* all packed weights                                         */
+} hgb_msgpack_plan;
+
+/* src_rows[s]: row-gather index (int64, length E) for source s or NULL for identity (row e).
+ * out_index: NULL -> out[e, :] = message (+ `out` is overwritten);
+ *            else  -> out[out_index[e], :] += message  (out must be pre-zeroed; receiver scatter-sum).
+ */
+int hgb_msgpack_forward(const hgb_msgpack_plan* plan_host, const float* const* src_host,
+                        const int64_t* const* src_rows_host, const float* sh, const float* rbf,
+                        int64_t n_edges, float* out, const int64_t* out_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].
+ * Replaces o3.Linear call sites (hamgnn/nn/convolution.py:112, interaction_blocks.py:126,306-309,
+ * embeddings.py:286, toolbox/nequip/nn/_atomwise.py:51, hamgnn_output.py:49), ResidualBlock.forward
+ * (hamgnn/nn/interaction_blocks.py:332-358, e3nn Gate with ssp/tanh), HamLayer.forward
+ * (hamgnn/models/hamgnn_output.py:38-58).
+ */
+typedef struct {
+  int32_t in_off, out_off, mul_in, mul_out, dim, w_off; /* out[r, out_off + w*dim + k] += sum_u in[r, in_off + u*dim + k] W[w_off + u*mul_out + w] */
+} hgb_linblock_t;
+
+typedef struct {
+  int32_t n_blocks, in_dim, out_dim, pad;
+  const hgb_linblock_t* blocks;  /* device */
+  const float* w;                /* device, pre-scaled by 1/sqrt(fan_in) */
+} hgb_linear_plan;
+
+/* y[r,:] = (accumulate ? y[r,:] : 0) + Linear(x[rows ? rows[r] : r, :]) */
+int hgb_linear_forward(const hgb_linear_plan* plan_host, const float* x, const int64_t* rows, int64_t n_rows,
+                       float* y, int32_t accumulate, void* stream);
+
+typedef struct {
+  /* e3nn Gate: input row = sorted/simplified (scalars | gates | gated), output row = scalars + gated */
+  int32_t n_scalar_slots;
+  int32_t sc_in_off[4], sc_out_off[4], sc_n[4], sc_act[4];  /* act: 0 = ssp (even), 1 = tanh (odd) */
+  int32_t n_gated;
+  int32_t gd_in_off[16], gd_out_off[16], gd_mul[16], gd_dim[16], gd_gate_off[16]; /* gate columns in the input row */
+  float c_ssp, c_tanh;             /* normalize2mom constants */
+  int32_t in_dim, out_dim;
+} hgb_gate_desc;
+
+/* y = x + Lin2(Gate(Lin1(x))) [+ extra]  ; if post != NULL: y = post(y).  x,y: [n_rows, D]. */
+int hgb_resblock_forward(const hgb_linear_plan* lin1_host, const hgb_gate_desc* gate_host,
+                         const hgb_linear_plan* lin2_host, const hgb_linear_plan* post_host,
+                         const float* x, const float* extra, int64_t n_rows, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14+a15: Clebsch-Gordan assembly of orbital blocks, orbital reorder, (anti-)symmetrisation with the
+ * inverse edge, +H0, orbital masks, interleaved per-crystal output rows.
+ * Replaces merge_tensor_components (hamgnn/models/hamgnn_output.py:851-891), reorder_matrix (:1056-1096),
+ * symmetrize_hamiltonian (:1231-1285), apply_orbital_masks_to_hamiltonians (:2288-2365),
+ * concatenate_hamiltonians_by_crystal (:1187-1229) and the +Hon0/+Hoff0 of forward (:3782-3795).
+ */
+typedef struct {
+  int32_t nao, n_coef, nnz, pad;
+  const int32_t* row_ptr;   /* device [nao*nao+1], CSR over the reordered flattened (a,b) entries */
+  const int32_t* col;       /* device [nnz] coefficient column                                   */
+  const float* val;         /* device [nnz] sqrt(2L+1) * w3j                                     */
+  const uint8_t* orb_mask;  /* device [128][nao] 1 if the orbital exists for element Z            */
+} hgb_ham_plan;
+
+/* raw[r, a*nao+b] = sum_nnz val * coef[r, col]  (CG merge + reorder) */
+int hgb_ham_assemble(const hgb_ham_plan* plan_host, const float* coef, int64_t n_rows, float* raw, void* stream);
+
+/* out[out_row[r], :] = mask(z[na[r]], z[nb[r]]) * ( (sym ? 0.5*(raw[r] + raw[partner[r]]^T) : raw[r]) + (h0 ? h0[r] : 0) )
+ * partner == NULL -> on-site (partner = r); node_a/node_b == NULL -> identity (row r is atom r). */
+int hgb_ham_finalize(const hgb_ham_plan* plan_host, const float* raw, const int64_t* partner, const float* h0,
+                     const int64_t* z, const int64_t* node_a, const int64_t* node_b, const int64_t* out_row,
+                     int64_t n_rows, int32_t symmetrize, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAMGNN_B200_H */

@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE -- CPU emulation of the *arithmetic* of the CUDA kernels, driven by the very same
+packed tables / ctypes structs that are uploaded to the GPU (types, paths, sparse CG lists, wbuf, linear
+blocks, gate descriptor, Hamiltonian CSR).  It lets the CPU test-suite check the host planners against the
+oracle without a GPU; it is never used by the product path (hamgnn_b200/ has no CPU fallback).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from hamgnn_b200 import lib as L
+from hamgnn_b200.plan import GateLayout, HamAssembly, LinearOp, MessagePackOp
+
+
+def _silu(x):
+    return x / (1.0 + torch.exp(-x))
+
+
+def emulate_msgpack(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, sh, rbf, out_rows=None, n_out=None):
+    """Mirrors msgpack_kernel: T -> A -> (A W) * g -> L' per path, summed per output slot."""
+    from hamgnn_b200 import so3
+    E = sh.shape[0]
+    dt = wbuf.dtype
+    D = op.irreps_out.dim
+    msg = torch.zeros(E, D, dtype=dt)
+    act = so3.normalize2mom_const("silu")
+    h2 = []
+    for b in range(len(op.branches)):
+        w1 = wbuf[op.fc1_off[b]:op.fc1_off[b] + op.rbf_dim * op.h1].view(op.rbf_dim, op.h1)
+        w2 = wbuf[op.fc2_off[b]:op.fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
+        h = _silu(rbf @ w1) * act
+        h2.append(_silu(h @ w2) * act)
+    gathered = [s if r is None else s[r] for s, r in zip(sources, rows)]
+    for t in range(len(op.irreps_out)):
+        ty = op.types_c[t]
+        d3 = 2 * ty.l + 1
+        acc = torch.zeros(E, d3, ty.mpad, dtype=dt)
+        for p in range(ty.path_begin, ty.path_end):
+            pa = op.paths_c[p]
+            d1 = 2 * pa.l1 + 1
+            K = pa.nsrc * pa.mul_in
+            x = torch.cat([gathered[pa.src0 + s][:, pa.in_off:pa.in_off + pa.mul_in * d1] for s in range(pa.nsrc)], dim=1)
+            x = x.reshape(E, K, d1)
+            if pa.kind == 0:
+                T = torch.zeros(E, d1, d3, dtype=dt)
+                ks = op.cg_ks[pa.cg_kstart:pa.cg_kstart + d3 + 1]
+                for k in range(d3):
+                    for n in range(ks[k], ks[k + 1]):
+                        ij = int(op.cg_ij[pa.cg_off + n])
+                        T[:, ij & 255, k] += float(op.cg_val[pa.cg_off + n]) * sh[:, pa.sh_off + (ij >> 8)]
+                A = torch.einsum("zui,zik->zku", x, T)
+                W = wbuf[pa.w_off:pa.w_off + K * ty.mpad].view(K, ty.mpad)
+                W3 = wbuf[pa.w3_off:pa.w3_off + op.h2 * ty.mpad].view(op.h2, ty.mpad)
+                Lf = wbuf[pa.lf_off:pa.lf_off + ty.mpad * ty.mpad].view(ty.mpad, ty.mpad)
+                g = h2[pa.branch] @ W3
+                B = (A @ W) * g[:, None, :]
+                acc += B @ Lf
+            else:
+                Lf = wbuf[pa.lf_off:pa.lf_off + K * ty.mpad].view(K, ty.mpad)
+                acc += x.transpose(1, 2) @ Lf
+        msg[:, ty.out_off:ty.out_off + ty.mul * d3] = acc[:, :, :ty.mul].transpose(1, 2).reshape(E, ty.mul * d3)
+    if out_rows is None:
+        return msg
+    out = torch.zeros(n_out, D, dtype=dt)
+    return out.index_add_(0, out_rows, msg)
+
+
+def emulate_linear(op: LinearOp, weight: torch.Tensor, x: torch.Tensor):
+    y = torch.zeros(x.shape[0], op.irreps_out.dim, dtype=x.dtype)
+    w = weight * torch.from_numpy(op._scale_np).to(x.dtype)
+    for b in op.blocks:
+        xi = x[:, b.in_off:b.in_off + b.mul_in * b.dim].reshape(-1, b.mul_in, b.dim)
+        W = w[b.w_off:b.w_off + b.mul_in * b.mul_out].view(b.mul_in, b.mul_out)
+        y[:, b.out_off:b.out_off + b.mul_out * b.dim] += torch.einsum("zui,uw->zwi", xi, W).reshape(x.shape[0], -1)
+    return y
+
+
+def emulate_gate(g: GateLayout, h: torch.Tensor):
+    d = g.desc
+    out = torch.zeros(h.shape[0], d.out_dim, dtype=h.dtype)
+    ssp = lambda v: torch.nn.functional.softplus(v) - np.log(2.0)
+    for s in range(d.n_scalar_slots):
+        v = h[:, d.sc_in_off[s]:d.sc_in_off[s] + d.sc_n[s]]
+        out[:, d.sc_out_off[s]:d.sc_out_off[s] + d.sc_n[s]] = ssp(v) * d.c_ssp if d.sc_act[s] == 0 else torch.tanh(v) * d.c_tanh
+    for s in range(d.n_gated):
+        mul, dim = d.gd_mul[s], d.gd_dim[s]
+        gate = ssp(h[:, d.gd_gate_off[s]:d.gd_gate_off[s] + mul]) * d.c_ssp
+        v = h[:, d.gd_in_off[s]:d.gd_in_off[s] + mul * dim].reshape(-1, mul, dim)
+        out[:, d.gd_out_off[s]:d.gd_out_off[s] + mul * dim] = (v * gate[:, :, None]).reshape(h.shape[0], -1)
+    return out
+
+
+def emulate_resblock(rb, x, extra=None, post=None, post_w=None):
+    h = emulate_linear(rb.op1, rb.linear1.weight.detach().to(x.dtype), x)
+    a = emulate_gate(rb.gate, h)
+    y = x + emulate_linear(rb.op2, rb.linear2.weight.detach().to(x.dtype), a)
+    if extra is not None:
+        y = y + extra
+    if post is not None:
+        y = emulate_linear(post, post_w.detach().to(x.dtype), y)
+    return y
+
+
+def emulate_ham(asm: HamAssembly, coef, partner, h0, z, na, nb, symmetrize=True):
+    nn2 = asm.nao ** 2
+    raw = torch.zeros(coef.shape[0], nn2, dtype=coef.dtype)
+    val = torch.from_numpy(asm.val).to(coef.dtype)
+    for q in range(nn2):
+        n0, n1 = asm.row_ptr[q], asm.row_ptr[q + 1]
+        if n1 > n0:
+            raw[:, q] = (coef[:, torch.from_numpy(asm.col[n0:n1]).long()] * val[n0:n1]).sum(-1)
+    m = raw.view(-1, asm.nao, asm.nao)
+    if symmetrize:
+        other = m if partner is None else m[partner]
+        m = 0.5 * (m + other.transpose(1, 2))
+    if h0 is not None:
+        m = m + h0.view(-1, asm.nao, asm.nao)
+    mask = torch.from_numpy(asm.mask).to(coef.dtype)
+    za = z if na is None else z[na]
+    zb = z if nb is None else z[nb]
+    return (m * mask[za][:, :, None] * mask[zb][:, None, :]).reshape(-1, nn2)

@@ -1,0 +1,131 @@
+"""CPU tests of the host planners: the packed tables that drive the CUDA kernels, executed by the
+arithmetic emulator (tests/kernel_emulator.py), must reproduce the oracle."""
+import pytest
+import torch
+
+from hamgnn_b200 import graph_data as gd
+from hamgnn_b200.irreps import Irreps
+from hamgnn_b200.plan import tp_paths
+import hgb_kernel_emulator as EM
+from hgb_testlib import SMALL_CFG, build_pair, oracle_forward, rel_err
+
+
+def test_default_mid_irreps_match_survey():
+    D = Irreps("64x0e+64x0o+32x1o+16x1e+12x2o+25x2e+18x3o+9x3e+4x4o+9x4e+4x5o+4x5e+2x6e")
+    sh = Irreps("0e + 1o + 2e + 3o + 4e + 5o")
+    mid, paths = tp_paths(D.scaled(2), sh, D)
+    assert str(mid.simplify()) == ("384x0o+384x0e+512x1o+240x1e+264x2o+550x2e+468x3o+225x3e+104x4o+234x4e+96x5o+"
+                                   "92x5e+36x6e")
+    assert len(paths) == 255 and sum(p.mul_in_total * p.mul_out for p in paths) == 118482
+    mid_e, paths_e = tp_paths(D, sh, D)
+    assert sum(p.mul_in_total * p.mul_out for p in paths_e) == 59241 and mid_e.dim == 17523
+
+
+@pytest.fixture(scope="module")
+def small():
+    pre, out, opre, oout = build_pair(SMALL_CFG)
+    g = gd.Batch.from_data_list([gd.bulk_silicon(), gd.graphene(rep=(2, 2, 1), seed=1)])
+    d, rep, res = oracle_forward(opre, oout, g)
+    return pre, out, opre, oout, g, d, rep, res
+
+
+def _dbl(t):
+    return t.detach().double()
+
+
+def test_conv_message_and_scatter(small):
+    pre, out, opre, oout, g, d, rep, res = small
+    # re-run the oracle up to the first conv to capture its inputs
+    from oracle import hamgnn_ref as R
+    dd = R.AttrDict({k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in g.to_dict().items()})
+    with torch.no_grad():
+        onehot = torch.nn.functional.one_hot(dd["z"], opre.num_types).double()
+        dd["node_attrs"] = dd["node_features"] = onehot
+        opre.edge_geometry(dd)
+        opre.pair_embedding(dd)
+        dd["node_features"] = opre.chemical_embedding.linear(onehot)
+        x, e = dd["node_features"].clone(), dd["edge_features"].clone()
+        conv = opre.convolutions[0]
+        s, r = dd["edge_index"]
+        m_ref = conv.conv_tp(x[s], x[r], e, dd["edge_attrs"], dd["edge_embedding"])
+    blk = pre.convolutions[0].conv_tp
+    st, wbuf = blk.op.pack(blk.weights())
+    m = EM.emulate_msgpack(blk.op, wbuf.double(), [x, x, e], [s, r, None], dd["edge_attrs"], dd["edge_embedding"])
+    assert rel_err(m, m_ref) < 2e-6
+    agg = EM.emulate_msgpack(blk.op, wbuf.double(), [x, x, e], [s, r, None], dd["edge_attrs"], dd["edge_embedding"],
+                             out_rows=r, n_out=x.shape[0])
+    agg_ref = torch.zeros_like(x).index_add_(0, r, m_ref)
+    assert rel_err(agg, agg_ref) < 2e-6
+
+
+def test_embedding_block(small):
+    pre, out, opre, oout, g, d, rep, res = small
+    from oracle import hamgnn_ref as R
+    dd = R.AttrDict({k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in g.to_dict().items()})
+    with torch.no_grad():
+        onehot = torch.nn.functional.one_hot(dd["z"], opre.num_types).double()
+        dd["node_features"] = onehot
+        opre.edge_geometry(dd)
+        ref = opre.pair_embedding(dd)
+    pe = pre.pair_embedding
+    s, r = dd["edge_index"]
+    h = EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_src.weight), onehot[s]) + \
+        EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_dst.weight), onehot[r])
+    st, wbuf = pe.conv_tp.op.pack(pe.conv_tp.weights())
+    got = EM.emulate_msgpack(pe.conv_tp.op, wbuf.double(), [h], [None], dd["edge_attrs"], dd["edge_embedding"])
+    assert rel_err(got, ref) < 2e-6
+
+
+def test_pair_block_with_skip(small):
+    pre, out, opre, oout, g, d, rep, res = small
+    torch.manual_seed(3)
+    E, N, D = g.edge_index.shape[1], g.num_nodes, pre.irreps_node_features.dim
+    x, e = torch.randn(N, D).double(), torch.randn(E, D).double()
+    dd = {"edge_index": g.edge_index, "node_features": x, "edge_features": e, "edge_attrs": d["edge_attrs"],
+          "edge_embedding": d["edge_embedding"]}
+    with torch.no_grad():
+        ref = opre.pair_interactions[1](dict(dd))
+    pb = pre.pair_interactions[1]
+    xs = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_src.weight), x)
+    xt = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_tar.weight), x)
+    st, wbuf = pb.conv_tp.op.pack(pb.conv_tp.weights(pb.skip_linear.weight))
+    s, r = g.edge_index
+    got = EM.emulate_msgpack(pb.conv_tp.op, wbuf.double(), [xs, xt, e], [s, r, None], d["edge_attrs"], d["edge_embedding"])
+    assert rel_err(got, ref) < 2e-6
+
+
+def test_resblock_and_head(small):
+    pre, out, opre, oout, g, d, rep, res = small
+    torch.manual_seed(4)
+    x = torch.randn(7, pre.irreps_node_features.dim).double()
+    with torch.no_grad():
+        ref = opre.convolutions[0].residual(x)
+        ref_head = oout.offsite_hamiltonian_network(x)
+    got = EM.emulate_resblock(pre.convolutions[0].residual, x)
+    assert rel_err(got, ref) < 2e-6
+    hl = out.offsite_hamiltonian_network
+    got_head = EM.emulate_resblock(hl.residual_block, x, post=hl.op, post_w=hl.linear_transform.weight)
+    assert rel_err(got_head, ref_head) < 2e-6
+
+
+def test_ham_assembly(small):
+    pre, out, opre, oout, g, d, rep, res = small
+    torch.manual_seed(5)
+    E, N = g.edge_index.shape[1], g.num_nodes
+    coef_on = torch.randn(N, out.assembly.n_coef).double()
+    coef_off = torch.randn(E, out.assembly.n_coef).double()
+    on_row, off_row, inv = out._row_maps(g)
+    with torch.no_grad():
+        Hon = oout._sym(oout.reorder_matrix(oout.merge_tensor_components(torch.split(coef_on, oout.ham_dims, -1)))) + d["Hon0"]
+        Hoff = oout._sym(oout.reorder_matrix(oout.merge_tensor_components(torch.split(coef_off, oout.ham_dims, -1))), inv) + d["Hoff0"]
+        Hon, Hoff = oout._mask(Hon, Hoff, d)
+    s, r = g.edge_index
+    got_on = EM.emulate_ham(out.assembly, coef_on, None, d["Hon0"], g.z, None, None)
+    got_off = EM.emulate_ham(out.assembly, coef_off, inv, d["Hoff0"], g.z, s, r)
+    assert rel_err(got_on, Hon) < 1e-6 and rel_err(got_off, Hoff) < 1e-6
+    # interleaved per-crystal rows
+    ref = oout.concat_by_crystal(d, Hon, Hoff)
+    H = torch.empty_like(ref)
+    H[on_row] = got_on
+    H[off_row] = got_off
+    assert rel_err(H, ref) < 1e-6
