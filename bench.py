@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- edge TP-messages/s of the HamGNN hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tbg_m28]
+
+A "step" is one full inference forward (HamGNN_pre + HamGNN_out: edge embedding, initial edge features,
+3 x (ConvBlockE3 + PairInteractionBlock) = 6 fused MessagePackBlock evaluations per directed edge, on-site and
+hopping heads, CG assembly/symmetrisation) of ONE synthetic carbon crystal graph: commensurate twisted bilayer
+graphene, twist index m=28 (N=9748 atoms, E~7.8e5 directed edges) -- the "~10k-atom carbon graph" on which
+BASELINE.json quotes its targets (configs[4]); it fits one GPU, so it is also the N=1 workload.
+(configs[1] is a *training* batch; backward kernels are the first "next" row and are not built yet, so a
+training step cannot be measured validly.)  One message = one MessagePackBlock evaluation for one directed
+edge; value = 6 E / step time.  Random-init weights (seed 0), synthetic H0 -- no datasets/checkpoints offline.
+
+N>1: the single graph is edge-sharded over the ranks (hamgnn_b200.dist), one NCCL all-reduce of the [N,877]
+aggregates per ConvBlockE3; total work is fixed => "scaling": "strong".
+
+--impl reference: the reference's own implementation (e3nn/PyG CPU path) cannot be installed offline, so
+this arm times the CPU restatement under oracle/ (kind "port") with all host threads on a bounded sample
+(a 32-atom graphene cell, same model config), rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+MSG_PER_EDGE = 6  # 3 layers x (ConvBlockE3 + PairInteractionBlock)
+
+
+def build_workload(name: str):
+    from hamgnn_b200 import graph_data as gd
+    if name.startswith("tbg_m"):
+        m = int(name[5:])
+        g = gd.twisted_bilayer_graphene(m=m, seed=0, nao_max=19)
+        desc = f"twisted bilayer graphene m={m}"
+    elif name == "graphene_4x4":
+        g = gd.graphene(rep=(4, 4, 1), seed=0)
+        desc = "graphene 4x4 supercell"
+    elif name == "carbon_batch":
+        gs = [gd.graphene(rep=(5, 5, 1), seed=i) if i % 2 == 0 else gd.diamond_carbon(rep=(2, 2, 2), seed=i) for i in range(8)]
+        return gd.Batch.from_data_list(gs), "8-graph carbon batch (graphene 5x5 + diamond 2x2x2)"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return gd.Batch.from_data_list([g]), desc
+
+
+def build_models(seed=0):
+    from hamgnn_b200.hamgnn_conv import HamGNNConvE3
+    from hamgnn_b200.hamgnn_output import HamGNNPlusPlusOut
+    torch.manual_seed(seed)
+    pre = HamGNNConvE3({})
+    out = HamGNNPlusPlusOut(pre.irreps_node_features, pre.irreps_node_features, nao_max=19, soc_switch=False,
+                            ham_only=True, add_H0=True, symmetrize=True)
+    return pre, out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(threads: int, repeats: int = 2):
+    """Oracle (CPU restatement of the reference arithmetic) on a bounded sample of the same model."""
+    from hgb_testlib import build_pair, oracle_forward
+    from hamgnn_b200 import graph_data as gd
+    torch.set_num_threads(threads)
+    pre, out, opre, oout = build_pair({}, nao_max=19, add_H0=True)
+    g = gd.Batch.from_data_list([gd.graphene(rep=(4, 4, 1), seed=0)])
+    E = g.edge_index.shape[1]
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        oracle_forward(opre, oout, g, dtype=torch.float32)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return MSG_PER_EDGE * E / best, E, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from hgb_testlib import build_pair, oracle_forward
+    from hamgnn_b200 import graph_data as gd
+    torch.set_num_threads(threads)
+    pre, out, opre, oout = build_pair({}, nao_max=19, add_H0=True)
+    g = gd.Batch.from_data_list([gd.graphene(rep=(4, 4, 1), seed=0)])
+    E = g.edge_index.shape[1]
+    for _ in range(min(args.warmup, 1)):
+        oracle_forward(opre, oout, g, dtype=torch.float32)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_forward(opre, oout, g, dtype=torch.float32)
+    dt = (time.perf_counter() - t) / args.steps
+    val = MSG_PER_EDGE * E / dt
+    sample = f"graphene 4x4x1 (N={g.num_nodes}, E={E}), full forward, default model, fp32"
+    line = {"impl": "reference", "metric": "edge_tp_messages_per_s", "value": val, "unit": "messages/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": sample, "model": "HamGNN_pre(default irreps, 3 layers)+HamGNN_out(nao 19)"},
+            "cpu_baseline": {"value": val, "unit": "messages/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tbg_m28")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from hamgnn_b200 import graph_data as gd
+    from hamgnn_b200 import lib as L
+    from hamgnn_b200 import plan as P
+    from hamgnn_b200.dist import install_edge_sharding, shard_edges
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    batch, desc = build_workload(args.workload)
+    E_total, N = batch.edge_index.shape[1], batch.num_nodes
+    pre, out = build_models(0)
+    pre.to(dev)
+    out.to(dev)
+    red = None
+    if world > 1:
+        host = shard_edges(batch, rank, world)
+        red = install_edge_sharding(pre)
+    else:
+        host = batch
+    host = gd.Batch(**{k: v for k, v in host.to_dict().items() if k not in ("Hon", "Hoff", "Son", "Soff", "cell_shift")})
+    E_local = host.edge_index.shape[1]
+    host.pin_memory()
+    resident = gd.Batch(**host.to_dict()).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        b = gd.Batch(**resident.to_dict())
+        with torch.no_grad():
+            return out(b, pre(b))["hamiltonian"]
+
+    h_host = torch.empty(N + E_local, 361, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.to_dict().values() if torch.is_tensor(v))
+
+    def step_e2e():
+        b = gd.Batch(**{k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.to_dict().items()})
+        with torch.no_grad():
+            H = out(b, pre(b))["hamiltonian"]
+        h_host.copy_(H, non_blocking=True)
+        return H
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = L.launch_count()
+    P.PROFILER = prof = P.KernelProfiler()
+    ms_step = timed(step_resident, args.steps)
+    P.PROFILER = None
+    launches = (L.launch_count() - n0)
+    torch.cuda.synchronize()
+    ksum = prof.summary()
+    clk = clocks.stop() if rank == 0 else None
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback"
+    value = MSG_PER_EDGE * E_total / (ms_step * 1e-3)
+    k_ms = ksum["total_ms"] / max(1, ksum["launches"])
+    k_tflops = ksum["flops"] / max(1e-9, ksum["total_ms"] * 1e-3) / 1e12
+    alg_bytes_per_edge = 4 * (877 + 36 + 64) + 16 + 2 * 877 * 4 * N / max(1, E_total)
+    k_gbs = ksum["edges"] * alg_bytes_per_edge / max(1e-9, ksum["total_ms"] * 1e-3) / 1e9
+    line = {
+        "metric": "edge_tp_messages_per_s", "value": value, "unit": "messages/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}, N={N}, E={E_total}, inference forward HamGNN_pre+HamGNN_out",
+                   "model": "default irreps (D=877, l<=6), SH l<=5, 3 layers, nao_max 19, add_H0, random init seed 0",
+                   "messages_per_edge": MSG_PER_EDGE, "parallelism": f"edge-shard x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (edge features 2.7 GB per tensor)"},
+        "clocks": clk,
+        "e2e": {"value": MSG_PER_EDGE * E_total / (ms_e2e * 1e-3), "unit": "messages/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": h_host.numel() * 4},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)", "bound": "tensor",
+                     "achieved": k_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k_tflops / bf16_peak,
+                     "peak_source": peak_src, "traffic": None, "avg_launch_ms": k_ms, "launches_timed": ksum["launches"],
+                     "kernel_share_of_step": ksum["total_ms"] / (ms_step * args.steps),
+                     "flop_per_edge": ksum["flops"] / max(1, ksum["edges"]),
+                     "hbm_view": {"achieved": k_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak,
+                                  "alg_bytes_per_edge": alg_bytes_per_edge},
+                     "fp32_simt_view": {"achieved": k_tflops, "peak_nominal": 148 * 128 * 2 * (clk["sm_mhz"] or 1700) * 1e6 / 1e12 if clk else None,
+                                        "unit": "TFLOP/s"}},
+    }
+    if red is not None:
+        line["collectives"] = {"all_reduce_calls_per_step": red.calls // (args.steps * 2 + args.warmup + 1), "bytes_each": N * 877 * 4}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, Es, dt = cpu_oracle_rate(threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "messages/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle full forward on graphene 4x4x1 (E={Es}), default model, fp32, best of 2 ({dt:.2f} s)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

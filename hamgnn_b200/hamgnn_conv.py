@@ -138,6 +138,7 @@ class ConvBlockE3(nn.Module):
         self.conv_tp = MessagePackBlock(D, D, irreps_sh, D, num_radial, radial_MLP)
         self.skip_op = LinearOp(D, D)
         self.skip_linear = _W(self.skip_op.weight_numel)
+        self.reduce_fn = None  # edge-sharded multi-GPU: all-reduce of the partial aggregates (hamgnn_b200.dist)
 
     def forward(self, data):
         sender, receiver = data["edge_index"][0], data["edge_index"][1]
@@ -146,6 +147,8 @@ class ConvBlockE3(nn.Module):
         agg = torch.zeros_like(x)
         self.conv_tp.op.forward(self.conv_tp.weights(), [x, x, e], [sender, receiver, None], data["edge_attrs"],
                                 data["edge_embedding"], e.shape[0], agg, out_index=receiver)
+        if self.reduce_fn is not None:
+            agg = self.reduce_fn(agg)
         out = self.residual.forward_cuda(agg, extra=skip)
         data["node_features"] = out
         return out

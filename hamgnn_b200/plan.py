@@ -202,6 +202,32 @@ class GateLayout:
 
 
 # ====================================================================================== MessagePack
+class KernelProfiler:
+    """CUDA-event bracket around every fused-message launch (bench.py's live roofline measurement); events
+    are recorded on the stream the kernel is launched on."""
+
+    def __init__(self):
+        self.records = []  # (start, end, flops, edges)
+
+    def begin(self, op, n_edges, device):
+        self._s = torch.cuda.Event(enable_timing=True)
+        self._e = torch.cuda.Event(enable_timing=True)
+        self._meta = (op.flops_per_edge() * n_edges, n_edges)
+        self._s.record(torch.cuda.current_stream(device))
+
+    def end(self, device):
+        self._e.record(torch.cuda.current_stream(device))
+        self.records.append((self._s, self._e) + self._meta)
+
+    def summary(self):
+        ms = [s.elapsed_time(e) for s, e, _, _ in self.records]
+        return {"launches": len(ms), "total_ms": sum(ms), "flops": sum(r[2] for r in self.records),
+                "edges": sum(r[3] for r in self.records)}
+
+
+PROFILER: Optional[KernelProfiler] = None
+
+
 @dataclass
 class Branch:
     """One tensor-product branch of a MessagePackBlock: `nsrc` input sources sharing `irreps_in`
@@ -480,13 +506,20 @@ class MessagePackOp:
         rws = (C.c_void_p * 4)(*[L.ptr(r) for r in rows] + [None] * (4 - ns))
         for s, d in zip(sources, self.src_dims):
             assert s.shape[-1] == d and s.is_contiguous(), (s.shape, d)
+        prof = PROFILER
+        if prof is not None:
+            prof.begin(self, int(n_edges), out.device)
         rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
                                           int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
+        if prof is not None:
+            prof.end(out.device)
         L.check(rc, "hgb_msgpack_forward")
         return out
 
     # FLOP / byte accounting for bench.py (per edge, algorithmic minimum of this formulation)
     def flops_per_edge(self) -> int:
+        if getattr(self, "_flops", None) is not None:
+            return self._flops
         fl = 0
         for b, br in enumerate(self.branches):
             fl += 2 * (self.rbf_dim * self.h1 + self.h1 * self.h2 + self.h2 * self.n_channels[b])
@@ -496,6 +529,7 @@ class MessagePackOp:
                 fl += 2 * K * min(nnz, d1 * d3) + 2 * K * M * d3 + M * d3 + 2 * M * M * d3
         if self.direct_src is not None:
             fl += sum(2 * m.mul * m.mul * m.ir.dim for m in self.irreps_out)
+        self._flops = fl
         return fl
 
 

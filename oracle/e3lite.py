@@ -411,7 +411,6 @@ class TensorProduct(torch.nn.Module):
             a = x1[:, s1[i1]].reshape(Z, m1, ir1.dim)
             b = x2[:, s2[i2]].reshape(Z, m2, ir2.dim)
             w3 = wigner_3j(ir1.l, ir2.l, iro.l, dtype=x1.dtype).to(x1.device)
-            xx = torch.einsum("zui,zvj->zuvij", a, b)
             w = None
             if hw:
                 n = math.prod(self.shapes[k])
@@ -420,18 +419,26 @@ class TensorProduct(torch.nn.Module):
                 else:
                     w = weight[:, off:off + n].reshape((Z,) + self.shapes[k])
                 off += n
-            if mode == "uvw":
-                if w.dim() == 3:
-                    y = torch.einsum("uvw,ijk,zuvij->zwk", w, w3, xx)
-                else:
-                    y = torch.einsum("zuvw,ijk,zuvij->zwk", w, w3, xx)
-            else:  # uvu
-                if w is None:
-                    y = torch.einsum("ijk,zuvij->zuk", w3, xx)
-                elif w.dim() == 2:
-                    y = torch.einsum("uv,ijk,zuvij->zuk", w, w3, xx)
-                else:
-                    y = torch.einsum("zuv,ijk,zuvij->zuk", w, w3, xx)
+            if mode == "uvw" and m2 == 1 and w.dim() == 3:
+                # same contraction order opt_einsum picks for e3nn's 'uvw,ijk,zuvij->zwk' (dense CG first,
+                # then the shared-weight GEMM), written as two matmuls
+                xx = (a[:, :, :, None] * b[:, None, 0, None, :]).reshape(Z * m1, ir1.dim * ir2.dim)
+                t = (xx @ w3.reshape(ir1.dim * ir2.dim, iro.dim)).reshape(Z, m1, iro.dim)
+                y = torch.matmul(t.transpose(1, 2), w[:, 0, :]).transpose(1, 2)
+            else:
+                xx = torch.einsum("zui,zvj->zuvij", a, b)
+                if mode == "uvw":
+                    if w.dim() == 3:
+                        y = torch.einsum("uvw,ijk,zuvij->zwk", w, w3, xx)
+                    else:
+                        y = torch.einsum("zuvw,ijk,zuvij->zwk", w, w3, xx)
+                else:  # uvu
+                    if w is None:
+                        y = torch.einsum("ijk,zuvij->zuk", w3, xx)
+                    elif w.dim() == 2:
+                        y = torch.einsum("uv,ijk,zuvij->zuk", w, w3, xx)
+                    else:
+                        y = torch.einsum("zuv,ijk,zuvij->zuk", w, w3, xx)
             y = self._coef(k) * y
             outs[io] = y if outs[io] is None else outs[io] + y
         res = []
