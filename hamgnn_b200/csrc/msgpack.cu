@@ -60,6 +60,18 @@ __device__ __forceinline__ void gemm_tiles(float (&acc)[NTL][4][4], const float*
   }
 }
 
+// Edges per sub-block of a tile for an output slot of dimension d3: the tile is cut into the smallest number of
+// near-equal pieces (multiples of 4 edges) whose row count nz*d3 fits RMAX.
+__host__ __device__ inline int sub_tile_edges(int te, int rmax, int d3) {
+  int nsub = (te * d3 + rmax - 1) / rmax;
+  int nz = ((te + nsub - 1) / nsub + 3) & ~3;
+  while (nz * d3 > rmax && nz > 4) {
+    ++nsub;
+    nz = ((te + nsub - 1) / nsub + 3) & ~3;
+  }
+  return nz;
+}
+
 template <int NTL>
 __device__ __forceinline__ void zero_tiles(float (&acc)[NTL][4][4]) {
 #pragma unroll
@@ -209,8 +221,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) msgpack_kernel(const 
     if (ty.path_begin == ty.path_end && a.out_index != nullptr) continue;  // nothing to scatter
     const int d3 = 2 * ty.l + 1;
     const int mpad = ty.mpad, M4 = mpad >> 2;
-    int tesub = (RMAX / d3) & ~3;
-    if (tesub > TE) tesub = TE;
+    const int tesub = sub_tile_edges(TE, RMAX, d3);
     for (int z0 = 0; z0 < TE; z0 += tesub) {
       const int nz = min(tesub, TE - z0);
       if (z0 >= ne) break;
@@ -372,8 +383,8 @@ extern "C" int hgb_msgpack_forward(const hgb_msgpack_plan* plan, const float* co
                   "hgb_msgpack_forward: output multiplicity %d (padded %d) unsupported (max %d)", ty.mul, ty.mpad, MPAD_MAX);
     HGB_CHECK_ARG(ty.out_off >= 0 && ty.out_off + ty.mul * d3 <= plan->out_dim, "hgb_msgpack_forward: slot %d outside the output row", t);
     HGB_CHECK_ARG(ty.path_begin >= 0 && ty.path_begin <= ty.path_end && ty.path_end <= plan->n_paths, "hgb_msgpack_forward: bad path range of slot %d", t);
-    int nz = (RMAX / d3) & ~3;
-    if (nz > TE) nz = TE;
+    const int nz = sub_tile_edges(TE, RMAX, d3);
+    HGB_CHECK_ARG(nz * d3 <= RMAX, "hgb_msgpack_forward: l=%d rows do not fit the %d-row tile", ty.l, RMAX);
     for (int p = ty.path_begin; p < ty.path_end; ++p) {
       const hgb_path_t& pa = plan->paths_host[p];
       const int d1 = 2 * pa.l1 + 1;

@@ -1,0 +1,104 @@
+// Self-test of the tcgen05 3xTF32 building block: C[128 x N] = A[128 x K] . B[K x N] per CTA, fp32 in/out,
+// operands staged in the interleaved K-major layout of tc_common.cuh, accumulator in TMEM.  Exposed through the
+// C ABI (hgb_tc_gemm_selftest) so the GPU test-suite can validate descriptors/layouts against a plain matmul
+// before the fused message kernel relies on them.
+#include "hgb_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+
+template <int NPAD>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                      float* __restrict__ C, int K, int N) {
+  extern __shared__ __align__(128) float smem[];
+  // layout: Ahi[K/4][128][4], Alo, Bhi[K/4][NPAD][4], Blo
+  float* Ahi = smem;
+  float* Alo = Ahi + (size_t)K * TM;
+  float* Bhi = Alo + (size_t)K * TM;
+  float* Blo = Bhi + (size_t)K * NPAD;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const float* Ab = A + (size_t)blockIdx.x * TM * K;
+  float* Cb = C + (size_t)blockIdx.x * TM * N;
+
+  if (tid == 0) {
+    tc::mbar_init(&mbar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<(NPAD < 32 ? 32 : NPAD)>(&tmem_base);
+  // stage + split A: element (r, k) -> (k/4)*(128*4) + r*4 + k%4
+  for (int idx = tid; idx < TM * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;
+    float hi, lo;
+    tc::split_tf32(Ab[idx], hi, lo);
+    const int o = (k >> 2) * (TM * 4) + r * 4 + (k & 3);
+    Ahi[o] = hi; Alo[o] = lo;
+  }
+  // stage + split B (global [K][N]) as [N][K] K-major: (n, k) -> (k/4)*(NPAD*4) + n*4 + k%4 ; zero padding
+  for (int idx = tid; idx < NPAD * K; idx += 128) {
+    const int k = idx / NPAD, n = idx - k * NPAD;
+    float hi = 0.f, lo = 0.f;
+    if (n < N) tc::split_tf32(B[(size_t)k * N + n], hi, lo);
+    const int o = (k >> 2) * (NPAD * 4) + n * 4 + (k & 3);
+    Bhi[o] = hi; Blo[o] = lo;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    constexpr uint32_t idesc = tc::idesc_tf32_m128(NPAD);
+    const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
+    const uint32_t lbo_a = TM * 16, lbo_b = NPAD * 16, sbo = 128;
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      const uint32_t oa = k8 * 2 * lbo_a, ob = k8 * 2 * lbo_b;
+      tc::mma_tf32(tmem, tc::smem_desc(a_lo + oa, lbo_a, sbo), tc::smem_desc(b_hi + ob, lbo_b, sbo), idesc, k8 > 0);
+      tc::mma_tf32(tmem, tc::smem_desc(a_hi + oa, lbo_a, sbo), tc::smem_desc(b_lo + ob, lbo_b, sbo), idesc, 1);
+      tc::mma_tf32(tmem, tc::smem_desc(a_hi + oa, lbo_a, sbo), tc::smem_desc(b_hi + ob, lbo_b, sbo), idesc, 1);
+    }
+    tc::mma_commit(&mbar);
+  }
+  tc::mbar_wait(&mbar, 0);
+  tc::fence_after_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < NPAD; c0 += 8) {
+    uint32_t r[8];
+    tc::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tc::tmem_ld_wait8(r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < N) Cb[(size_t)row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<(NPAD < 32 ? 32 : NPAD)>(tmem);
+}
+
+template <int NPAD>
+int launch(const float* A, const float* B, float* C, int tiles, int K, int N, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * K * TM + 2 * K * NPAD) * sizeof(float);
+  HGB_CHECK_ARG(smem <= 200 * 1024, "hgb_tc_gemm_selftest: K=%d too large for the staging buffers", K);
+  HGB_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_gemm_kernel<NPAD><<<tiles, 128, smem, st>>>(A, B, C, K, N);
+  HGB_LAUNCH_OK("tc_gemm_kernel");
+  return 0;
+}
+
+}  // namespace
+
+// C[t] (128 x N) = A[t] (128 x K) . B (K x N) for t < tiles.  K % 8 == 0, N <= 64.
+extern "C" int hgb_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t tiles, int32_t K, int32_t N,
+                                    void* stream) {
+  HGB_CHECK_ARG(A && B && C, "hgb_tc_gemm_selftest: NULL argument");
+  HGB_CHECK_ARG(K > 0 && K % 8 == 0, "hgb_tc_gemm_selftest: K=%d must be a positive multiple of 8", K);
+  HGB_CHECK_ARG(N > 0 && N <= 64, "hgb_tc_gemm_selftest: N=%d out of range (1..64)", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N <= 16) return launch<16>(A, B, C, tiles, K, N, st);
+  if (N <= 32) return launch<32>(A, B, C, tiles, K, N, st);
+  if (N <= 48) return launch<48>(A, B, C, tiles, K, N, st);
+  return launch<64>(A, B, C, tiles, K, N, st);
+}

@@ -167,6 +167,14 @@ int hgb_ham_finalize(const hgb_ham_plan* plan_host, const float* raw, const int6
                      const int64_t* z, const int64_t* node_a, const int64_t* node_b, const int64_t* out_row,
                      int64_t n_rows, int32_t symmetrize, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 3xTF32 GEMM building block (TMEM accumulator, interleaved K-major shared-memory
+ * operands): C[t] (128 x N) = A[t] (128 x K) . B (K x N), t < tiles; K % 8 == 0, N <= 64.  No reference
+ * counterpart -- it validates the tensor-core path that replaces the dense per-path contractions of
+ * o3.TensorProduct / o3.Linear (hamgnn/nn/message_passing.py:81-134) against a plain matmul.
+ */
+int hgb_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t tiles, int32_t K, int32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
