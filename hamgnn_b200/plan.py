@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -226,6 +227,8 @@ class KernelProfiler:
 
 
 PROFILER: Optional[KernelProfiler] = None
+# which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
+BACKEND = os.environ.get("HGB_MSGPACK", "simt")
 
 
 @dataclass
@@ -348,6 +351,7 @@ class MessagePackOp:
         self.n_channels = [mid.num_irreps for mid in self.mid]
         self.tp_numel = [sum(p.mul_in_total * p.mul_out for p in ps) for ps in self.paths_by_branch]
         self._build_pack_program()
+        self._build_tc_program()
         self._dev: Dict[str, dict] = {}
 
     # -------------------------------------------------------------------------------- packing program
@@ -382,6 +386,7 @@ class MessagePackOp:
             self.src_layout.append(("direct", 0, self.direct_blocks[1]))
             cur += self.direct_blocks[1]
         self.src_total = cur
+        self._src_base = base
 
         def add(d, s, sc):
             dst.append(np.asarray(d, dtype=np.int64).ravel())
@@ -495,11 +500,163 @@ class MessagePackOp:
             st["plan"] = plan
         return st, st["wbuf"]
 
+
+    # -------------------------------------------------------------------------------- tensor-core packing
+    def _build_tc_program(self):
+        """Tables + packing program of the tcgen05 kernel (csrc/msgpack_tc.cu): multiplicities padded to 16,
+        every operand stored as hi|lo images in the UMMA interleaved K-major layout
+        image[(k/4) * N * 4 + n * 4 + k % 4] with N = padded multiplicity (rows of the B operand)."""
+        KCH = 32
+        base = self._src_base
+        sh_offs = self.irreps_sh.offsets()
+        out_offs = self.irreps_out.offsets()
+        in_offs_by_branch = [br.irreps_in.offsets() for br in self.branches]
+        dst, src, scale, part = [], [], [], []
+
+        def add(d, s_, sc, pt):
+            d = np.asarray(d, dtype=np.int64).ravel()
+            dst.append(d)
+            src.append(np.asarray(s_, dtype=np.int64).ravel())
+            scale.append(np.broadcast_to(np.asarray(sc, dtype=np.float32), d.shape).ravel())
+            part.append(np.full(d.shape, pt, dtype=np.int8))
+
+        def add_image(img0, N, kk, nn, srcidx, sc, kc):
+            """operand element (k=kk, n=nn) of an image with kc K-columns starting at float offset img0."""
+            off = (kk // 4) * (N * 4) + nn * 4 + (kk % 4)
+            add(img0 + off, srcidx, sc, 0)
+            add(img0 + N * kc + off, srcidx, sc, 1)
+
+        wcur = 0
+        self.tc_fc1_off, self.tc_fc2_off = [], []
+        for b in range(len(self.branches)):
+            n1, n2 = self.rbf_dim * self.h1, self.h1 * self.h2
+            self.tc_fc1_off.append(wcur)
+            add(wcur + np.arange(n1), base[("fc0", b)] + np.arange(n1), 1.0 / math.sqrt(self.rbf_dim), 2)
+            wcur += n1
+            self.tc_fc2_off.append(wcur)
+            add(wcur + np.arange(n2), base[("fc1", b)] + np.arange(n2), 1.0 / math.sqrt(self.h1), 2)
+            wcur += n2
+        # reuse the CG tables of the SIMT plan (offsets are identical)
+        types = (L.TypeT * len(self.irreps_out))()
+        plist = []
+        simt_iter = iter(range(self.n_paths))
+        for t, m in enumerate(self.irreps_out):
+            mp = (m.mul + 15) // 16 * 16
+            begin = len(plist)
+            for b, br in enumerate(self.branches):
+                tpaths = [p for p in self.paths_by_branch[b] if p.ir_out == m.ir]
+                ch_type0 = tpaths[0].ch_off if tpaths else 0
+                for p in tpaths:
+                    sp = self.paths_c[next(simt_iter)]
+                    K, M = p.mul_in_total, p.mul_out
+                    Kpad = (K + 7) // 8 * 8
+                    w_off = wcur
+                    coef = math.sqrt(p.ir_out.dim / K)
+                    for c, u0 in enumerate(range(0, Kpad, KCH)):
+                        kc = min(KCH, Kpad - u0)
+                        ku = np.arange(u0, min(u0 + kc, K))
+                        if len(ku):
+                            kk, nn = np.meshgrid(ku, np.arange(M), indexing="ij")
+                            add_image(w_off + 2 * mp * KCH * c, mp, kk - u0, nn, base[("tp", b)] + p.w_off + kk * M + nn, coef, kc)
+                    wcur += 2 * mp * Kpad
+                    w3_off = wcur
+                    hh, nn = np.meshgrid(np.arange(self.h2), np.arange(M), indexing="ij")
+                    add_image(w3_off, mp, hh, nn, base[("fc2", b)] + hh * self.n_channels[b] + p.ch_off + nn,
+                              1.0 / math.sqrt(self.h2), self.h2)
+                    wcur += 2 * mp * self.h2
+                    lf_off = wcur
+                    f0, rows, Mt = self.f_slices[(b, t)]
+                    ww, wo = np.meshgrid(np.arange(M), np.arange(Mt), indexing="ij")   # k = w (row of L'), n = w'
+                    add_image(lf_off, mp, ww, wo, base[("F", b)] + f0 + (p.ch_off - ch_type0 + ww) * Mt + wo, 1.0, mp)
+                    wcur += 2 * mp * mp
+                    plist.append(L.PathT(0, b, br.src0, br.nsrc, sp.in_off, sp.mul_in, sp.l1, sp.l2, sp.l3, sp.sh_off,
+                                         sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, 0))
+            if self.direct_src is not None:
+                sp = self.paths_c[next(simt_iter)]
+                bl = [x for x in self.direct_blocks[0] if x.i_out == t][0]
+                K = bl.mul_in
+                Kpad = (K + 7) // 8 * 8
+                lf_off = wcur
+                for c, u0 in enumerate(range(0, Kpad, KCH)):
+                    kc = min(KCH, Kpad - u0)
+                    ku = np.arange(u0, min(u0 + kc, K))
+                    if len(ku):
+                        kk, nn = np.meshgrid(ku, np.arange(bl.mul_out), indexing="ij")
+                        add_image(lf_off + 2 * mp * KCH * c, mp, kk - u0, nn, base[("direct", 0)] + bl.w_off + kk * bl.mul_out + nn,
+                                  bl.scale, kc)
+                wcur += 2 * mp * Kpad
+                plist.append(L.PathT(1, 0, self.direct_src, 1, sp.in_off, sp.mul_in, sp.l1, 0, sp.l3, 0, 0, 0, 0, 0, lf_off, 0))
+            types[t] = L.TypeT(m.mul, mp, m.ir.l, out_offs[t], begin, len(plist), 0, 0)
+        self.tc_w_total = wcur
+        self.tc_types_c = types
+        self.tc_paths_c = (L.PathT * max(1, len(plist)))(*plist)
+        self._tc_dst = np.concatenate(dst)
+        self._tc_src = np.concatenate(src)
+        self._tc_scale = np.concatenate(scale)
+        self._tc_part = np.concatenate(part)
+
+    def tc_supported(self) -> bool:
+        return (max((m.mul for m in self.irreps_out), default=0) <= 64 and self.h2 % 16 == 0 and self.h2 <= 64
+                and self.h1 <= 64 and len(self.irreps_out) <= 32)
+
+    def pack_tc(self, weights: dict) -> dict:
+        dev = weights["tp"][0].device
+        st = self._device_state(dev)
+        allp = [*weights["tp"], *[w for fc in weights["fc"] for w in fc], *weights["lin_mid"],
+                *[w for w in weights["lin_out"] if w is not None]]
+        if weights.get("direct") is not None:
+            allp.append(weights["direct"])
+        ver = tuple((p._version, p.data_ptr()) for p in allp)
+        if st.get("tc_ver") != ver:
+            if "tc_dst" not in st:
+                st["tc_types"] = torch.from_numpy(np.frombuffer(bytes(self.tc_types_c), dtype=np.uint8).copy()).to(dev)
+                st["tc_paths"] = torch.from_numpy(np.frombuffer(bytes(self.tc_paths_c), dtype=np.uint8).copy()).to(dev)
+                st["tc_dst"] = torch.from_numpy(self._tc_dst).to(dev)
+                st["tc_src"] = torch.from_numpy(self._tc_src).to(dev)
+                st["tc_scale"] = torch.from_numpy(self._tc_scale).to(dev)
+                st["tc_part"] = torch.from_numpy(self._tc_part).to(dev)
+            with torch.no_grad():
+                parts = []
+                for b in range(len(self.branches)):
+                    parts += [weights["tp"][b].reshape(-1), weights["fc"][b][0].reshape(-1), weights["fc"][b][1].reshape(-1),
+                              weights["fc"][b][2].reshape(-1), self._fold(b, weights["lin_mid"][b], weights["lin_out"][b])]
+                if self.direct_src is not None:
+                    parts.append(weights["direct"].reshape(-1))
+                cat = torch.cat(parts).float()
+                vals = cat[st["tc_src"]] * st["tc_scale"]
+                hi = (vals.view(torch.int32) & -8192).view(torch.float32)          # top 19 bits (tf32 payload)
+                lo = vals - hi
+                pt = st["tc_part"]
+                packed = torch.where(pt == 0, hi, torch.where(pt == 1, lo, vals))
+                wbuf = torch.zeros(self.tc_w_total, device=dev, dtype=torch.float32)
+                wbuf.index_copy_(0, st["tc_dst"], packed)
+            st["tc_wbuf"] = wbuf
+            st["tc_ver"] = ver
+            plan = L.MsgpackPlan()
+            plan.n_types, plan.n_paths = len(self.irreps_out), self.n_paths
+            plan.n_branches, plan.n_sources = len(self.branches), len(self.src_dims)
+            plan.sh_dim, plan.rbf_dim, plan.h1, plan.h2 = self.irreps_sh.dim, self.rbf_dim, self.h1, self.h2
+            plan.out_dim = self.irreps_out.dim
+            for q, d in enumerate(self.src_dims):
+                plan.src_dim[q] = d
+            for b in range(len(self.branches)):
+                plan.fc1_off[b] = self.tc_fc1_off[b]
+                plan.fc2_off[b] = self.tc_fc2_off[b]
+            plan.act_const = so3.normalize2mom_const("silu")
+            plan.types, plan.paths = st["tc_types"].data_ptr(), st["tc_paths"].data_ptr()
+            plan.types_host = C.cast(self.tc_types_c, C.c_void_p).value
+            plan.paths_host = C.cast(self.tc_paths_c, C.c_void_p).value
+            plan.cg_ij, plan.cg_val, plan.cg_kstart = st["cg_ij"].data_ptr(), st["cg_val"].data_ptr(), st["cg_ks"].data_ptr()
+            plan.wbuf = wbuf.data_ptr()
+            st["tc_plan"] = plan
+        return st
+
     def forward(self, weights: dict, sources: Sequence[torch.Tensor], rows: Sequence[Optional[torch.Tensor]],
                 sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
                 out_index: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
-        st, _ = self.pack(weights)
+        use_tc = (BACKEND == "tc") and self.tc_supported()
+        st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
         assert len(sources) == ns and len(rows) == ns
         srcs = (C.c_void_p * 4)(*[L.f32c(s).data_ptr() for s in sources] + [None] * (4 - ns))
@@ -509,11 +666,17 @@ class MessagePackOp:
         prof = PROFILER
         if prof is not None:
             prof.begin(self, int(n_edges), out.device)
-        rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
-                                          int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
+        if use_tc:
+            h2 = torch.empty(len(self.branches) * int(n_edges) * self.h2, device=out.device, dtype=torch.float32)
+            rc = L.load().hgb_msgpack_tc_forward(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
+                                                 h2.data_ptr(), int(n_edges), out.data_ptr(), L.ptr(out_index),
+                                                 L.stream_ptr(out.device))
+        else:
+            rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
+                                              int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
         if prof is not None:
             prof.end(out.device)
-        L.check(rc, "hgb_msgpack_forward")
+        L.check(rc, "hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward")
         return out
 
     # FLOP / byte accounting for bench.py (per edge, algorithmic minimum of this formulation)

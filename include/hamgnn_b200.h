@@ -107,6 +107,14 @@ int hgb_msgpack_forward(const hgb_msgpack_plan* plan_host, const float* const* s
                         const int64_t* const* src_rows_host, const float* sh, const float* rbf,
                         int64_t n_edges, float* out, const int64_t* out_index, void* stream);
 
+/* Same operation on the tcgen05 tensor cores (3xTF32, fp32-accurate; csrc/msgpack_tc.cu).  `plan->wbuf` holds
+ * the tensor-core packing (hi|lo operand images in the UMMA interleaved K-major layout, multiplicities padded to
+ * 16 in plan->types[].mpad); h2_ws is a device workspace of n_branches * n_edges * h2 floats for the radial-MLP
+ * hidden activations.  Replaces the same reference functions as hgb_msgpack_forward. */
+int hgb_msgpack_tc_forward(const hgb_msgpack_plan* plan_host, const float* const* src_host,
+                           const int64_t* const* src_rows_host, const float* sh, const float* rbf, float* h2_ws,
+                           int64_t n_edges, float* out, const int64_t* out_index, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].
  * Replaces o3.Linear call sites (hamgnn/nn/convolution.py:112, interaction_blocks.py:126,306-309,
@@ -169,11 +177,13 @@ int hgb_ham_finalize(const hgb_ham_plan* plan_host, const float* raw, const int6
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 GEMM building block (TMEM accumulator, interleaved K-major shared-memory
- * operands): C[t] (128 x N) = A[t] (128 x K) . B (K x N), t < tiles; K % 8 == 0, N <= 64.  No reference
+ * operands, or A staged in TMEM when a_from_tmem != 0): C[t] (128 x N) = A[t] (128 x K) . B (K x N), t < tiles;
+ * K % 8 == 0, N <= 64.  No reference
  * counterpart -- it validates the tensor-core path that replaces the dense per-path contractions of
  * o3.TensorProduct / o3.Linear (hamgnn/nn/message_passing.py:81-134) against a plain matmul.
  */
-int hgb_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t tiles, int32_t K, int32_t N, void* stream);
+int hgb_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t tiles, int32_t K, int32_t N,
+                         int32_t a_from_tmem, void* stream);
 
 #ifdef __cplusplus
 }

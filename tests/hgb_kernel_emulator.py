@@ -119,3 +119,64 @@ def emulate_ham(asm: HamAssembly, coef, partner, h0, z, na, nb, symmetrize=True)
     za = z if na is None else z[na]
     zb = z if nb is None else z[nb]
     return (m * mask[za][:, :, None] * mask[zb][:, None, :]).reshape(-1, nn2)
+
+
+def _decode_image(wbuf, off, N, kc):
+    """hi|lo operand image (UMMA interleaved K-major, N rows, kc K-columns) -> dense [kc, N] fp32 (hi + lo)."""
+    k = torch.arange(kc)[:, None]
+    n = torch.arange(N)[None, :]
+    idx = (k // 4) * (N * 4) + n * 4 + (k % 4)
+    hi = wbuf[off + idx]
+    lo = wbuf[off + N * kc + idx]
+    # hi must be representable in tf32 (13 low mantissa bits clear)
+    assert int((hi.float().view(torch.int32) & 8191).abs().max()) == 0
+    return hi + lo
+
+
+def emulate_msgpack_tc(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, sh, rbf, out_rows=None, n_out=None):
+    """Mirrors msgpack_tc_kernel's arithmetic from the tensor-core packing (tc_types_c / tc_paths_c / tc wbuf)."""
+    from hamgnn_b200 import so3
+    E = sh.shape[0]
+    dt = wbuf.dtype
+    D = op.irreps_out.dim
+    msg = torch.zeros(E, D, dtype=dt)
+    act = so3.normalize2mom_const("silu")
+    h2 = []
+    for b in range(len(op.branches)):
+        w1 = wbuf[op.tc_fc1_off[b]:op.tc_fc1_off[b] + op.rbf_dim * op.h1].view(op.rbf_dim, op.h1)
+        w2 = wbuf[op.tc_fc2_off[b]:op.tc_fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
+        h2.append(_silu(_silu(rbf @ w1) * act @ w2) * act)
+    gathered = [s if r is None else s[r] for s, r in zip(sources, rows)]
+    for t in range(len(op.irreps_out)):
+        ty = op.tc_types_c[t]
+        assert ty.mpad % 16 == 0
+        d3 = 2 * ty.l + 1
+        acc = torch.zeros(E, d3, ty.mpad, dtype=dt)
+        for p in range(ty.path_begin, ty.path_end):
+            pa = op.tc_paths_c[p]
+            d1 = 2 * pa.l1 + 1
+            K = pa.nsrc * pa.mul_in
+            Kpad = (K + 7) // 8 * 8
+            x = torch.cat([gathered[pa.src0 + s][:, pa.in_off:pa.in_off + pa.mul_in * d1] for s in range(pa.nsrc)], dim=1)
+            x = torch.nn.functional.pad(x.reshape(E, K, d1), (0, 0, 0, Kpad - K))
+            woff = pa.w_off if pa.kind == 0 else pa.lf_off
+            W = torch.cat([_decode_image(wbuf, woff + 2 * ty.mpad * 32 * c, ty.mpad, min(32, Kpad - u0))
+                           for c, u0 in enumerate(range(0, Kpad, 32))], dim=0)
+            if pa.kind == 0:
+                T = torch.zeros(E, d1, d3, dtype=dt)
+                ks = op.cg_ks[pa.cg_kstart:pa.cg_kstart + d3 + 1]
+                for k in range(d3):
+                    for n in range(ks[k], ks[k + 1]):
+                        ij = int(op.cg_ij[pa.cg_off + n])
+                        T[:, ij & 255, k] += float(op.cg_val[pa.cg_off + n]) * sh[:, pa.sh_off + (ij >> 8)]
+                A = torch.einsum("zui,zik->zku", x, T)
+                W3 = _decode_image(wbuf, pa.w3_off, ty.mpad, op.h2)
+                Lf = _decode_image(wbuf, pa.lf_off, ty.mpad, ty.mpad)      # [k = w, n = w']
+                g = h2[pa.branch] @ W3
+                acc += ((A @ W) * g[:, None, :]) @ Lf
+            else:
+                acc += x.transpose(1, 2) @ W
+        msg[:, ty.out_off:ty.out_off + ty.mul * d3] = acc[:, :, :ty.mul].transpose(1, 2).reshape(E, ty.mul * d3)
+    if out_rows is None:
+        return msg
+    return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)

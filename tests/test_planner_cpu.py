@@ -129,3 +129,36 @@ def test_ham_assembly(small):
     H[on_row] = got_on
     H[off_row] = got_off
     assert rel_err(H, ref) < 1e-6
+
+
+def test_tensor_core_packing_matches_oracle(small):
+    """The hi|lo operand images consumed by the tcgen05 kernel decode to the same operator as the oracle."""
+    pre, out, opre, oout, g, d, rep, res = small
+    torch.manual_seed(6)
+    E, N, D = g.edge_index.shape[1], g.num_nodes, pre.irreps_node_features.dim
+    x, e = torch.randn(N, D).double(), torch.randn(E, D).double()
+    dd = {"edge_index": g.edge_index, "node_features": x, "edge_features": e, "edge_attrs": d["edge_attrs"],
+          "edge_embedding": d["edge_embedding"]}
+    s, r = g.edge_index
+    with torch.no_grad():
+        ref_pair = opre.pair_interactions[1](dict(dd))
+        ref_msg = opre.convolutions[0].conv_tp(x[s], x[r], e, d["edge_attrs"], d["edge_embedding"])
+    pb = pre.pair_interactions[1]
+    xs = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_src.weight), x)
+    xt = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_tar.weight), x)
+    st = pb.conv_tp.op.pack_tc(pb.conv_tp.weights(pb.skip_linear.weight))
+    got = EM.emulate_msgpack_tc(pb.conv_tp.op, st["tc_wbuf"].double(), [xs, xt, e], [s, r, None], d["edge_attrs"], d["edge_embedding"])
+    assert rel_err(got, ref_pair) < 2e-6
+    cb = pre.convolutions[0].conv_tp
+    st = cb.op.pack_tc(cb.weights())
+    got = EM.emulate_msgpack_tc(cb.op, st["tc_wbuf"].double(), [x, x, e], [s, r, None], d["edge_attrs"], d["edge_embedding"])
+    assert rel_err(got, ref_msg) < 2e-6
+    pe = pre.pair_embedding
+    onehot = torch.nn.functional.one_hot(g.z, opre.num_types).double()
+    h = EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_src.weight), onehot[s]) + EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_dst.weight), onehot[r])
+    st = pe.conv_tp.op.pack_tc(pe.conv_tp.weights())
+    got = EM.emulate_msgpack_tc(pe.conv_tp.op, st["tc_wbuf"].double(), [h], [None], d["edge_attrs"], d["edge_embedding"])
+    dd2 = dict(dd); dd2["node_features"] = onehot
+    with torch.no_grad():
+        ref_emb = opre.pair_embedding(dd2)
+    assert rel_err(got, ref_emb) < 2e-6
