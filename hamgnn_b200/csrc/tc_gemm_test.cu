@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ 
     tc::mbar_init(&mbar, 1);
     tc::mbar_fence_init();
   }
-  constexpr int TCOLS = (MODE == 0) ? (NPAD < 32 ? 32 : NPAD) : 256;  // TS: D at col 0, A_hi at 64, A_lo at 128
+  constexpr int TCOLS = (MODE == 0) ? (NPAD <= 32 ? 32 : 64) : 256;  // power of two >= 32  // TS: D at col 0, A_hi at 64, A_lo at 128
   if (warp == 0) tc::tmem_alloc<TCOLS>(&tmem_base);
   // stage + split A: element (r, k) -> (k/4)*(128*4) + r*4 + k%4
   for (int idx = tid; idx < TM * K; idx += 128) {
