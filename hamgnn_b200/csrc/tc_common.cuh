@@ -69,9 +69,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Bounded wait: a tensor-core pipeline bug must surface as a kernel error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = smem_u32(mbar);
   uint32_t done;
+  const long long t0 = clock64();
   do {
     asm volatile(
         "{\n\t"
@@ -82,6 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
   } while (!done);
 }
 
