@@ -6,7 +6,7 @@
 // with SBO = 128 (8-row groups contiguous) and LBO = rows * 16 (one K-slab of 4 columns for all rows).
 // One tcgen05.mma.kind::tf32 consumes K = 8 (two K-slabs).
 //
-// fp32 accuracy on the tf32 pipe: every operand is split a = hi + lo (hi = top 19 bits, lo = exact remainder)
+// fp32 accuracy on the tf32 pipe: every operand is split a = hi + lo (hi = a rounded to tf32, lo = the rounded remainder)
 // and three MMAs accumulate lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator ("3xTF32").
 #pragma once
 #include <cuda_runtime.h>
@@ -16,11 +16,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// ---- operand split
-__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xffffe000u); }
+// ---- operand split: hi = round-to-nearest tf32(a), lo = round-to-nearest tf32(a - hi).  |lo| <= 2^-11 |a|, so the
+// dropped lo*lo term and the residual of lo are both O(2^-22 |a b|) ~ 2.4e-7 relative per product.
+__device__ __forceinline__ float tf32_rn(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
-  hi = tf32_hi(a);
-  lo = a - hi;
+  hi = tf32_rn(a);
+  lo = tf32_rn(a - hi);
 }
 
 // ---- descriptors

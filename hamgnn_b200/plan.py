@@ -203,6 +203,12 @@ class GateLayout:
 
 
 # ====================================================================================== MessagePack
+def _tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to the nearest tf32 (10-bit mantissa), ties away from zero like `cvt.rna.tf32.f32`."""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & -8192).view(torch.float32)
+
+
 class KernelProfiler:
     """CUDA-event bracket around every fused-message launch (bench.py's live roofline measurement); events
     are recorded on the stream the kernel is launched on."""
@@ -624,8 +630,8 @@ class MessagePackOp:
                     parts.append(weights["direct"].reshape(-1))
                 cat = torch.cat(parts).float()
                 vals = cat[st["tc_src"]] * st["tc_scale"]
-                hi = (vals.view(torch.int32) & -8192).view(torch.float32)          # top 19 bits (tf32 payload)
-                lo = vals - hi
+                hi = _tf32_round(vals)                                              # round-to-nearest tf32
+                lo = _tf32_round(vals - hi)
                 pt = st["tc_part"]
                 packed = torch.where(pt == 0, hi, torch.where(pt == 1, lo, vals))
                 wbuf = torch.zeros(self.tc_w_total, device=dev, dtype=torch.float32)

@@ -4,8 +4,9 @@
 set -x
 TAG=${1:-r01c}
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -s -k tensor_core > gpurun_out/${TAG}_tc_parity.log 2>&1; tail -12 gpurun_out/${TAG}_tc_parity.log | cut -c1-400
-if grep -q "passed" gpurun_out/${TAG}_tc_parity.log && ! grep -q "failed" gpurun_out/${TAG}_tc_parity.log; then
+timeout 150 python -m pytest tests/test_gpu_parity.py -q -s -k tensor_core > gpurun_out/${TAG}_tc_parity.log 2>&1; tail -12 gpurun_out/${TAG}_tc_parity.log | cut -c1-400
+grep -E "rel err|passed|failed" gpurun_out/${TAG}_tc_parity.log | cut -c1-300
+if grep -q "passed" gpurun_out/${TAG}_tc_parity.log; then
   HGB_MSGPACK=tc timeout 120 python bench.py --steps 3 --warmup 3 --workload tbg_m8 --no-cpu-baseline > gpurun_out/${TAG}_bench_m8_tc.json 2> gpurun_out/${TAG}_bench_m8_tc.err; cut -c1-400 gpurun_out/${TAG}_bench_m8_tc.json; tail -3 gpurun_out/${TAG}_bench_m8_tc.err
   HGB_MSGPACK=tc timeout 300 python bench.py --steps 3 --warmup 3 --workload tbg_m28 > gpurun_out/${TAG}_bench_m28_tc.json 2> gpurun_out/${TAG}_bench_m28_tc.err; cut -c1-1800 gpurun_out/${TAG}_bench_m28_tc.json; tail -3 gpurun_out/${TAG}_bench_m28_tc.err
   HGB_MSGPACK=tc timeout 400 ncu --set full --clock-control none --import-source on -k regex:msgpack_tc -s 8 -c 1 -f -o gpurun_out/${TAG}_msgpack_tc_full \
