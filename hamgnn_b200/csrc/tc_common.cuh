@@ -36,6 +36,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); layout_type 0 = SWIZZLE_NONE, base_offset 0
   return d;
 }
+// Descriptors of one operand differ only in the 14-bit start-address field: build the constant part once and add
+// (byte offset >> 4) to the low word per MMA (what CUTLASS' DescriptorIterator does).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_tf32_m128(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
@@ -91,6 +98,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
         : "memory");
     if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
   } while (!done);
+}
+
+// CTA-wide wait: one lane polls the mbarrier, everybody else parks in bar.sync (no issue slots burnt by spinning).
+__device__ __forceinline__ void cta_wait(uint64_t* mbar, uint32_t parity) {
+  if (threadIdx.x == 0) mbar_wait(mbar, parity);
+  __syncthreads();
 }
 
 // ---- TMEM

@@ -132,7 +132,9 @@ class LinearOp:
         if ent["ver"] != ver:
             ent["w"] = (weight.detach() * ent["scale"]).contiguous()
             ent["ver"] = ver
-            ent["plan"] = L.LinearPlan(len(self.blocks), self.irreps_in.dim, self.irreps_out.dim, 0,
+            outs = [b.i_out for b in self.blocks]
+            disjoint = 1 if len(set(outs)) == len(outs) else 0   # bit 0 of `pad`: every block owns its output slot
+            ent["plan"] = L.LinearPlan(len(self.blocks), self.irreps_in.dim, self.irreps_out.dim, disjoint,
                                        ent["blocks"].data_ptr(), ent["w"].data_ptr())
         return ent["plan"]
 

@@ -127,7 +127,8 @@ typedef struct {
 } hgb_linblock_t;
 
 typedef struct {
-  int32_t n_blocks, in_dim, out_dim, pad;
+  int32_t n_blocks, in_dim, out_dim;
+  int32_t pad;                   /* bit 0: every block writes its own output slot (single-pass evaluation) */
   const hgb_linblock_t* blocks;  /* device */
   const float* w;                /* device, pre-scaled by 1/sqrt(fan_in) */
 } hgb_linear_plan;
