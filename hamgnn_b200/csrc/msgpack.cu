@@ -20,6 +20,8 @@
 // thread-tile, A operand K-major in shared memory so that a float4 covers 4 rows, weights read as
 // warp-uniform float4 through the read-only path).  fp32 FMA throughout: the 1e-5 parity bar rules out
 // single-pass TF32/BF16 tensor-core products (SURVEY.md section 7 "Hard parts").
+#include <stdlib.h>
+
 #include "hgb_common.cuh"
 
 namespace {
@@ -374,7 +376,9 @@ extern "C" int hgb_msgpack_forward(const hgb_msgpack_plan* plan, const float* co
   HGB_CHECK_ARG(plan->sh_dim <= 84, "hgb_msgpack_forward: sh_dim=%d too large", plan->sh_dim);
   HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_msgpack_forward: bad edge count");
   HGB_CHECK_ARG(plan->types_host && plan->paths_host, "hgb_msgpack_forward: host copies of the type/path tables are required");
-  constexpr int TE = 32, RMAX = 128, NT = 256;
+  // tile configuration: 32 edges x 128 rows x 256 threads (2 CTAs/SM) or, with HGB_SIMT_TILE=64, 64 x 256 x 512
+  static const bool big_tile = [] { const char* e = getenv("HGB_SIMT_TILE"); return e && atoi(e) == 64; }();
+  const int TE = big_tile ? 64 : 32, RMAX = big_tile ? 256 : 128;
   for (int t = 0; t < plan->n_types; ++t) {
     const hgb_type_t& ty = plan->types_host[t];
     const int d3 = 2 * ty.l + 1;
@@ -409,5 +413,5 @@ extern "C" int hgb_msgpack_forward(const hgb_msgpack_plan* plan, const float* co
     a.src_rows[s] = src_rows ? src_rows[s] : nullptr;
   }
   a.sh = sh; a.rbf = rbf; a.n_edges = n_edges; a.out = out; a.out_index = out_index;
-  return launch<TE, RMAX, NT>(a, (cudaStream_t)stream);
+  return big_tile ? launch<64, 256, 512>(a, (cudaStream_t)stream) : launch<32, 128, 256>(a, (cudaStream_t)stream);
 }

@@ -16,8 +16,8 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// ---- operand split: hi = round-to-nearest tf32(a), lo = round-to-nearest tf32(a - hi).  |lo| <= 2^-11 |a|, so the
-// dropped lo*lo term and the residual of lo are both O(2^-22 |a b|) ~ 2.4e-7 relative per product.
+// ---- operand split: hi = round-to-nearest tf32(a), lo = a - hi (exact).  |lo| <= 2^-11 |a|, so the dropped lo*lo
+// term and the truncation of lo inside the tensor core are both O(2^-22 |a b|) ~ 2.4e-7 relative per product.
 __device__ __forceinline__ float tf32_rn(float a) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
@@ -25,7 +25,7 @@ __device__ __forceinline__ float tf32_rn(float a) {
 }
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = tf32_rn(a);
-  lo = tf32_rn(a - hi);
+  lo = a - hi;  // exact; |lo| <= 2^-11 |a|, the tensor core drops its bits below tf32 (<= 2^-22 |a|)
 }
 
 // ---- descriptors
