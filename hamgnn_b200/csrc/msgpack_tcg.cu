@@ -1,0 +1,547 @@
+// Fused MessagePackBlock forward on tcgen05, variant "tcg": the radial gate g[e][c] = h2[e] . W3[:, c] is produced
+// once per call by `radial_gate_kernel` (one [E, n_channels] fp32 tensor per branch, written once and read once),
+// so the message kernel needs neither the G' MMA nor the hidden activations in TMEM.  That shrinks the TMEM
+// footprint to 3 regions  C | B -> (B*g)hi | (B*g)lo  (96 or 192 columns) and the shared-memory footprint below
+// 113 KB, i.e. TWO CTAs per SM for every slot class -- the measured bottleneck of msgpack_tc_kernel was exposed
+// latency with one (or two) resident CTAs, not tensor or FMA throughput (profiles/r01g_*).
+//
+// Everything else (tables, packing, A-operand generation, 3xTF32 split, GEMM1 / GEMM2 structure) is identical to
+// msgpack_tc.cu.  Price: 2 x 4 B x n_channels (28.7 KB) of extra HBM write + read per message.
+#include "hgb_common.cuh"
+#include "tc_common.cuh"
+#include "msgpack_tc_helpers.cuh"
+
+namespace {
+using namespace tcmsg;
+
+constexpr int KCH = 32;
+constexpr int NMAX = 64;
+
+struct TgArgs {
+  hgb_msgpack_plan plan;
+  const float* src[4];
+  const int64_t* src_rows[4];
+  const float* sh;
+  const float* g;       // [n_branches][E][gstride]
+  int64_t n_edges;
+  int gstride;
+  float* out;
+  const int64_t* out_index;
+  int tile_start[33];
+  int type_order[32];
+  int n_sched;
+};
+
+template <int RW>
+struct TmG {
+  static constexpr uint32_t C = 0, B = RW, BGH = RW, BGL = 2 * RW;
+  static constexpr int COLS = (RW == 32) ? 128 : 256;
+};
+
+template <int RW>
+struct SmemG {
+  static constexpr int XBLK = (RW == 64) ? 6144 : 4096;
+  static constexpr int TBLK = (RW == 64) ? 1536 : 3072;   // RW = 64 serves d3 == 1 (compact T: 128 * d1 floats, l1 <= 5)
+  static constexpr int A = 0;
+  static constexpr int W = A + 2 * 8 * ROWS * 4;
+  static constexpr int L = W + 2 * RW * KCH;
+  static constexpr int X = L + 2 * RW * RW;
+  static constexpr int T = X + XBLK;
+  static constexpr int ROW = T + TBLK;
+  static constexpr int TOTAL = ROW + 4 * ROWS;
+};
+
+// d3 == 1 specialisation of the A-operand generator with a compact T (one float per (z, i))
+template <int NT>
+__device__ __forceinline__ void agen_d3_1(float* __restrict__ sA, const float* __restrict__ sX, int ldx, int cc,
+                                          const float* __restrict__ sT, int d1, int nz, uint32_t mz, int slab0,
+                                          int nquad) {
+  for (int item = threadIdx.x; item < nz * nquad; item += NT) {
+    const int q = (int)fdiv((uint32_t)item, mz), z = item - q * nz;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xz = sX + (size_t)z * ldx + q * 4;
+    const float* tz = sT + (size_t)z * d1;
+    for (int i = 0; i < d1; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(xz + i * cc);
+      const float t = tz[i];
+      acc.x = fmaf(x.x, t, acc.x); acc.y = fmaf(x.y, t, acc.y); acc.z = fmaf(x.z, t, acc.z); acc.w = fmaf(x.w, t, acc.w);
+    }
+    float4 h, l;
+    tc::split_tf32(acc.x, h.x, l.x); tc::split_tf32(acc.y, h.y, l.y);
+    tc::split_tf32(acc.z, h.z, l.z); tc::split_tf32(acc.w, h.w, l.w);
+    float* hi = sA + (size_t)(slab0 + q) * (ROWS * 4) + (size_t)z * 4;
+    *reinterpret_cast<float4*>(hi) = h;
+    *reinterpret_cast<float4*>(hi + 8 * ROWS * 4) = l;
+  }
+}
+
+template <int RW, int NT>
+__global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constant__ TgArgs a) {
+  using SM = SmemG<RW>;
+  constexpr int WPQ = NT / 128;
+  constexpr int NGRP = (RW / 8 + WPQ - 1) / WPQ;  // 8-column groups per warp in the epilogues
+  constexpr int XBLK = SM::XBLK;
+  constexpr uint32_t TC_C = TmG<RW>::C, TC_B = TmG<RW>::B, TC_BGH = TmG<RW>::BGH, TC_BGL = TmG<RW>::BGL;
+  extern __shared__ __align__(128) float smem[];
+  float* sA = smem + SM::A;
+  float* sW = smem + SM::W;
+  float* sL = smem + SM::L;
+  float* sX = smem + SM::X;
+  float* sT = smem + SM::T;
+  int* sRow = reinterpret_cast<int*>(smem + SM::ROW);
+  __shared__ uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const hgb_msgpack_plan& P = a.plan;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ wbuf = P.wbuf;
+
+  int sq = 0;
+  while (sq + 1 < a.n_sched && (int)blockIdx.x >= a.tile_start[sq + 1]) ++sq;
+  const int t = a.type_order[sq];
+  const hgb_type_t ty = P.types[t];
+  const int d3 = 2 * ty.l + 1;
+  const int mp = ty.mpad;
+  const int nz_full = ROWS / d3;
+  const int64_t e0 = (int64_t)(blockIdx.x - a.tile_start[sq]) * nz_full;
+  const int nz = (int)min((int64_t)nz_full, a.n_edges - e0);
+  const int R = nz * d3;
+  const int S = P.sh_dim;
+
+  if (tid == 0) {
+    tc::mbar_init(&mbar[0], 1);
+    tc::mbar_init(&mbar[1], 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<TmG<RW>::COLS>(&tmem_slot);
+  for (int idx = tid; idx < P.n_sources * nz; idx += NT) {
+    const int s = idx / nz, z = idx - s * nz;
+    const int64_t e = e0 + z;
+    sRow[s * ROWS + z] = (int)(a.src_rows[s] ? a.src_rows[s][e] : e);
+  }
+  for (int idx = tid; idx < 2 * 8 * ROWS * 4; idx += NT) sA[idx] = 0.f;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int my_row = (warp & 3) * 32 + lane;
+  const bool live = my_row < R;
+  const int my_z = live ? my_row / d3 : 0;
+  const int wq = warp >> 2;
+  const uint32_t idesc = tc::idesc_tf32_m128(mp);
+  const uint32_t sbo = 128, lbo_a = ROWS * 16, lbo_n = (uint32_t)mp * 16;
+
+  uint32_t ph0 = 0, ph1 = 0;
+  bool pend0 = false, pend1 = false, c_started = false;
+  const uint32_t mz = fdiv_magic((uint32_t)nz), md3 = fdiv_magic_odd(ty.l);
+  const int xcap = XBLK / nz - 4;
+
+  for (int p = ty.path_begin; p < ty.path_end; ++p) {
+    const hgb_path_t pa = P.paths[p];
+    const int d1 = 2 * pa.l1 + 1;
+    const int K = pa.nsrc * pa.mul_in;
+    const int Kpad = (K + 7) & ~7;
+    if (pend1) { tc::cta_wait(&mbar[1], ph1); ph1 ^= 1; pend1 = false; tc::fence_after_sync(); }
+    if (pend0) { tc::cta_wait(&mbar[0], ph0); ph0 ^= 1; pend0 = false; tc::fence_after_sync(); }
+
+    if (pa.kind == 0) copy_f4<NT>(sL, wbuf + pa.lf_off, 2 * mp * mp);
+    // T_z: padded rows (stride ldt, ldt/4 odd) for d3 > 1, compact [z][i] for d3 == 1; Y is read from global (L1/L2)
+    const int d3p = (d3 + 3) & ~3;
+    int ldt = d1 * d3p;
+    if (((ldt >> 2) & 1) == 0) ldt += 4;
+    if (d3 == 1) {
+      for (int idx = tid; idx < nz * d1; idx += NT) sT[idx] = 0.f;
+      __syncthreads();
+      if (pa.kind == 0) {
+        const int n1 = P.cg_kstart[pa.cg_kstart + 1];
+        for (int idx = tid; idx < nz * n1; idx += NT) {
+          const int z = idx / n1, n = idx - z * n1;
+          const int ij = P.cg_ij[pa.cg_off + n];
+          atomicAdd(&sT[z * d1 + (ij & 255)], P.cg_val[pa.cg_off + n] * __ldg(a.sh + (e0 + z) * S + pa.sh_off + (ij >> 8)));
+        }
+      } else {
+        for (int z = tid; z < nz; z += NT) sT[z] = 1.f;  // d1 == d3 == 1
+      }
+    } else {
+      for (int idx = tid; idx < nz * d3; idx += NT) {
+        const int z = (int)fdiv((uint32_t)idx, md3), k = idx - z * d3;
+        float* tz = sT + (size_t)z * ldt;
+        for (int i = 0; i < d1; ++i) tz[i * d3p + k] = 0.f;
+        if (pa.kind == 0) {
+          const float* yz = a.sh + (e0 + z) * S + pa.sh_off;
+          const int n0 = P.cg_kstart[pa.cg_kstart + k], n1 = P.cg_kstart[pa.cg_kstart + k + 1];
+          for (int n = n0; n < n1; ++n) {
+            const int ij = P.cg_ij[pa.cg_off + n];
+            tz[(ij & 255) * d3p + k] += P.cg_val[pa.cg_off + n] * __ldg(yz + (ij >> 8));
+          }
+        } else {
+          tz[k * d3p + k] = 1.f;
+        }
+      }
+    }
+
+    // ---- GEMM1 in K chunks
+    int chunk = 0;
+    for (int u0 = 0; u0 < Kpad; u0 += KCH, ++chunk) {
+      const int kc = min(KCH, Kpad - u0);
+      if (pend0) { tc::cta_wait(&mbar[0], ph0); ph0 ^= 1; pend0 = false; tc::fence_after_sync(); }
+      const float* wimg = wbuf + (pa.kind == 0 ? pa.w_off : pa.lf_off) + (size_t)2 * mp * KCH * chunk;
+      copy_f4<NT>(sW, wimg, 2 * mp * kc);
+      const uint32_t md1 = fdiv_magic_odd(pa.l1);
+      int cch = (int)fdiv((uint32_t)xcap, md1) & ~3;
+      if (cch > kc) cch = kc;
+      for (int ua = u0; ua < u0 + kc; ua += cch) {
+        const int cc = min(cch, u0 + kc - ua);
+        int ldx = cc * d1;
+        if (((ldx >> 2) & 1) == 0) ldx += 4;
+        for (int z = warp; z < nz; z += NT / 32) {
+          float* xrow = sX + (size_t)z * ldx;
+          for (int sg = 0; sg < pa.nsrc; ++sg) {
+            const int ulo = max(ua, sg * pa.mul_in), uhi = min(min(ua + cc, (sg + 1) * pa.mul_in), K);
+            if (ulo >= uhi) continue;
+            const int sidx = pa.src0 + sg;
+            const float* gsrc = a.src[sidx] + (size_t)sRow[sidx * ROWS + z] * P.src_dim[sidx] + pa.in_off + (ulo - sg * pa.mul_in) * d1;
+            const int n = (uhi - ulo) * d1, cbase = ulo - ua;
+            for (int j = lane; j < n; j += 32) {
+              const int ul = (int)fdiv((uint32_t)j, md1), i = j - ul * d1;
+              cp_async4(xrow + i * cc + cbase + ul, gsrc + j);
+            }
+          }
+          const int upad = max(K, ua) - ua;
+          if (upad < cc)
+            for (int j = lane; j < (cc - upad) * d1; j += 32) {
+              const int ul = (int)fdiv((uint32_t)j, md1), i = j - ul * d1;
+              xrow[i * cc + upad + ul] = 0.f;
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (d3 == 1) agen_d3_1<NT>(sA, sX, ldx, cc, sT, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
+        else agen_tc_dispatch<NT>(d3, sA, sX, ldx, cc, sT, ldt, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
+        if (ua + cch < u0 + kc) __syncthreads();
+      }
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t dhi = tc::smem_desc_hi(sbo);
+        const uint32_t ah = tc::smem_desc_lo(tc::smem_u32(sA), lbo_a), al = ah + ((8 * ROWS * 4 * 4) >> 4);
+        const uint32_t wh = tc::smem_desc_lo(tc::smem_u32(sW), lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
+        const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
+        const uint32_t dcol = tmem + (pa.kind == 0 ? TC_B : TC_C);
+        const uint32_t acc0 = (pa.kind == 0) ? (uint32_t)(chunk > 0) : (uint32_t)(c_started || chunk > 0);
+        for (int k8 = 0; k8 < (kc >> 3); ++k8) {
+          const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
+          const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl = tc::desc64(wl + k8 * bstep, dhi);
+          tc::mma_tf32(dcol, dal, dbh, idesc, acc0 | (uint32_t)(k8 > 0));
+          tc::mma_tf32(dcol, dah, dbl, idesc, 1);
+          tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+        }
+        tc::mma_commit(&mbar[0]);
+      }
+      pend0 = true;
+    }
+    if (pa.kind != 0) { c_started = true; continue; }
+
+    // ---- gate: the radial gate of this path's channels is fetched while GEMM1 drains
+    float gv[NGRP][8];
+    {
+      const float* gp = a.g + ((size_t)pa.branch * a.n_edges + (size_t)(e0 + my_z)) * a.gstride + pa.pad0;
+#pragma unroll
+      for (int q = 0; q < NGRP; ++q) {
+        const int c0 = (wq + q * WPQ) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[q][j] = (live && c0 + j < ty.mul) ? __ldg(gp + c0 + j) : 0.f;
+      }
+    }
+    tc::cta_wait(&mbar[0], ph0); ph0 ^= 1; pend0 = false;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < NGRP; ++q) {
+      const int c0 = (wq + q * WPQ) * 8;
+      if (c0 < mp) {  // warp-uniform
+        uint32_t rb[8], hi[8], lo[8];
+        tc::tmem_ld8(tmem + lane_base + TC_B + c0, rb);
+        tc::tmem_ld_wait8(rb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float h, l;
+          tc::split_tf32(__uint_as_float(rb[j]) * gv[q][j], h, l);
+          hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
+        }
+        tc::tmem_st8(tmem + lane_base + TC_BGH + c0, hi);
+        tc::tmem_st8(tmem + lane_base + TC_BGL + c0, lo);
+      }
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t dhi = tc::smem_desc_hi(sbo);
+      const uint32_t lh = tc::smem_desc_lo(tc::smem_u32(sL), lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
+      const uint32_t kstep = (2 * lbo_n) >> 4;
+      for (int k8 = 0; k8 < (mp >> 3); ++k8) {
+        const uint64_t bh = tc::desc64(lh + k8 * kstep, dhi), bl = tc::desc64(ll + k8 * kstep, dhi);
+        tc::mma_tf32_ts(tmem + TC_C, tmem + TC_BGL + k8 * 8, bh, idesc, (uint32_t)(c_started || k8 > 0));
+        tc::mma_tf32_ts(tmem + TC_C, tmem + TC_BGH + k8 * 8, bl, idesc, 1);
+        tc::mma_tf32_ts(tmem + TC_C, tmem + TC_BGH + k8 * 8, bh, idesc, 1);
+      }
+      tc::mma_commit(&mbar[1]);
+    }
+    pend1 = true;
+    c_started = true;
+  }
+  if (pend1) { tc::cta_wait(&mbar[1], ph1); ph1 ^= 1; }
+  if (pend0) { tc::cta_wait(&mbar[0], ph0); ph0 ^= 1; }
+  tc::fence_after_sync();
+
+  {
+    const int z = my_z, k = live ? my_row - z * d3 : 0;
+    const int64_t e = e0 + z;
+    const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
+    float* o = a.out + orow * P.out_dim + ty.out_off + k;
+    for (int c0 = wq * 8; c0 < mp; c0 += WPQ * 8) {
+      if (c0 >= ty.mul) break;
+      uint32_t rc[8];
+      if (c_started) {
+        tc::tmem_ld8(tmem + lane_base + TC_C + c0, rc);
+        tc::tmem_ld_wait8(rc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rc[j] = 0u;
+      }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int w = c0 + j;
+          if (w < ty.mul) {
+            if (a.out_index) atomicAdd(o + w * d3, __uint_as_float(rc[j]));
+            else o[w * d3] = __uint_as_float(rc[j]);
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<TmG<RW>::COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// radial MLP, all three layers: g[b][e][c] = (act(act(rbf W1) W2) W3)[c], c < nch_b.  One CTA = 64 edges; the last
+// layer is a register-tiled SGEMM (4 rows x 8 columns per thread, K = h2) streamed over 128-column tiles of W3.
+struct GateArgs {
+  const float* rbf;
+  const float* w1[2];
+  const float* w2[2];
+  const float* w3[2];   // [h2][nch] row-major, pre-scaled
+  int nch[2];
+  float* g;             // [n_branches][E][gstride]
+  int64_t n_edges;
+  int n_branches, rbf_dim, h1, h2dim, gstride;
+  float act_const;
+};
+constexpr int GE = 64;    // edges per CTA
+constexpr int GN = 128;   // W3 column tile
+
+constexpr int GATE_SMEM_FLOATS = GE * 65 + 64 * (GE + 4) + 64 * GN;
+
+__global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant__ GateArgs a) {
+  extern __shared__ __align__(16) float gsm[];
+  float (*sH)[GE + 4] = reinterpret_cast<float (*)[GE + 4]>(gsm);                       // h2, K-major: sH[h][z]
+  float (*sB)[GN] = reinterpret_cast<float (*)[GN]>(gsm + 64 * (GE + 4));              // W3 tile
+  float (*sIn)[65] = reinterpret_cast<float (*)[65]>(gsm + 64 * (GE + 4) + 64 * GN);   // rbf tile, later h1
+  const int tid = threadIdx.x;
+  const int64_t e0 = (int64_t)blockIdx.x * GE;
+  const int ne = (int)min((int64_t)GE, a.n_edges - e0);
+  const int tx = tid & 15, ty = tid >> 4;  // 16 column groups of 8, 16 row groups of 4
+  for (int b = 0; b < a.n_branches; ++b) {
+    __syncthreads();
+    for (int idx = tid; idx < GE * a.rbf_dim; idx += 256) {
+      const int z = idx / a.rbf_dim, c = idx - z * a.rbf_dim;
+      sIn[z][c] = (z < ne) ? a.rbf[(e0 + z) * a.rbf_dim + c] : 0.f;
+    }
+    __syncthreads();
+    // layer 1 -> registers -> sIn (as h1) ; rbf_dim, h1, h2 <= 64
+    float h1v[16];
+    {
+      int cnt = 0;
+      for (int idx = tid; idx < GE * a.h1; idx += 256, ++cnt) {
+        const int z = idx / a.h1, c = idx - z * a.h1;
+        float acc = 0.f;
+        for (int r = 0; r < a.rbf_dim; ++r) acc = fmaf(sIn[z][r], __ldg(a.w1[b] + r * a.h1 + c), acc);
+        h1v[cnt] = hgb::silu_f(acc) * a.act_const;
+      }
+      __syncthreads();
+      cnt = 0;
+      for (int idx = tid; idx < GE * a.h1; idx += 256, ++cnt) sIn[idx / a.h1][idx % a.h1] = h1v[cnt];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < GE * a.h2dim; idx += 256) {
+      const int z = idx / a.h2dim, c = idx - z * a.h2dim;
+      float acc = 0.f;
+      for (int r = 0; r < a.h1; ++r) acc = fmaf(sIn[z][r], __ldg(a.w2[b] + r * a.h2dim + c), acc);
+      sH[c][z] = hgb::silu_f(acc) * a.act_const;
+    }
+    __syncthreads();
+    // layer 3: g tile [GE x GN] per column tile
+    const int nch = a.nch[b];
+    float* gb = a.g + ((size_t)b * a.n_edges + e0) * a.gstride;
+    for (int n0 = 0; n0 < nch; n0 += GN) {
+      for (int idx = tid; idx < 64 * (GN / 4); idx += 256) {
+        const int h = idx / (GN / 4), c4 = idx - h * (GN / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < a.h2dim) {
+          const int c = n0 + c4 * 4;
+          const float* wp = a.w3[b] + (size_t)h * nch + c;
+          if (c + 3 < nch && ((((size_t)h * nch + c) & 3) == 0)) v = __ldg(reinterpret_cast<const float4*>(wp));
+          else {
+            if (c < nch) v.x = __ldg(wp);
+            if (c + 1 < nch) v.y = __ldg(wp + 1);
+            if (c + 2 < nch) v.z = __ldg(wp + 2);
+            if (c + 3 < nch) v.w = __ldg(wp + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(&sB[h][c4 * 4]) = v;
+      }
+      __syncthreads();
+      float acc[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int h = 0; h < a.h2dim; ++h) {
+        const float4 av = *reinterpret_cast<const float4*>(&sH[h][ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&sB[h][tx * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&sB[h][tx * 8 + 4]);
+        const float ar[4] = {av.x, av.y, av.z, av.w};
+        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int z = ty * 4 + i;
+        if (z < ne) {
+          float* gr = gb + (size_t)z * a.gstride + n0 + tx * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + tx * 8 + j < nch) gr[j] = acc[i][j];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace
+
+// g_ws: device workspace of n_branches * n_edges * gstride floats (gstride >= max n_channels).  w3_off[b] / nch[b]:
+// offset (floats, into plan->wbuf) of the pre-scaled last radial layer [h2][nch_b] and its width.  paths[].pad0
+// holds the first gate column of the path.  Otherwise like hgb_msgpack_tc_forward.
+extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float* const* src,
+                                       const int64_t* const* src_rows, const float* sh, const float* rbf,
+                                       const int32_t* w3_off, const int32_t* nch, int32_t gstride, float* g_ws,
+                                       int64_t n_edges, float* out, const int64_t* out_index, void* stream) {
+  HGB_CHECK_ARG(plan && src && sh && rbf && out && g_ws && w3_off && nch, "hgb_msgpack_tcg_forward: NULL argument");
+  HGB_CHECK_ARG(plan->types_host && plan->paths_host, "hgb_msgpack_tcg_forward: host copies of the type/path tables are required");
+  HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
+                "hgb_msgpack_tcg_forward: bad source/branch count");
+  HGB_CHECK_ARG(plan->h2 <= 64 && plan->h1 <= 64 && plan->rbf_dim <= 64,
+                "hgb_msgpack_tcg_forward: radial MLP [%d,%d,%d] unsupported (all widths <= 64)", plan->rbf_dim, plan->h1, plan->h2);
+  HGB_CHECK_ARG(plan->n_types <= 32, "hgb_msgpack_tcg_forward: too many output slots");
+  HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_msgpack_tcg_forward: bad edge count");
+  if (n_edges == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  GateArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.n_branches = plan->n_branches; ga.rbf_dim = plan->rbf_dim;
+  ga.h1 = plan->h1; ga.h2dim = plan->h2; ga.gstride = gstride; ga.act_const = plan->act_const;
+  for (int b = 0; b < plan->n_branches; ++b) {
+    HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "hgb_msgpack_tcg_forward: gate width %d exceeds stride %d", nch[b], gstride);
+    ga.w1[b] = plan->wbuf + plan->fc1_off[b];
+    ga.w2[b] = plan->wbuf + plan->fc2_off[b];
+    ga.w3[b] = plan->wbuf + w3_off[b];
+    ga.nch[b] = nch[b];
+  }
+  constexpr size_t gate_smem = (size_t)GATE_SMEM_FLOATS * sizeof(float);
+  HGB_CUDA_OK(cudaFuncSetAttribute(radial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
+  radial_gate_kernel<<<(unsigned)((n_edges + GE - 1) / GE), 256, gate_smem, st>>>(ga);
+  HGB_LAUNCH_OK("radial_gate_kernel");
+
+  TgArgs cls[2];
+  int ctas[2] = {0, 0};
+  double cost[32];
+  int order[32], klass[32];
+  for (int t = 0; t < plan->n_types; ++t) {
+    const hgb_type_t& ty = plan->types_host[t];
+    HGB_CHECK_ARG(ty.l >= 0 && ty.l <= HGB_MAX_L && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
+                  "hgb_msgpack_tcg_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
+    const int d3 = 2 * ty.l + 1;
+    klass[t] = (ty.mpad <= 32 && d3 >= 3) ? 1 : 0;
+    HGB_CHECK_ARG(klass[t] == 1 || d3 == 1, "hgb_msgpack_tcg_forward: slot %d (multiplicity %d > 32 with l = %d) unsupported", t, ty.mul, ty.l);
+    double c = 0;
+    for (int p = ty.path_begin; p < ty.path_end; ++p) {
+      const hgb_path_t& pa = plan->paths_host[p];
+      const int d1 = 2 * pa.l1 + 1;
+      HGB_CHECK_ARG(pa.l3 == ty.l && pa.l1 >= 0 && pa.l1 <= HGB_MAX_L && pa.l2 >= 0 && pa.l2 <= HGB_MAX_L, "hgb_msgpack_tcg_forward: bad path %d", p);
+      HGB_CHECK_ARG(pa.nsrc >= 1 && pa.nsrc <= 2 && pa.src0 >= 0 && pa.src0 + pa.nsrc <= plan->n_sources, "hgb_msgpack_tcg_forward: path %d sources", p);
+      HGB_CHECK_ARG(pa.kind != 0 || (pa.pad0 >= 0 && pa.pad0 + ty.mul <= nch[pa.branch]), "hgb_msgpack_tcg_forward: gate columns of path %d out of range", p);
+      const int xb = klass[t] ? SmemG<32>::XBLK : SmemG<64>::XBLK, tb = klass[t] ? SmemG<32>::TBLK : SmemG<64>::TBLK;
+      const int tneed = (d3 == 1) ? (ROWS * d1) : (ROWS / d3) * (d1 * ((d3 + 3) & ~3) + 4);
+      HGB_CHECK_ARG((ROWS / d3) * (d1 * 4 + 4) <= xb && tneed <= tb, "hgb_msgpack_tcg_forward: staging buffers too small for path %d", p);
+      c += (double)(pa.nsrc * pa.mul_in + ty.mpad) * ty.mpad * d3;
+    }
+    cost[t] = c;
+    order[t] = t;
+  }
+  for (int i = 0; i < plan->n_types; ++i)
+    for (int j = i + 1; j < plan->n_types; ++j)
+      if (cost[order[j]] > cost[order[i]]) { int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+  for (int k = 0; k < 2; ++k) {
+    TgArgs& a = cls[k];
+    memset(&a, 0, sizeof(a));
+    a.plan = *plan;
+    int ns = 0;
+    for (int q = 0; q < plan->n_types; ++q) {
+      const int t = order[q];
+      const hgb_type_t& ty = plan->types_host[t];
+      if (klass[t] != k) continue;
+      if (ty.path_begin == ty.path_end && out_index != nullptr) continue;
+      const int nzf = ROWS / (2 * ty.l + 1);
+      a.type_order[ns] = t;
+      a.tile_start[ns] = ctas[k];
+      ctas[k] += (int)((n_edges + nzf - 1) / nzf);
+      ++ns;
+    }
+    a.tile_start[ns] = ctas[k];
+    a.n_sched = ns;
+    for (int s = 0; s < plan->n_sources; ++s) {
+      HGB_CHECK_ARG(src[s] != nullptr, "hgb_msgpack_tcg_forward: source %d is NULL", s);
+      a.src[s] = src[s];
+      a.src_rows[s] = src_rows ? src_rows[s] : nullptr;
+    }
+    a.sh = sh; a.g = g_ws; a.gstride = gstride; a.n_edges = n_edges; a.out = out; a.out_index = out_index;
+  }
+  if (ctas[0] > 0) {
+    constexpr size_t smem = (size_t)SmemG<64>::TOTAL * sizeof(float);
+    static_assert(smem <= 113 * 1024, "2 CTAs/SM budget");
+    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msgpack_tcg_kernel<64, 256><<<(unsigned)ctas[0], 256, smem, st>>>(cls[0]);
+    HGB_LAUNCH_OK("msgpack_tcg_kernel<64,256>");
+  }
+  if (ctas[1] > 0) {
+    constexpr size_t smem = (size_t)SmemG<32>::TOTAL * sizeof(float);
+    static_assert(smem <= 113 * 1024, "2 CTAs/SM budget");
+    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msgpack_tcg_kernel<32, 256><<<(unsigned)ctas[1], 256, smem, st>>>(cls[1]);
+    HGB_LAUNCH_OK("msgpack_tcg_kernel<32,256>");
+  }
+  return 0;
+}

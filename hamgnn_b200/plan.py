@@ -235,7 +235,8 @@ class KernelProfiler:
 
 
 PROFILER: Optional[KernelProfiler] = None
-# which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
+# which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
+# pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
 BACKEND = os.environ.get("HGB_MSGPACK", "simt")
 
 
@@ -544,6 +545,13 @@ class MessagePackOp:
             self.tc_fc2_off.append(wcur)
             add(wcur + np.arange(n2), base[("fc1", b)] + np.arange(n2), 1.0 / math.sqrt(self.h1), 2)
             wcur += n2
+        # plain (un-split) last radial layer per branch, [h2][n_channels], for the "tcg" variant's gate pre-pass
+        self.tc_w3_off = []
+        for b in range(len(self.branches)):
+            n3 = self.h2 * self.n_channels[b]
+            self.tc_w3_off.append(wcur)
+            add(wcur + np.arange(n3), base[("fc2", b)] + np.arange(n3), 1.0 / math.sqrt(self.h2), 2)
+            wcur += (n3 + 3) // 4 * 4
         # reuse the CG tables of the SIMT plan (offsets are identical)
         types = (L.TypeT * len(self.irreps_out))()
         plist = []
@@ -578,7 +586,7 @@ class MessagePackOp:
                     add_image(lf_off, mp, ww, wo, base[("F", b)] + f0 + (p.ch_off - ch_type0 + ww) * Mt + wo, 1.0, mp)
                     wcur += 2 * mp * mp
                     plist.append(L.PathT(0, b, br.src0, br.nsrc, sp.in_off, sp.mul_in, sp.l1, sp.l2, sp.l3, sp.sh_off,
-                                         sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, 0))
+                                         sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, p.ch_off))  # pad0 = first gate column
             if self.direct_src is not None:
                 sp = self.paths_c[next(simt_iter)]
                 bl = [x for x in self.direct_blocks[0] if x.i_out == t][0]
@@ -663,7 +671,7 @@ class MessagePackOp:
                 sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
                 out_index: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
-        use_tc = (BACKEND == "tc") and self.tc_supported()
+        use_tc = (BACKEND in ("tc", "tcg")) and self.tc_supported()
         st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
         assert len(sources) == ns and len(rows) == ns
@@ -674,7 +682,16 @@ class MessagePackOp:
         prof = PROFILER
         if prof is not None:
             prof.begin(self, int(n_edges), out.device)
-        if use_tc:
+        if use_tc and BACKEND == "tcg":
+            nb = len(self.branches)
+            gstride = (max(self.n_channels) + 3) // 4 * 4
+            g_ws = torch.empty(nb * int(n_edges) * gstride, device=out.device, dtype=torch.float32)
+            w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
+            nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
+            rc = L.load().hgb_msgpack_tcg_forward(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
+                                                  w3o, nch, gstride, g_ws.data_ptr(), int(n_edges), out.data_ptr(),
+                                                  L.ptr(out_index), L.stream_ptr(out.device))
+        elif use_tc:
             h2 = torch.empty(len(self.branches) * int(n_edges) * self.h2, device=out.device, dtype=torch.float32)
             rc = L.load().hgb_msgpack_tc_forward(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
                                                  h2.data_ptr(), int(n_edges), out.data_ptr(), L.ptr(out_index),

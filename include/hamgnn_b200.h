@@ -115,6 +115,15 @@ int hgb_msgpack_tc_forward(const hgb_msgpack_plan* plan_host, const float* const
                            const int64_t* const* src_rows_host, const float* sh, const float* rbf, float* h2_ws,
                            int64_t n_edges, float* out, const int64_t* out_index, void* stream);
 
+/* Variant of the tensor-core kernel that evaluates the radial gate g = FCN(rbf) [n_branches][E][gstride] once per
+ * call into the workspace g_ws (so that two CTAs fit per SM in the message kernel; csrc/msgpack_tcg.cu).
+ * w3_off_host[b] / nch_host[b]: offset into plan->wbuf of the pre-scaled last radial layer [h2][nch_b], and nch_b;
+ * plan->paths[].pad0 = first gate column of the path.  Replaces the same reference functions. */
+int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan_host, const float* const* src_host,
+                            const int64_t* const* src_rows_host, const float* sh, const float* rbf,
+                            const int32_t* w3_off_host, const int32_t* nch_host, int32_t gstride, float* g_ws,
+                            int64_t n_edges, float* out, const int64_t* out_index, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].
  * Replaces o3.Linear call sites (hamgnn/nn/convolution.py:112, interaction_blocks.py:126,306-309,

@@ -192,9 +192,10 @@ def test_errors_are_loud():
         pre(_to_dev(batch, dev))  # grad mode: forward-only kernels refuse
 
 
+@pytest.mark.parametrize("backend", ["tc", "tcg"])
 @pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si")])
-def test_tensor_core_backend_matches_oracle(cfg_name, gname):
-    """Same full forward with the tcgen05 (3xTF32) message kernel instead of the fp32-FMA one."""
+def test_tensor_core_backend_matches_oracle(cfg_name, gname, backend):
+    """Same full forward with the tcgen05 (3xTF32) message kernels instead of the fp32-FMA one."""
     from hamgnn_b200 import plan as P
     cfg = SMALL_CFG if cfg_name == "small" else DEFAULT_CFG
     pre, out, opre, oout = build_pair(cfg, nao_max=19, add_H0=False)
@@ -204,7 +205,7 @@ def test_tensor_core_backend_matches_oracle(cfg_name, gname):
     pre.to(dev)
     out.to(dev)
     old = P.BACKEND
-    P.BACKEND = "tc"
+    P.BACKEND = backend
     try:
         b = _to_dev(batch, dev)
         with torch.no_grad():
@@ -216,5 +217,5 @@ def test_tensor_core_backend_matches_oracle(cfg_name, gname):
     e_node = rel_err(r["node_attr"].cpu(), rep["node_attr"])
     e_edge = rel_err(r["edge_attr"].cpu(), rep["edge_attr"])
     e_h = rel_err(o["hamiltonian"].cpu(), res["hamiltonian"])
-    print(f"[tc] rel err node {e_node:.2e} edge {e_edge:.2e} H {e_h:.2e}")
+    print(f"[{backend}] rel err node {e_node:.2e} edge {e_edge:.2e} H {e_h:.2e}")
     assert e_node < TOL and e_edge < TOL and e_h < TOL
