@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t magic) { return ma
 // sX is channel-minor ([z][i][c], 16-byte aligned quads), T_z rows are padded to D3P = round4(D3) floats, both with
 // (row stride / 4) odd so that the 128-bit loads of a quarter warp (lanes = consecutive z) hit distinct banks.
 template <int NT, int D3>
-__device__ __forceinline__ void agen_tc(float* __restrict__ sA, const float* __restrict__ sX, int ldx, int cc,
+__device__ __forceinline__ void agen_tc(float* __restrict__ sA, int lo_off, const float* __restrict__ sX, int ldx, int cc,
                                         const float* __restrict__ sT, int ldt, int d1, int nz, uint32_t mz, int slab0,
                                         int nquad) {
   constexpr int D3P = (D3 + 3) & ~3;
@@ -66,7 +66,7 @@ __device__ __forceinline__ void agen_tc(float* __restrict__ sA, const float* __r
       }
     }
     float* hi = sA + (size_t)(slab0 + q) * (ROWS * 4) + (size_t)z * D3 * 4;
-    float* lo = hi + 8 * ROWS * 4;
+    float* lo = hi + lo_off;
 #pragma unroll
     for (int k = 0; k < D3; ++k) {
       float4 h, l;
@@ -81,18 +81,18 @@ __device__ __forceinline__ void agen_tc(float* __restrict__ sA, const float* __r
 }
 
 template <int NT>
-__device__ __forceinline__ void agen_tc_dispatch(int d3, float* sA, const float* sX, int ldx, int cc, const float* sT,
+__device__ __forceinline__ void agen_tc_dispatch(int d3, float* sA, int lo_off, const float* sX, int ldx, int cc, const float* sT,
                                                  int ldt, int d1, int nz, uint32_t mz, int slab0, int nquad) {
   switch (d3) {
-    case 1: agen_tc<NT, 1>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 3: agen_tc<NT, 3>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 5: agen_tc<NT, 5>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 7: agen_tc<NT, 7>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 9: agen_tc<NT, 9>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 11: agen_tc<NT, 11>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 13: agen_tc<NT, 13>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    case 15: agen_tc<NT, 15>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
-    default: agen_tc<NT, 17>(sA, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 1: agen_tc<NT, 1>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 3: agen_tc<NT, 3>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 5: agen_tc<NT, 5>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 7: agen_tc<NT, 7>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 9: agen_tc<NT, 9>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 11: agen_tc<NT, 11>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 13: agen_tc<NT, 13>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    case 15: agen_tc<NT, 15>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
+    default: agen_tc<NT, 17>(sA, lo_off, sX, ldx, cc, sT, ldt, d1, nz, mz, slab0, nquad); break;
   }
 }
 

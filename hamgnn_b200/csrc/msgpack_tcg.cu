@@ -14,7 +14,7 @@
 namespace {
 using namespace tcmsg;
 
-constexpr int KCH = 32;
+constexpr int KIMG = 32;  // K-chunking of the packed W images (host side)
 constexpr int NMAX = 64;
 
 struct TgArgs {
@@ -38,13 +38,16 @@ struct TmG {
   static constexpr int COLS = (RW == 32) ? 128 : 256;
 };
 
-template <int RW>
+// KC = channels per GEMM1 step (A image of KC/4 slabs): 32 for the wide class, 16 for the small class, which then
+// fits FOUR CTAs of 128 threads per SM (50 KB shared memory, 128 TMEM columns, 128 registers each).
+template <int RW, int KC>
 struct SmemG {
-  static constexpr int XBLK = (RW == 64) ? 6144 : 4096;
+  static constexpr int NSLAB = KC / 4;
+  static constexpr int XBLK = (RW == 64) ? 6144 : 2560;
   static constexpr int TBLK = (RW == 64) ? 1536 : 3072;   // RW = 64 serves d3 == 1 (compact T: 128 * d1 floats, l1 <= 5)
   static constexpr int A = 0;
-  static constexpr int W = A + 2 * 8 * ROWS * 4;
-  static constexpr int L = W + 2 * RW * KCH;
+  static constexpr int W = A + 2 * NSLAB * ROWS * 4;
+  static constexpr int L = W + 2 * RW * KC;
   static constexpr int X = L + 2 * RW * RW;
   static constexpr int T = X + XBLK;
   static constexpr int ROW = T + TBLK;
@@ -53,7 +56,7 @@ struct SmemG {
 
 // d3 == 1 specialisation of the A-operand generator with a compact T (one float per (z, i))
 template <int NT>
-__device__ __forceinline__ void agen_d3_1(float* __restrict__ sA, const float* __restrict__ sX, int ldx, int cc,
+__device__ __forceinline__ void agen_d3_1(float* __restrict__ sA, int lo_off, const float* __restrict__ sX, int ldx, int cc,
                                           const float* __restrict__ sT, int d1, int nz, uint32_t mz, int slab0,
                                           int nquad) {
   for (int item = threadIdx.x; item < nz * nquad; item += NT) {
@@ -71,13 +74,14 @@ __device__ __forceinline__ void agen_d3_1(float* __restrict__ sA, const float* _
     tc::split_tf32(acc.z, h.z, l.z); tc::split_tf32(acc.w, h.w, l.w);
     float* hi = sA + (size_t)(slab0 + q) * (ROWS * 4) + (size_t)z * 4;
     *reinterpret_cast<float4*>(hi) = h;
-    *reinterpret_cast<float4*>(hi + 8 * ROWS * 4) = l;
+    *reinterpret_cast<float4*>(hi + lo_off) = l;
   }
 }
 
-template <int RW, int NT>
-__global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constant__ TgArgs a) {
-  using SM = SmemG<RW>;
+template <int RW, int NT, int KC>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 4 : 2)) msgpack_tcg_kernel(const __grid_constant__ TgArgs a) {
+  using SM = SmemG<RW, KC>;
+  constexpr int LO = SM::NSLAB * ROWS * 4;  // float offset of the lo image of A
   constexpr int WPQ = NT / 128;
   constexpr int NGRP = (RW / 8 + WPQ - 1) / WPQ;  // 8-column groups per warp in the epilogues
   constexpr int XBLK = SM::XBLK;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constan
     const int64_t e = e0 + z;
     sRow[s * ROWS + z] = (int)(a.src_rows[s] ? a.src_rows[s][e] : e);
   }
-  for (int idx = tid; idx < 2 * 8 * ROWS * 4; idx += NT) sA[idx] = 0.f;
+  for (int idx = tid; idx < 2 * LO; idx += NT) sA[idx] = 0.f;
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -183,11 +187,16 @@ __global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constan
 
     // ---- GEMM1 in K chunks
     int chunk = 0;
-    for (int u0 = 0; u0 < Kpad; u0 += KCH, ++chunk) {
-      const int kc = min(KCH, Kpad - u0);
+    for (int u0 = 0; u0 < Kpad; u0 += KC, ++chunk) {
+      const int kc = min(KC, Kpad - u0);
       if (pend0) { tc::cta_wait(&mbar[0], ph0); ph0 ^= 1; pend0 = false; tc::fence_after_sync(); }
-      const float* wimg = wbuf + (pa.kind == 0 ? pa.w_off : pa.lf_off) + (size_t)2 * mp * KCH * chunk;
-      copy_f4<NT>(sW, wimg, 2 * mp * kc);
+      {
+        // the packed image is chunked by KIMG = 32 channels: [kimg/4 slabs][mp][4] hi | lo; take our KC-slice of both
+        const int img = u0 / KIMG, kimg = min(KIMG, Kpad - img * KIMG), s0 = (u0 - img * KIMG) >> 2;
+        const float* base = wbuf + (pa.kind == 0 ? pa.w_off : pa.lf_off) + (size_t)2 * mp * KIMG * img;
+        copy_f4<NT>(sW, base + (size_t)s0 * mp * 4, mp * kc);
+        copy_f4<NT>(sW + mp * kc, base + (size_t)mp * kimg + (size_t)s0 * mp * 4, mp * kc);
+      }
       const uint32_t md1 = fdiv_magic_odd(pa.l1);
       int cch = (int)fdiv((uint32_t)xcap, md1) & ~3;
       if (cch > kc) cch = kc;
@@ -217,8 +226,8 @@ __global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constan
         }
         cp_async_wait_all();
         __syncthreads();
-        if (d3 == 1) agen_d3_1<NT>(sA, sX, ldx, cc, sT, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
-        else agen_tc_dispatch<NT>(d3, sA, sX, ldx, cc, sT, ldt, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
+        if (d3 == 1) agen_d3_1<NT>(sA, LO, sX, ldx, cc, sT, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
+        else agen_tc_dispatch<NT>(d3, sA, LO, sX, ldx, cc, sT, ldt, d1, nz, mz, (ua - u0) >> 2, cc >> 2);
         if (ua + cch < u0 + kc) __syncthreads();
       }
       tc::fence_proxy_async();
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(NT, 2) msgpack_tcg_kernel(const __grid_constan
       if (tid == 0) {
         tc::fence_after_sync();
         const uint32_t dhi = tc::smem_desc_hi(sbo);
-        const uint32_t ah = tc::smem_desc_lo(tc::smem_u32(sA), lbo_a), al = ah + ((8 * ROWS * 4 * 4) >> 4);
+        const uint32_t ah = tc::smem_desc_lo(tc::smem_u32(sA), lbo_a), al = ah + ((LO * 4) >> 4);
         const uint32_t wh = tc::smem_desc_lo(tc::smem_u32(sW), lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
         const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
         const uint32_t dcol = tmem + (pa.kind == 0 ? TC_B : TC_C);
@@ -493,7 +502,7 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
       HGB_CHECK_ARG(pa.l3 == ty.l && pa.l1 >= 0 && pa.l1 <= HGB_MAX_L && pa.l2 >= 0 && pa.l2 <= HGB_MAX_L, "hgb_msgpack_tcg_forward: bad path %d", p);
       HGB_CHECK_ARG(pa.nsrc >= 1 && pa.nsrc <= 2 && pa.src0 >= 0 && pa.src0 + pa.nsrc <= plan->n_sources, "hgb_msgpack_tcg_forward: path %d sources", p);
       HGB_CHECK_ARG(pa.kind != 0 || (pa.pad0 >= 0 && pa.pad0 + ty.mul <= nch[pa.branch]), "hgb_msgpack_tcg_forward: gate columns of path %d out of range", p);
-      const int xb = klass[t] ? SmemG<32>::XBLK : SmemG<64>::XBLK, tb = klass[t] ? SmemG<32>::TBLK : SmemG<64>::TBLK;
+      const int xb = klass[t] ? SmemG<32, 16>::XBLK : SmemG<64, 32>::XBLK, tb = klass[t] ? SmemG<32, 16>::TBLK : SmemG<64, 32>::TBLK;
       const int tneed = (d3 == 1) ? (ROWS * d1) : (ROWS / d3) * (d1 * ((d3 + 3) & ~3) + 4);
       HGB_CHECK_ARG((ROWS / d3) * (d1 * 4 + 4) <= xb && tneed <= tb, "hgb_msgpack_tcg_forward: staging buffers too small for path %d", p);
       c += (double)(pa.nsrc * pa.mul_in + ty.mpad) * ty.mpad * d3;
@@ -530,18 +539,18 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     a.sh = sh; a.g = g_ws; a.gstride = gstride; a.n_edges = n_edges; a.out = out; a.out_index = out_index;
   }
   if (ctas[0] > 0) {
-    constexpr size_t smem = (size_t)SmemG<64>::TOTAL * sizeof(float);
+    constexpr size_t smem = (size_t)SmemG<64, 32>::TOTAL * sizeof(float);
     static_assert(smem <= 113 * 1024, "2 CTAs/SM budget");
-    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msgpack_tcg_kernel<64, 256><<<(unsigned)ctas[0], 256, smem, st>>>(cls[0]);
-    HGB_LAUNCH_OK("msgpack_tcg_kernel<64,256>");
+    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<64, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msgpack_tcg_kernel<64, 256, 32><<<(unsigned)ctas[0], 256, smem, st>>>(cls[0]);
+    HGB_LAUNCH_OK("msgpack_tcg_kernel<64,256,32>");
   }
   if (ctas[1] > 0) {
-    constexpr size_t smem = (size_t)SmemG<32>::TOTAL * sizeof(float);
-    static_assert(smem <= 113 * 1024, "2 CTAs/SM budget");
-    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    msgpack_tcg_kernel<32, 256><<<(unsigned)ctas[1], 256, smem, st>>>(cls[1]);
-    HGB_LAUNCH_OK("msgpack_tcg_kernel<32,256>");
+    constexpr size_t smem = (size_t)SmemG<32, 16>::TOTAL * sizeof(float);
+    static_assert(smem <= 56 * 1024, "4 CTAs/SM budget");
+    HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<32, 128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    msgpack_tcg_kernel<32, 128, 16><<<(unsigned)ctas[1], 128, smem, st>>>(cls[1]);
+    HGB_LAUNCH_OK("msgpack_tcg_kernel<32,128,16>");
   }
   return 0;
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU visit: parity prints, tensor-core / big-tile SIMT message kernel benches + ncu.  Tight per-stage timeouts.
 set -x
-TAG=${1:-r01i}
+TAG=${1:-r01j}
 BK=${2:-tcg}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -q -s -m gpu -k "tensor_core or full_forward or golden" > gpurun_out/${TAG}_pytest_gpu.log 2>&1
