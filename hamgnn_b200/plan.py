@@ -237,7 +237,7 @@ class KernelProfiler:
 PROFILER: Optional[KernelProfiler] = None
 # which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
-BACKEND = os.environ.get("HGB_MSGPACK", "simt")
+BACKEND = os.environ.get("HGB_MSGPACK", "tcg")
 
 
 @dataclass
@@ -671,7 +671,7 @@ class MessagePackOp:
                 sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
                 out_index: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
-        use_tc = (BACKEND in ("tc", "tcg")) and self.tc_supported()
+        use_tc = (BACKEND in ("tc", "tcg")) and self.tc_supported()   # configs outside the tensor-core kernels' limits run on the fp32-FMA kernel
         st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
         assert len(sources) == ns and len(rows) == ns
