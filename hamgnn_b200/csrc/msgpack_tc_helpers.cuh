@@ -17,6 +17,10 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// group form: commit what this thread has issued so far; wait until at most N of its newest groups are in flight
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int NT>
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int nfloats) {
   for (int i = threadIdx.x; i < (nfloats >> 2); i += NT) cp_async16(dst + 4 * i, src + 4 * i);

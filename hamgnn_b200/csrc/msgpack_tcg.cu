@@ -448,6 +448,8 @@ __global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant_
   }
 }
 
+#include "msgpack_tcr_kernel.cuh"
+
 }  // namespace
 
 // g_ws: device workspace of n_branches * n_edges * gstride floats (gstride >= max n_channels).  w3_off[b] / nch[b]:
@@ -479,13 +481,13 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     ga.w3[b] = plan->wbuf + w3_off[b];
     ga.nch[b] = nch[b];
   }
-  constexpr size_t gate_smem = (size_t)GATE_SMEM_FLOATS * sizeof(float);
-  HGB_CUDA_OK(cudaFuncSetAttribute(radial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
-  radial_gate_kernel<<<(unsigned)((n_edges + GE - 1) / GE), 256, gate_smem, st>>>(ga);
-  HGB_LAUNCH_OK("radial_gate_kernel");
-
-  TgArgs cls[2];
-  int ctas[2] = {0, 0};
+  // slot classes: 0 = scalar slots (d3 == 1, up to 64 channels) on msgpack_tcg_kernel<64,256,32>;
+  // 1 / 2 = l >= 1 slots padded to 16 / 32 channels on the rows-in-lanes pipeline msgpack_tcr_kernel<16 / 32>
+  // (HGB_TCG_ROWS=0 keeps them on msgpack_tcg_kernel<32,128,16>, the r01j kernel, for A/B measurements).
+  const char* rows_env = getenv("HGB_TCG_ROWS");
+  const bool use_rows = !(rows_env && rows_env[0] == '0');
+  TgArgs cls[3];
+  int ctas[3] = {0, 0, 0};
   double cost[32];
   int order[32], klass[32];
   for (int t = 0; t < plan->n_types; ++t) {
@@ -493,8 +495,8 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     HGB_CHECK_ARG(ty.l >= 0 && ty.l <= HGB_MAX_L && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
                   "hgb_msgpack_tcg_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
     const int d3 = 2 * ty.l + 1;
-    klass[t] = (ty.mpad <= 32 && d3 >= 3) ? 1 : 0;
-    HGB_CHECK_ARG(klass[t] == 1 || d3 == 1, "hgb_msgpack_tcg_forward: slot %d (multiplicity %d > 32 with l = %d) unsupported", t, ty.mul, ty.l);
+    klass[t] = (ty.mpad <= 32 && d3 >= 3) ? ((use_rows && ty.mpad == 32) ? 2 : 1) : 0;
+    HGB_CHECK_ARG(klass[t] != 0 || d3 == 1, "hgb_msgpack_tcg_forward: slot %d (multiplicity %d > 32 with l = %d) unsupported", t, ty.mul, ty.l);
     double c = 0;
     for (int p = ty.path_begin; p < ty.path_end; ++p) {
       const hgb_path_t& pa = plan->paths_host[p];
@@ -504,7 +506,11 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
       HGB_CHECK_ARG(pa.kind != 0 || (pa.pad0 >= 0 && pa.pad0 + ty.mul <= nch[pa.branch]), "hgb_msgpack_tcg_forward: gate columns of path %d out of range", p);
       const int xb = klass[t] ? SmemG<32, 16>::XBLK : SmemG<64, 32>::XBLK, tb = klass[t] ? SmemG<32, 16>::TBLK : SmemG<64, 32>::TBLK;
       const int tneed = (d3 == 1) ? (ROWS * d1) : (ROWS / d3) * (d1 * ((d3 + 3) & ~3) + 4);
-      HGB_CHECK_ARG((ROWS / d3) * (d1 * 4 + 4) <= xb && tneed <= tb, "hgb_msgpack_tcg_forward: staging buffers too small for path %d", p);
+      if (use_rows && klass[t] != 0) {
+        HGB_CHECK_ARG(d1 <= tcr::D1MAX && (31 / d3 + 2) * ((pa.nsrc * pa.mul_in > 4) ? 8 : 4) * d1 <= tcr::XW && ROWS / d3 <= tcr::ZSTR, "hgb_msgpack_tcg_forward: staging buffers too small for path %d", p);
+      } else {
+        HGB_CHECK_ARG((ROWS / d3) * (d1 * 4 + 4) <= xb && tneed <= tb, "hgb_msgpack_tcg_forward: staging buffers too small for path %d", p);
+      }
       c += (double)(pa.nsrc * pa.mul_in + ty.mpad) * ty.mpad * d3;
     }
     cost[t] = c;
@@ -513,7 +519,7 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
   for (int i = 0; i < plan->n_types; ++i)
     for (int j = i + 1; j < plan->n_types; ++j)
       if (cost[order[j]] > cost[order[i]]) { int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     TgArgs& a = cls[k];
     memset(&a, 0, sizeof(a));
     a.plan = *plan;
@@ -538,6 +544,11 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     }
     a.sh = sh; a.g = g_ws; a.gstride = gstride; a.n_edges = n_edges; a.out = out; a.out_index = out_index;
   }
+  constexpr size_t gate_smem = (size_t)GATE_SMEM_FLOATS * sizeof(float);
+  HGB_CUDA_OK(cudaFuncSetAttribute(radial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
+  radial_gate_kernel<<<(unsigned)((n_edges + GE - 1) / GE), 256, gate_smem, st>>>(ga);
+  HGB_LAUNCH_OK("radial_gate_kernel");
+
   if (ctas[0] > 0) {
     constexpr size_t smem = (size_t)SmemG<64, 32>::TOTAL * sizeof(float);
     static_assert(smem <= 113 * 1024, "2 CTAs/SM budget");
@@ -545,7 +556,22 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     msgpack_tcg_kernel<64, 256, 32><<<(unsigned)ctas[0], 256, smem, st>>>(cls[0]);
     HGB_LAUNCH_OK("msgpack_tcg_kernel<64,256,32>");
   }
-  if (ctas[1] > 0) {
+  if (use_rows) {
+    if (ctas[1] > 0) {
+      constexpr size_t smem = (size_t)tcr::Sm<16>::TOTAL * sizeof(float);
+      static_assert(smem <= 55 * 1024 + 512, "4 CTAs/SM budget");
+      HGB_CUDA_OK(cudaFuncSetAttribute(tcr::msgpack_tcr_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tcr::msgpack_tcr_kernel<16><<<(unsigned)ctas[1], tcr::NTHR, smem, st>>>(cls[1]);
+      HGB_LAUNCH_OK("msgpack_tcr_kernel<16>");
+    }
+    if (ctas[2] > 0) {
+      constexpr size_t smem = (size_t)tcr::Sm<32>::TOTAL * sizeof(float);
+      static_assert(smem <= 112 * 1024, "2 CTAs/SM budget");
+      HGB_CUDA_OK(cudaFuncSetAttribute(tcr::msgpack_tcr_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tcr::msgpack_tcr_kernel<32><<<(unsigned)ctas[2], tcr::NTHR, smem, st>>>(cls[2]);
+      HGB_LAUNCH_OK("msgpack_tcr_kernel<32>");
+    }
+  } else if (ctas[1] > 0) {
     constexpr size_t smem = (size_t)SmemG<32, 16>::TOTAL * sizeof(float);
     static_assert(smem <= 56 * 1024, "4 CTAs/SM budget");
     HGB_CUDA_OK(cudaFuncSetAttribute(msgpack_tcg_kernel<32, 128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

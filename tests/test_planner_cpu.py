@@ -162,3 +162,43 @@ def test_tensor_core_packing_matches_oracle(small):
     with torch.no_grad():
         ref_emb = opre.pair_embedding(dd2)
     assert rel_err(got, ref_emb) < 2e-6
+
+
+@pytest.mark.parametrize("cfg_name", ["small", "default"])
+def test_tensor_core_launcher_accepts_every_message_plan(cfg_name):
+    """Host-side validation of hgb_msgpack_tcg_forward (slot classes, staging-buffer limits of both message kernels)
+    runs before any CUDA call, so it can be exercised without a GPU: with dummy device pointers the call must get
+    past validation and fail only at the first CUDA runtime call."""
+    import ctypes as C
+    from hamgnn_b200 import lib as L, plan as PL, so3
+    from hamgnn_b200.hamgnn_conv import HamGNNConvE3
+    if torch.cuda.is_available():
+        pytest.skip("with a GPU the dummy pointers would be dereferenced; the GPU parity tests cover this path")
+    pre = HamGNNConvE3(dict(SMALL_CFG) if cfg_name == "small" else {})
+    ops = [v for m in pre.modules() for v in vars(m).values() if isinstance(v, PL.MessagePackOp)]
+    assert ops
+    lib = L.load()
+    dummy = 0x10000
+    for op in ops:
+        if not op.tc_supported():
+            continue
+        plan = L.MsgpackPlan()
+        plan.n_types, plan.n_paths = len(op.irreps_out), op.n_paths
+        plan.n_branches, plan.n_sources = len(op.branches), len(op.src_dims)
+        plan.sh_dim, plan.rbf_dim, plan.h1, plan.h2 = op.irreps_sh.dim, op.rbf_dim, op.h1, op.h2
+        plan.out_dim = op.irreps_out.dim
+        for q, d in enumerate(op.src_dims):
+            plan.src_dim[q] = d
+        plan.act_const = so3.normalize2mom_const("silu")
+        plan.types = plan.paths = plan.cg_ij = plan.cg_val = plan.cg_kstart = plan.wbuf = dummy
+        plan.types_host = C.cast(op.tc_types_c, C.c_void_p).value
+        plan.paths_host = C.cast(op.tc_paths_c, C.c_void_p).value
+        ns, nb = len(op.src_dims), len(op.branches)
+        srcs = (C.c_void_p * 4)(*([dummy] * ns + [None] * (4 - ns)))
+        rws = (C.c_void_p * 4)(*([None] * 4))
+        gstride = (max(op.n_channels) + 3) // 4 * 4
+        w3o = (C.c_int32 * 2)(*(list(op.tc_w3_off) + [0] * (2 - nb)))
+        nch = (C.c_int32 * 2)(*(list(op.n_channels) + [0] * (2 - nb)))
+        rc = lib.hgb_msgpack_tcg_forward(C.byref(plan), srcs, rws, dummy, dummy, w3o, nch, gstride, dummy, 1000, dummy, None, None)
+        msg = lib.hgb_last_error().decode()
+        assert rc != 0 and "failed" in msg and "hgb_msgpack_tcg_forward" not in msg, msg
