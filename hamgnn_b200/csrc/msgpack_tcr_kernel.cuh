@@ -47,11 +47,14 @@ struct Sm {
   static constexpr int TOTAL = ROW + 4 * ZSTR;
 };
 
+__device__ __forceinline__ void cp_async4_s(uint32_t dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
 }
-// Wait with a hardware-suspended try_wait (time hint ~10 us) instead of a busy poll: the waiting warp must not eat
-// the issue slots of the producer warps on its scheduler.  Bounded: ~2^20 expiries, then trap.
+// Wait with try_wait (suspend hint) + nanosleep back-off instead of a busy poll: a waiting warp must not eat the
+// issue slots of the producer warps on its scheduler.  Bounded: 2^22 expiries (> 0.25 s), then trap.
 __device__ __forceinline__ void mbar_wait_suspend(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = tc::smem_u32(mbar);
   uint32_t done;
@@ -66,7 +69,10 @@ __device__ __forceinline__ void mbar_wait_suspend(uint64_t* mbar, uint32_t parit
         : "=r"(done)
         : "r"(addr), "r"(parity), "r"(10000u)
         : "memory");
-    if (!done && ++spins > (1 << 20)) __trap();
+    if (!done) {
+      __nanosleep(64);
+      if (++spins > (1 << 22)) __trap();
+    }
   } while (!done);
 }
 // one lane waits, the warp re-converges
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(NTHR, (RW == 16 ? 4 : 2)) msgpack_tcr_kernel(c
     // ---- compute cursor
     int p = ty.path_begin, o = 0, q = 0, buf = 0;
     int pend_q = -1, pend_branch = 0, pend_goff = 0;
-    int c_d1 = 1, c_K = 0, c_nocts = 0, c_kind = 0, c_branch = 0, c_goff = 0;
+    int c_d1 = 1, c_K = 0, c_nocts = 0, c_kind = 0, c_branch = 0, c_goff = 0, c_tkey = -1;
 
     for (int n = -1; p < ty.path_end; ++n) {
       // -- stage the next oct: channels [8 s_o, 8 s_o + 8) of path s_p -> xbuf[buf ^ 1][zl][nchan * d1]
@@ -341,12 +347,12 @@ __global__ void __launch_bounds__(NTHR, (RW == 16 ? 4 : 2)) msgpack_tcr_kernel(c
         const int nAB = nA + ((s_nsrc == 2) ? max(0, min(u0 + 8, s_K) - ub) * s_d1 : 0);
         if (rowok) {
           float* d = xbuf + ((n < 0) ? buf : (buf ^ 1)) * XW + zl_l * L;
+          const uint32_t d32 = tc::smem_u32(d);
           const float* pa_ = s_pA + u0 * s_d1;
           const float* pb_ = s_pB + (ub - s_m) * s_d1 - nA;
 #pragma unroll 4
           for (int j = g; j < L; j += G) {
-            if (j < nA) cp_async4(d + j, pa_ + j);
-            else if (j < nAB) cp_async4(d + j, pb_ + j);
+            if (j < nAB) cp_async4_s(d32 + 4 * j, (j < nA ? pa_ : pb_) + j);
             else d[j] = 0.f;
           }
         }
@@ -362,9 +368,14 @@ __global__ void __launch_bounds__(NTHR, (RW == 16 ? 4 : 2)) msgpack_tcr_kernel(c
         const hgb_path_t& pa = P.paths[p];
         c_d1 = 2 * pa.l1 + 1; c_K = pa.nsrc * pa.mul_in; c_nocts = (c_K + 7) >> 3;
         c_kind = pa.kind; c_branch = pa.branch; c_goff = pa.pad0;
-        // T_z[.][k] of this path, thread-private column of sTp
-        for (int i = 0; i < c_d1; ++i) tcol[i * NPROD] = 0.f;
-        if (live) {
+        // T_z[.][k] of this path, thread-private column of sTp; consecutive gated paths with the same (l1, l2) --
+        // the two branches of one CG path -- share it
+        const int tkey = (pa.kind == 0) ? (pa.l1 * 16 + pa.l2) : -1;
+        const bool t_same = (tkey >= 0 && tkey == c_tkey);
+        c_tkey = tkey;
+        if (!t_same)
+          for (int i = 0; i < c_d1; ++i) tcol[i * NPROD] = 0.f;
+        if (live && !t_same) {
           if (c_kind == 0) {
             const float* yz = a.sh + (e0 + my_z) * S + pa.sh_off;
             const int* cij = P.cg_ij + pa.cg_off;

@@ -587,6 +587,8 @@ class MessagePackOp:
                     wcur += 2 * mp * mp
                     plist.append(L.PathT(0, b, br.src0, br.nsrc, sp.in_off, sp.mul_in, sp.l1, sp.l2, sp.l3, sp.sh_off,
                                          sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, p.ch_off))  # pad0 = first gate column
+            # same (l1, l2) paths of the two branches adjacent: they share T_z (the rows-in-lanes kernel builds it once)
+            plist[begin:] = sorted(plist[begin:], key=lambda q: (q.l1, q.l2, q.branch))
             if self.direct_src is not None:
                 sp = self.paths_c[next(simt_iter)]
                 bl = [x for x in self.direct_blocks[0] if x.i_out == t][0]

@@ -12,3 +12,7 @@ if grep -q "passed" gpurun_out/${TAG}_pytest_gpu.log; then
   HGB_MSGPACK=$BK timeout 400 ncu --set full --clock-control none --import-source on -k regex:msgpack_tcr -s 8 -c 1 -f -o gpurun_out/${TAG}_msgpack_${BK}_full \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload tbg_m8 > gpurun_out/${TAG}_ncu_tc.log 2>&1; tail -3 gpurun_out/${TAG}_ncu_tc.log | cut -c1-300
 fi
+if grep -q "passed" gpurun_out/${TAG}_pytest_gpu.log; then
+  HGB_MSGPACK=$BK timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_m8.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --workload tbg_m8 > gpurun_out/${TAG}_ncu_list.log 2>&1
+fi
