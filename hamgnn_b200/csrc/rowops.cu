@@ -68,22 +68,24 @@ __device__ __forceinline__ void lin_apply(const hgb_linblock_t* __restrict__ blo
 
 // global [rows][dim] (optionally gathered) -> transposed tile; rows >= nr are zero-filled
 __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g, const int64_t* rows, int64_t r0, int nr,
-                                          int dim, bool add) {
+                                          int dim, bool add, int64_t ld = -1) {
+  if (ld < 0) ld = dim;
   for (int idx = threadIdx.x; idx < TR * dim; idx += RO_THREADS) {
     const int r = idx / dim, c = idx - r * dim;
     float v = 0.f;
     if (r < nr) {
       const int64_t row = rows ? rows[r0 + r] : (r0 + r);
-      v = g[row * dim + c];
+      v = g[row * ld + c];
     }
     if (add) s[(size_t)c * LDR + r] += v;
     else s[(size_t)c * LDR + r] = v;
   }
 }
-__device__ __forceinline__ void store_tile(const float* s, float* __restrict__ g, int64_t r0, int nr, int dim) {
+__device__ __forceinline__ void store_tile(const float* s, float* __restrict__ g, int64_t r0, int nr, int dim, int64_t ld = -1) {
+  if (ld < 0) ld = dim;
   for (int idx = threadIdx.x; idx < nr * dim; idx += RO_THREADS) {
     const int r = idx / dim, c = idx - r * dim;
-    g[(r0 + r) * dim + c] = s[(size_t)c * LDR + r];
+    g[(r0 + r) * ld + c] = s[(size_t)c * LDR + r];
   }
 }
 __device__ __forceinline__ void zero_tile(float* s, int dim) {
@@ -96,6 +98,7 @@ struct LinArgs {
   const int64_t* rows;
   int64_t n_rows;
   float* y;
+  int64_t ldy;
   int accumulate;
 };
 
@@ -107,11 +110,11 @@ __global__ void __launch_bounds__(RO_THREADS) linear_kernel(const __grid_constan
   const int64_t r0 = (int64_t)blockIdx.x * TR;
   const int nr = (int)min((int64_t)TR, a.n_rows - r0);
   load_tile(sx, a.x, a.rows, r0, nr, din, false);
-  if (a.accumulate) load_tile(sy, a.y, nullptr, r0, nr, dout, false);
+  if (a.accumulate) load_tile(sy, a.y, nullptr, r0, nr, dout, false, a.ldy);
   else zero_tile(sy, dout);
   __syncthreads();
   lin_apply(a.plan.blocks, a.plan.n_blocks, a.plan.pad & 1, a.plan.w, sx, sy);
-  store_tile(sy, a.y, r0, nr, dout);
+  store_tile(sy, a.y, r0, nr, dout, a.ldy);
 }
 
 struct ResArgs {
@@ -175,11 +178,18 @@ __global__ void __launch_bounds__(RO_THREADS) resblock_kernel(const __grid_const
 
 extern "C" int hgb_linear_forward(const hgb_linear_plan* plan, const float* x, const int64_t* rows, int64_t n_rows,
                                   float* y, int32_t accumulate, void* stream) {
+  HGB_CHECK_ARG(plan, "hgb_linear_forward: NULL argument");
+  return hgb_linear_forward_ld(plan, x, rows, n_rows, y, plan->out_dim, accumulate, stream);
+}
+
+extern "C" int hgb_linear_forward_ld(const hgb_linear_plan* plan, const float* x, const int64_t* rows, int64_t n_rows,
+                                     float* y, int64_t ldy, int32_t accumulate, void* stream) {
   HGB_CHECK_ARG(plan && x && y, "hgb_linear_forward: NULL argument");
   HGB_CHECK_ARG(n_rows >= 0, "hgb_linear_forward: negative row count");
+  HGB_CHECK_ARG(ldy >= plan->out_dim, "hgb_linear_forward: output row stride %lld < out_dim %d", (long long)ldy, plan->out_dim);
   if (n_rows == 0) return 0;
   LinArgs a;
-  a.plan = *plan; a.x = x; a.rows = rows; a.n_rows = n_rows; a.y = y; a.accumulate = accumulate;
+  a.plan = *plan; a.x = x; a.rows = rows; a.n_rows = n_rows; a.y = y; a.ldy = ldy; a.accumulate = accumulate;
   const size_t smem = (size_t)LDR * (plan->in_dim + plan->out_dim) * sizeof(float);
   HGB_CHECK_ARG(smem <= 220 * 1024, "hgb_linear_forward: rows of %d+%d floats do not fit in shared memory", plan->in_dim, plan->out_dim);
   HGB_CUDA_OK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -188,7 +188,7 @@ def save_graph_data_npz(path: str, graphs: Sequence[Data]):
 # ------------------------------------------------------------------------------------ neighbour lists
 def build_graph(z: np.ndarray, pos_bohr: np.ndarray, cell_bohr: np.ndarray, pbc=(True, True, True),
                 radius_scale: float = 1.0, nao_max: int = 19, seed: int = 0, with_targets: bool = True,
-                dtype=torch.float32) -> Data:
+                dtype=torch.float32, soc: bool = False) -> Data:
     """Reference neighbour rule on a periodic cell; returns a `Data` with the graph_data.npz fields."""
     from scipy.spatial import cKDTree
 
@@ -267,6 +267,34 @@ def build_graph(z: np.ndarray, pos_bohr: np.ndarray, cell_bohr: np.ndarray, pbc=
         d.Hoff = sym_off(d.Hoff0 + 0.01 * torch.randn(E, nn2, generator=g)).to(dtype)
         d.Son = sym_on(torch.rand(n, nn2, generator=g)).to(dtype)
         d.Soff = sym_off(0.1 * torch.rand(E, nn2, generator=g)).to(dtype)
+        if soc:
+            add_soc_targets(d, nao_max, seed=seed + 1, dtype=dtype)
+    return d
+
+
+def add_soc_targets(d: Data, nao_max: int, seed: int = 0, dtype=torch.float32) -> Data:
+    """Synthetic spin-orbit fields of a graph_data.npz entry (graph_data_gen.py SOC branch): Hon/Hoff/Hon0/Hoff0 become
+    the real parts of the (2 nao)^2 spin-orbital blocks, iHon/iHoff/iHon0/iHoff0 the imaginary parts (Hermitian with
+    the inverse edge), Lon/Loff [*, nao^2, 3] the orbital angular-momentum matrices of the so3 basis and
+    Hon_nonsoc/Hoff_nonsoc the spin-less blocks used with add_H_nonsoc."""
+    g = torch.Generator().manual_seed(seed)
+    n, E = d.z.shape[0], d.edge_index.shape[1]
+    M = 2 * nao_max
+    inv = d.inv_edge_idx
+
+    def herm(re, im, partner):
+        c = torch.complex(re, im).view(-1, M, M)
+        o = c if partner is None else c[partner]
+        c = 0.5 * (c + o.conj().transpose(1, 2))
+        return c.real.reshape(-1, M * M).to(dtype).contiguous(), c.imag.reshape(-1, M * M).to(dtype).contiguous()
+
+    d.Hon_nonsoc, d.Hoff_nonsoc = d.Hon.clone(), d.Hoff.clone()
+    d.Hon0, d.iHon0 = herm(0.1 * torch.randn(n, M * M, generator=g), 0.1 * torch.randn(n, M * M, generator=g), None)
+    d.Hoff0, d.iHoff0 = herm(0.1 * torch.randn(E, M * M, generator=g), 0.1 * torch.randn(E, M * M, generator=g), inv)
+    d.Hon, d.iHon = herm(d.Hon0 + 0.01 * torch.randn(n, M * M, generator=g), d.iHon0 + 0.01 * torch.randn(n, M * M, generator=g), None)
+    d.Hoff, d.iHoff = herm(d.Hoff0 + 0.01 * torch.randn(E, M * M, generator=g), d.iHoff0 + 0.01 * torch.randn(E, M * M, generator=g), inv)
+    d.Lon = torch.randn(n, nao_max * nao_max, 3, generator=g).to(dtype)
+    d.Loff = torch.randn(E, nao_max * nao_max, 3, generator=g).to(dtype)
     return d
 
 

@@ -1,12 +1,17 @@
-"""`HamGNNPlusPlusOut` ("HamGNN_out") on the B200 kernels -- host-side mirror of the non-SOC, non-magnetic
-branch of /root/reference/hamgnn/models/hamgnn_output.py (ctor :96-256, forward :2916-2990, 3771-3799,
-3966-4021) for the OpenMX basis tables (:345-526).
+"""`HamGNNPlusPlusOut` ("HamGNN_out") on the B200 kernels -- host-side mirror of
+/root/reference/hamgnn/models/hamgnn_output.py (ctor :96-256, forward :2916-4021) for the OpenMX basis tables
+(:345-526): the non-SOC branch (:3771-3799), the two spin-orbit branches (soc_basis 'su2' :3146-3178 and 'so3'
+:3026-3144, non-collinear, +H0 / real;imag stacking :3603-3625, result dict :3889-3931) and the overlap head
+(ham_only=False, :2996-3019, 4006-4014).
 
 Kernels: hgb_resblock_forward (HamLayer = ResidualBlock + o3.Linear, :38-58), hgb_ham_assemble
 (merge_tensor_components :851-891 + reorder_matrix :1056-1096 as one CSR product), hgb_ham_finalize
-(symmetrize :1231-1285, +H0 :3782-3795, orbital masks :2288-2365, per-crystal interleave :1187-1229).
-SOC (su2/so3), spin-constrained, band-energy and overlap heads are outside this round's scope and raise
-NotImplementedError.
+(symmetrize :1231-1285, +H0 :3782-3795, orbital masks :2288-2365, per-crystal interleave :1187-1229);
+SOC: hgb_linear_forward_ld (the used half of the 4x-wide su2 head in irrep-sorted layout), hgb_csr_rows
+(E3TensorDecomposition.get_H, hamgnn/nn/tensor_decomposition.py:575-627), hgb_ham_finalize_su2,
+hgb_ksi_shell_average (symmetrize_orbital_coefficients :2367-2431), hgb_ham_finalize_so3.
+Spin-constrained / collinear heads, band energies and the SIESTA/ABACUS basis tables raise NotImplementedError
+(SURVEY.md section 8f).
 """
 from __future__ import annotations
 
@@ -19,7 +24,7 @@ from torch import nn
 from . import lib as L
 from .hamgnn_conv import ResidualBlock, _W
 from .irreps import Irreps
-from .plan import HamAssembly, LinearOp
+from .plan import HamAssembly, LinearOp, SocSU2Assembly, SortedHeadOp
 
 
 def openmx_basis(nao_max: int):
@@ -87,6 +92,20 @@ class HamLayer(nn.Module):
         return self.residual_block.forward_cuda(x, post=self.op, post_w=self.linear_transform.weight)
 
 
+class SocHamLayer(nn.Module):
+    """HamLayer whose trailing o3.Linear is the su2 head `2 * hamiltonian_irreps_su2` (hamgnn_output.py:190-198);
+    only the half of its outputs that get_H reads is evaluated (SortedHeadOp)."""
+
+    def __init__(self, irreps_in, assembly: SocSU2Assembly):
+        super().__init__()
+        self.residual_block = ResidualBlock(irreps_in, irreps_in)
+        self.head = SortedHeadOp(irreps_in, assembly.head_irreps, assembly.used)
+        self.linear_transform = _W(self.head.weight_numel)
+
+    def forward_cuda(self, x):
+        return self.head.forward(self.linear_transform.weight, self.residual_block.forward_cuda(x))
+
+
 class HamGNNPlusPlusOut(nn.Module):
     def __init__(self, irreps_in_node=None, irreps_in_edge=None, nao_max: int = 14, return_forces: bool = False,
                  create_graph: bool = False, ham_type: str = "openmx", ham_only: bool = False, symmetrize: bool = True,
@@ -109,9 +128,10 @@ class HamGNNPlusPlusOut(nn.Module):
             if self.ham_type in ("siesta", "abacus", "pasp"):
                 raise NotImplementedError(f"ham_type '{ham_type}' basis tables are not part of this round's hot path")
             raise NotImplementedError(f"Hamiltonian type '{self.ham_type}' is not supported.")
-        for flag, name in ((soc_switch, "soc_switch"), (spin_constrained, "spin_constrained"),
+        self.soc_basis, self.add_H_nonsoc = soc_basis.lower(), add_H_nonsoc
+        for flag, name in ((spin_constrained, "spin_constrained"), (collinear_spin, "collinear_spin"),
                            (calculate_band_energy, "calculate_band_energy"), (return_forces, "return_forces"),
-                           (not ham_only, "ham_only=False"), (nonlinearity_type != "gate", "nonlinearity_type!='gate'"),
+                           (nonlinearity_type != "gate", "nonlinearity_type!='gate'"),
                            (get_nonzero_mask_tensor, "get_nonzero_mask_tensor"),
                            (export_reciprocal_values, "export_reciprocal_values")):
             if flag:
@@ -124,6 +144,32 @@ class HamGNNPlusPlusOut(nn.Module):
         self.hamiltonian_irreps = self.assembly.hamiltonian_irreps
         self.onsite_hamiltonian_network = HamLayer(Irreps(irreps_in_node), self.hamiltonian_irreps)
         self.offsite_hamiltonian_network = HamLayer(Irreps(irreps_in_edge), self.hamiltonian_irreps)
+        if soc_switch:
+            if self.soc_basis == "su2":
+                self.soc_assembly = SocSU2Assembly(self.row, self.col, idx, self.basis_def)
+                self.hamiltonian_irreps_su2 = self.soc_assembly.hamiltonian_irreps_su2
+                self.onsite_hamiltonian_network = SocHamLayer(Irreps(irreps_in_node), self.soc_assembly)
+                self.offsite_hamiltonian_network = SocHamLayer(Irreps(irreps_in_edge), self.soc_assembly)
+                if self.onsite_hamiltonian_network.head.pos.tolist() != self.offsite_hamiltonian_network.head.pos.tolist():
+                    raise NotImplementedError("su2 head: node and edge features must carry the same set of irreps")
+                self.soc_assembly.build_csr(self.onsite_hamiltonian_network.head.pos)
+            elif self.soc_basis == "so3":
+                ksi = Irreps([(nao_max ** 2, (0, 1))])
+                self.onsite_ksi_network = HamLayer(Irreps(irreps_in_node), ksi)
+                self.offsite_ksi_network = HamLayer(Irreps(irreps_in_edge), ksi)
+                shells = [(3, 6), (6, 9), (9, 14)] if nao_max >= 14 else []     # symmetrize_orbital_coefficients :2400-2410
+                if nao_max >= 19:
+                    shells.append((14, 19))
+                if nao_max == 26:
+                    shells.append((19, 26))
+                self._shell_lo = (C.c_int32 * 8)(*[a for a, _ in shells])
+                self._shell_hi = (C.c_int32 * 8)(*[b for _, b in shells])
+                self._n_shells = len(shells)
+            else:
+                raise NotImplementedError(f"SOC basis '{soc_basis}' not supported!")
+        if not ham_only:
+            self.onsite_overlap_network = HamLayer(Irreps(irreps_in_node), self.hamiltonian_irreps)
+            self.offsite_overlap_network = HamLayer(Irreps(irreps_in_edge), self.hamiltonian_irreps)
         self._tables: Dict[str, tuple] = {}
 
     # ---------------------------------------------------------------------------------------------
@@ -205,31 +251,108 @@ class HamGNNPlusPlusOut(nn.Module):
         src, dst = L.i64c(data["edge_index"][0]), L.i64c(data["edge_index"][1])
         z = L.i64c(data["z"])
         on_row, off_row, inv = self._row_maps(data)
-        N, E, nn2 = node_attr.shape[0], edge_attr.shape[0], self.nao_max ** 2
+        N, E, nao = node_attr.shape[0], edge_attr.shape[0], self.nao_max
+        nn2 = nao * nao
         plan = self.assembly.plan(dev)
         lib, st = L.load(), L.stream_ptr(dev)
-        H = torch.empty(N + E, nn2, device=dev, dtype=torch.float32)
 
-        coef_on = self.onsite_hamiltonian_network.forward_cuda(node_attr)
-        raw_on = torch.empty(N, nn2, device=dev, dtype=torch.float32)
-        L.check(lib.hgb_ham_assemble(C.byref(plan), coef_on.data_ptr(), N, raw_on.data_ptr(), st), "hgb_ham_assemble")
-        h0 = L.f32c(data["Hon0"]) if self.add_H0 else None
-        L.check(lib.hgb_ham_finalize(C.byref(plan), raw_on.data_ptr(), None, L.ptr(h0), z.data_ptr(), None, None,
-                                     on_row.data_ptr(), N, int(self.symmetrize), H.data_ptr(), st), "hgb_ham_finalize")
+        def spinless(on_net, off_net, h0_on, h0_off, out, rows_on, rows_off):
+            """CG merge + reorder + symmetrise (+H0) + masks of one (on-site, off-site) HamLayer pair."""
+            coef_on = on_net.forward_cuda(node_attr)
+            raw_on = torch.empty(N, nn2, device=dev, dtype=torch.float32)
+            L.check(lib.hgb_ham_assemble(C.byref(plan), coef_on.data_ptr(), N, raw_on.data_ptr(), st), "hgb_ham_assemble")
+            L.check(lib.hgb_ham_finalize(C.byref(plan), raw_on.data_ptr(), None, L.ptr(h0_on), z.data_ptr(), None, None,
+                                         L.ptr(rows_on), N, int(self.symmetrize), out[0].data_ptr(), st), "hgb_ham_finalize")
+            coef_off = off_net.forward_cuda(edge_attr)
+            raw_off = torch.empty(E, nn2, device=dev, dtype=torch.float32)
+            L.check(lib.hgb_ham_assemble(C.byref(plan), coef_off.data_ptr(), E, raw_off.data_ptr(), st), "hgb_ham_assemble")
+            L.check(lib.hgb_ham_finalize(C.byref(plan), raw_off.data_ptr(), inv.data_ptr(), L.ptr(h0_off), z.data_ptr(),
+                                         src.data_ptr(), dst.data_ptr(), L.ptr(rows_off), E, int(self.symmetrize),
+                                         out[1].data_ptr(), st), "hgb_ham_finalize")
 
-        coef_off = self.offsite_hamiltonian_network.forward_cuda(edge_attr)
-        raw_off = torch.empty(E, nn2, device=dev, dtype=torch.float32)
-        L.check(lib.hgb_ham_assemble(C.byref(plan), coef_off.data_ptr(), E, raw_off.data_ptr(), st), "hgb_ham_assemble")
-        h0 = L.f32c(data["Hoff0"]) if self.add_H0 else None
-        L.check(lib.hgb_ham_finalize(C.byref(plan), raw_off.data_ptr(), inv.data_ptr(), L.ptr(h0), z.data_ptr(),
-                                     src.data_ptr(), dst.data_ptr(), off_row.data_ptr(), E, int(self.symmetrize),
-                                     H.data_ptr(), st), "hgb_ham_finalize")
-        if self.zero_point_shift:
-            S = data["overlap"]
-            sel = S > 1e-6
-            shift = ((H - data["hamiltonian"]) * sel).sum() / (S * sel).sum()
-            H = H - shift * S
-        result = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+        overlap = None
+        if not self.ham_only:
+            overlap = torch.empty(N + E, nn2, device=dev, dtype=torch.float32)
+            spinless(self.onsite_overlap_network, self.offsite_overlap_network, None, None, (overlap, overlap), on_row, off_row)
+
+        if self.soc_switch:
+            result = self._forward_soc(data, node_attr, edge_attr, spinless, on_row, off_row, inv, src, dst, z)
+        else:
+            H = torch.empty(N + E, nn2, device=dev, dtype=torch.float32)
+            spinless(self.onsite_hamiltonian_network, self.offsite_hamiltonian_network,
+                     L.f32c(data["Hon0"]) if self.add_H0 else None, L.f32c(data["Hoff0"]) if self.add_H0 else None,
+                     (H, H), on_row, off_row)
+            if self.zero_point_shift:
+                S = data["overlap"]
+                sel = S > 1e-6
+                shift = ((H - data["hamiltonian"]) * sel).sum() / (S * sel).sum()
+                H = H - shift * S
+            result = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+        if overlap is not None:
+            result["overlap"] = overlap
         if self.calculate_sparsity:
             result["sparsity_ratio"] = self.calculate_sparsity_ratio(data)
         return result
+
+    # ---------------------------------------------------------------------------------------------
+    def _forward_soc(self, data, node_attr, edge_attr, spinless, on_row, off_row, inv, src, dst, z):
+        """Spin-orbit branches of forward (hamgnn_output.py:3022-3178, 3603-3625, 3889-3931), non-collinear."""
+        dev = node_attr.device
+        N, E, nao = node_attr.shape[0], edge_attr.shape[0], self.nao_max
+        M = 2 * nao
+        MM = M * M
+        lib, st = L.load(), L.stream_ptr(dev)
+        H = torch.empty(2 * (N + E), MM, device=dev, dtype=torch.float32)   # rows [0, N+E): real, [N+E, 2(N+E)): imaginary
+        H_re, H_im = H[:N + E], H[N + E:]
+        h0 = {k: (L.f32c(data[k]) if self.add_H0 else None) for k in ("Hon0", "Hoff0", "iHon0", "iHoff0")}
+        if self.soc_basis == "su2":
+            asm = self.soc_assembly
+            tb = asm.tables(dev)
+            for net, x, n, partner, na, nb, rows, kre, kim in (
+                    (self.onsite_hamiltonian_network, node_attr, N, None, None, None, on_row, "Hon0", "iHon0"),
+                    (self.offsite_hamiltonian_network, edge_attr, E, inv, src, dst, off_row, "Hoff0", "iHoff0")):
+                coef = net.forward_cuda(x)
+                raw = torch.empty(n, 2 * MM, device=dev, dtype=torch.float32)
+                L.check(lib.hgb_csr_rows(tb["row_ptr"].data_ptr(), tb["col"].data_ptr(), tb["val"].data_ptr(), asm.n_out,
+                                         net.head.out_dim, coef.data_ptr(), n, raw.data_ptr(), st), "hgb_csr_rows")
+                L.check(lib.hgb_ham_finalize_su2(nao, tb["mask"].data_ptr(), raw.data_ptr(), L.ptr(partner), L.ptr(h0[kre]),
+                                                 L.ptr(h0[kim]), z.data_ptr(), L.ptr(na), L.ptr(nb), rows.data_ptr(), n,
+                                                 int(self.symmetrize), H_re.data_ptr(), H_im.data_ptr(), st),
+                        "hgb_ham_finalize_su2")
+        else:
+            nn2 = nao * nao
+            if self.add_H_nonsoc:
+                hns_on, hns_off = L.f32c(data["Hon_nonsoc"]), L.f32c(data["Hoff_nonsoc"])
+            else:
+                hns_on = torch.empty(N, nn2, device=dev, dtype=torch.float32)
+                hns_off = torch.empty(E, nn2, device=dev, dtype=torch.float32)
+                spinless(self.onsite_hamiltonian_network, self.offsite_hamiltonian_network, None, None,
+                         (hns_on, hns_off), None, None)
+            for net, x, n, hns, lkey, partner, rows, kre, kim in (
+                    (self.onsite_ksi_network, node_attr, N, hns_on, "Lon", None, on_row, "Hon0", "iHon0"),
+                    (self.offsite_ksi_network, edge_attr, E, hns_off, "Loff", inv, off_row, "Hoff0", "iHoff0")):
+                ksi = net.forward_cuda(x)
+                L.check(lib.hgb_ksi_shell_average(nao, self._shell_lo, self._shell_hi, self._n_shells, ksi.data_ptr(), n, st),
+                        "hgb_ksi_shell_average")
+                lmat = L.f32c(data[lkey])
+                if tuple(lmat.shape) != (n, nn2, 3):
+                    raise ValueError(f"data.{lkey} must have shape [{n}, {nn2}, 3], got {tuple(lmat.shape)}")
+                L.check(lib.hgb_ham_finalize_so3(nao, hns.data_ptr(), ksi.data_ptr(), lmat.data_ptr(), L.ptr(partner),
+                                                 L.ptr(h0[kre]), L.ptr(h0[kim]), rows.data_ptr(), n, int(self.symmetrize),
+                                                 int(self.add_H_nonsoc), H_re.data_ptr(), H_im.data_ptr(), st),
+                        "hgb_ham_finalize_so3")
+        if "Hon" in data and "iHon" in data:
+            data["hamiltonian_real"] = self.concatenate_hamiltonians_by_crystal(data, data["Hon"], data["Hoff"])
+            data["hamiltonian_imag"] = self.concatenate_hamiltonians_by_crystal(data, data["iHon"], data["iHoff"])
+            data["hamiltonian"] = torch.cat((data["hamiltonian_real"], data["hamiltonian_imag"]), dim=0)
+        if self.zero_point_shift:
+            S = data["overlap"].reshape(-1, nao, nao)
+            Hr = H_re.view(-1, 2, nao, 2, nao)
+            Tr = data["hamiltonian_real"].reshape(-1, 2, nao, 2, nao)
+            sel = S > 1e-6
+            diff = (Hr[:, 0, :, 0, :] + Hr[:, 1, :, 1, :]) - (Tr[:, 0, :, 0, :] + Tr[:, 1, :, 1, :])
+            shift = (diff * sel).sum() / (2.0 * (S * sel).sum())
+            Hr[:, 0, :, 0, :] -= shift * S
+            Hr[:, 1, :, 1, :] -= shift * S
+        return {"hamiltonian": H, "hamiltonian_real": H_re, "hamiltonian_imag": H_im, "band_energy": None,
+                "wavefunction": None}

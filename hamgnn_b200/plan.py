@@ -778,3 +778,210 @@ class HamAssembly:
                           t["val"].data_ptr(), t["mask"].data_ptr())
             self._dev[key] = (p, t)
         return self._dev[key][0]
+
+
+# ====================================================================================== SOC heads (a16)
+class SortedHeadOp:
+    """o3.Linear(irreps_in -> out_list) for a long list of multiplicity-1 output slots (the SOC head has
+    4 x 322 of them for nao_max 19), evaluated only on the slots in `used` and written in an irrep-sorted
+    layout: all used slots of one irrep form ONE [mul_in, n_used(ir)] block, so the row kernel sees <= 13
+    disjoint blocks instead of thousands of rank-1 ones.  The parameter keeps e3nn's flat layout (loop over
+    input slots, then over matching output slots, each block [mul_in, 1]) so reference state_dicts load
+    unchanged; `plan()` gathers the used columns.  `pos[q]` is the first column of used slot q in the sorted
+    row (its 2l+1 components are contiguous)."""
+
+    def __init__(self, irreps_in, out_list: Irreps, used: Sequence[int], max_cols: int = 2900):
+        self.irreps_in, self.out_list = Irreps(irreps_in), Irreps(out_list)
+        if any(m.mul != 1 for m in self.out_list):
+            raise NotImplementedError("SortedHeadOp expects multiplicity-1 output slots")
+        used = list(used)
+        # e3nn flat layout: blocks in (i_in, i_out) order
+        w_off, off = {}, 0
+        for i, mi in enumerate(self.irreps_in):
+            for o, mo in enumerate(self.out_list):
+                if mi.ir == mo.ir:
+                    w_off[(i, o)] = off
+                    off += mi.mul
+        self.weight_numel = off
+        irs = sorted({self.out_list[o].ir for o in used}, key=lambda ir: (ir.l, ir.p))
+        irs = [ir for ir in irs if any(mi.ir == ir for mi in self.irreps_in)]
+        slots = {ir: [o for o in used if self.out_list[o].ir == ir] for ir in irs}
+        self.sorted_irreps = Irreps([MulIr(len(slots[ir]), ir) for ir in irs])
+        offs = self.sorted_irreps.offsets()
+        self.pos = np.full(len(used), -1, dtype=np.int64)      # -1: no input slot carries this irrep -> output is 0
+        rank = {o: q for q, o in enumerate(used)}
+        for t, ir in enumerate(irs):
+            for w, o in enumerate(slots[ir]):
+                self.pos[rank[o]] = offs[t] + w * ir.dim
+        # column chunks: the row kernel keeps [in_dim + chunk columns] x 8 rows in shared memory
+        self.out_dim = self.sorted_irreps.dim
+        self.chunks = []   # (LinearOp, first column, gather index into the e3nn flat weight)
+        t0 = 0
+        while t0 < len(irs):
+            t1, cols = t0, 0
+            while t1 < len(irs) and (t1 == t0 or cols + self.sorted_irreps[t1].dim <= max_cols):
+                cols += self.sorted_irreps[t1].dim
+                t1 += 1
+            sub = Irreps(self.sorted_irreps.items[t0:t1])
+            op = LinearOp(self.irreps_in, sub)
+            gather = np.zeros(op.weight_numel, dtype=np.int64)
+            for b in op.blocks:
+                ir = sub[b.i_out].ir
+                for w, o in enumerate(slots[ir]):
+                    u = np.arange(b.mul_in)
+                    gather[b.w_off + u * b.mul_out + w] = w_off[(b.i_in, o)] + u
+            self.chunks.append((op, offs[t0], gather))
+            t0 = t1
+        self._dev: Dict[str, dict] = {}
+
+    def forward(self, weight: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """[rows, in_dim] -> [rows, out_dim] in the sorted layout (hgb_linear_forward_ld per column chunk)."""
+        L.require_cuda(x, weight)
+        x = L.f32c(x)
+        key = str(weight.device)
+        ent = self._dev.setdefault(key, {"ver": None})
+        ver = (weight._version, weight.data_ptr())
+        if ent["ver"] != ver:
+            if "gather" not in ent:
+                ent["gather"] = [torch.from_numpy(g).to(weight.device) for _, _, g in self.chunks]
+            flat = weight.detach().reshape(-1)
+            ent["w"] = [flat[g].contiguous() for g in ent["gather"]]
+            ent["ver"] = ver
+        n = x.shape[0]
+        y = torch.empty(n, self.out_dim, device=x.device, dtype=torch.float32)
+        lib, st = L.load(), L.stream_ptr(x.device)
+        for (op, col0, _), w in zip(self.chunks, ent["w"]):
+            plan = op.plan(w)
+            rc = lib.hgb_linear_forward_ld(C.byref(plan), x.data_ptr(), None, n, y.data_ptr() + 4 * col0, self.out_dim, 0, st)
+            L.check(rc, "hgb_linear_forward_ld")
+        return y
+
+
+def su2_slot_table(js: Sequence[Tuple[int, int]]):
+    """Slot list of E3TensorDecomposition(spinful=True) (hamgnn/nn/tensor_decomposition.py:471-541): per (l1, l2)
+    block the irreps (+)_L L, then for every L the (L x 1) irreps; returns (base irreps, per-block structure)."""
+    base, blocks, off = [], [], 0
+    for l1, l2 in js:
+        p = (-1) ** (l1 + l2)
+        Ls = list(range(abs(l1 - l2), l1 + l2 + 1))
+        start = off
+        l_off = []
+        for Lq in Ls:
+            base.append(MulIr(1, Ir(Lq, p)))
+            l_off.append(off)
+            off += 2 * Lq + 1
+        sp = []
+        for Lq in Ls:
+            ent = []
+            for Lp in range(abs(Lq - 1), Lq + 2):
+                base.append(MulIr(1, Ir(Lp, p)))
+                ent.append((Lp, off))
+                off += 2 * Lp + 1
+            sp.append(ent)
+        blocks.append(dict(l1=l1, l2=l2, Ls=Ls, l_off=l_off, sp=sp, start=start, end=off))
+    return Irreps(base), blocks
+
+
+class SocSU2Assembly:
+    """CSR form of E3TensorDecomposition.get_H (spinful; hamgnn/nn/tensor_decomposition.py:575-627) followed by
+    reorder_matrix and the (spin, orbital) interleave of hamgnn_output.py:3148-3153.
+
+    Input row: the used head outputs in SortedHeadOp layout -- slots [0, n_base) are the real halves, slots
+    [n_base, 2 n_base) the imaginary halves of the complex coefficients.  Output row: [2][2 nao][2 nao] floats
+    (real plane, imaginary plane) of the spin-orbital matrix with row index s1*nao + a, column s2*nao + b."""
+
+    def __init__(self, row: Irreps, col: Irreps, index_change: Sequence[int], basis_def: Dict[int, Sequence[int]],
+                 minus_index: Optional[Sequence[int]] = None):
+        nao = row.dim
+        assert col.dim == nao
+        self.nao = nao
+        js = [(li.ir.l, lj.ir.l) for li in row for lj in col]
+        self.base_irreps, blocks = su2_slot_table(js)
+        self.n_base_slots, self.base_dim = len(self.base_irreps), self.base_irreps.dim
+        self.hamiltonian_irreps_su2 = self.base_irreps * 2               # required_irreps_out (:543-544)
+        self.head_irreps = self.hamiltonian_irreps_su2 * 2               # `2*self.hamiltonian_irreps_su2` (hamgnn_output.py:193)
+        # used head slots: first copy (real halves) and third copy (imaginary halves); get_H never reads the rest
+        self.used = list(range(self.n_base_slots)) + list(range(2 * self.n_base_slots, 3 * self.n_base_slots))
+        s2 = math.sqrt(2.0)
+        oyzx = np.array([[1, 0, 1, 0], [0, -1j, 0, 1], [0, 1j, 0, 1], [1, 0, -1, 0]], dtype=np.complex128) / s2
+        # dense complex map M[j, a, b, c] per block, scattered into (out entry) -> [(base column, complex value)]
+        idx = list(index_change) if index_change is not None else list(range(nao))
+        inv_idx = {old: new for new, old in enumerate(idx)}              # raw orbital -> reordered position
+        sign = np.ones(nao)
+        if minus_index is not None:
+            sign[list(minus_index)] = -1
+        M2 = 2 * nao
+        entries: Dict[int, list] = {}
+        nrow = len(col)
+        r0 = c0 = 0
+        for bi, blk in enumerate(blocks):
+            l1, l2 = blk["l1"], blk["l2"]
+            d1, d2 = 2 * l1 + 1, 2 * l2 + 1
+            nc = blk["end"] - blk["start"]
+            # Hb[m, n, c]: (L-concatenated component m, spin index n) as a linear map of the block coefficients
+            Hb = np.zeros((d1 * d2, 4, nc))
+            wm = np.concatenate([so3.wigner_3j(l1, l2, Lq) for Lq in blk["Ls"]], axis=-1)      # [d1, d2, d1*d2]
+            m0 = 0
+            for qi, Lq in enumerate(blk["Ls"]):
+                dl = 2 * Lq + 1
+                for m in range(dl):
+                    Hb[m0 + m, 0, blk["l_off"][qi] - blk["start"] + m] = 1.0
+                for Lp, poff in blk["sp"][qi]:
+                    w = so3.wigner_3j(Lq, 1, Lp)                                              # [dl, 3, 2Lp+1]
+                    for m in range(dl):
+                        for k in range(3):
+                            Hb[m0 + m, 1 + k, poff - blk["start"]:poff - blk["start"] + 2 * Lp + 1] += w[m, k, :]
+                m0 += dl
+            T = np.einsum("mnc,abm,jn->jabc", Hb, wm, oyzx)                                    # [4, d1, d2, nc] complex
+            nzj, nza, nzb, nzc = np.nonzero(np.abs(T) > 1e-14)
+            for j, a, b_, c in zip(nzj, nza, nzb, nzc):
+                pa, pb = inv_idx[r0 + a], inv_idx[c0 + b_]
+                s1, s2_ = divmod(int(j), 2)
+                o = (s1 * nao + pa) * M2 + (s2_ * nao + pb)
+                entries.setdefault(o, []).append((blk["start"] + int(c), T[j, a, b_, c] * sign[pa] * sign[pb]))
+            if (bi + 1) % nrow == 0:
+                r0, c0 = r0 + d1, 0
+            else:
+                c0 += d2
+        self._entries = entries
+        mask = np.zeros((128, nao), dtype=np.uint8)
+        for Z, orbs in basis_def.items():
+            mask[int(Z), list(orbs)] = 1
+        self.mask = mask
+        self._dev = {}
+
+    def build_csr(self, pos: np.ndarray):
+        """CSR over the SortedHeadOp row: `pos[q]` = first column of used slot q (q < n_base: real, else imaginary)."""
+        # column of base coefficient c (flat over base irreps) -> (slot, component)
+        slot_of, comp_of = [], []
+        for q, m in enumerate(self.base_irreps):
+            for k in range(m.ir.dim):
+                slot_of.append(q)
+                comp_of.append(k)
+        nb = self.n_base_slots
+        M2 = 2 * self.nao
+        n_out = 2 * M2 * M2
+        row_ptr, colv, valv = [0], [], []
+        for plane in range(2):
+            for o in range(M2 * M2):
+                for c, v in self._entries.get(o, []):
+                    q, k = slot_of[c], comp_of[c]
+                    pre, pim = pos[q], pos[nb + q]
+                    # (re + i im) * (vr + i vi): real plane = vr re - vi im ; imaginary plane = vi re + vr im
+                    terms = ((pre, v.real), (pim, -v.imag)) if plane == 0 else ((pre, v.imag), (pim, v.real))
+                    for p_, val in terms:
+                        if p_ >= 0 and abs(val) > 1e-14:
+                            colv.append(int(p_) + k)
+                            valv.append(val)
+                row_ptr.append(len(colv))
+        self.row_ptr = np.asarray(row_ptr, dtype=np.int32)
+        self.col = np.asarray(colv, dtype=np.int32)
+        self.val = np.asarray(valv, dtype=np.float32)
+        self.n_out = n_out
+        return self
+
+    def tables(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(getattr(self, k)).to(device) for k in ("row_ptr", "col", "val", "mask")}
+        return self._dev[key]

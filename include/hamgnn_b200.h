@@ -145,6 +145,10 @@ typedef struct {
 /* y[r,:] = (accumulate ? y[r,:] : 0) + Linear(x[rows ? rows[r] : r, :]) */
 int hgb_linear_forward(const hgb_linear_plan* plan_host, const float* x, const int64_t* rows, int64_t n_rows,
                        float* y, int32_t accumulate, void* stream);
+/* same with an explicit output row stride ldy >= plan->out_dim (floats): writes columns [0, out_dim) of rows of a
+ * wider matrix -- used to evaluate a wide head Linear (SOC: hamgnn_output.py:190-198) in column chunks. */
+int hgb_linear_forward_ld(const hgb_linear_plan* plan_host, const float* x, const int64_t* rows, int64_t n_rows,
+                          float* y, int64_t ldy, int32_t accumulate, void* stream);
 
 typedef struct {
   /* e3nn Gate: input row = sorted/simplified (scalars | gates | gated), output row = scalars + gated */
@@ -184,6 +188,35 @@ int hgb_ham_assemble(const hgb_ham_plan* plan_host, const float* coef, int64_t n
 int hgb_ham_finalize(const hgb_ham_plan* plan_host, const float* raw, const int64_t* partner, const float* h0,
                      const int64_t* z, const int64_t* node_a, const int64_t* node_b, const int64_t* out_row,
                      int64_t n_rows, int32_t symmetrize, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a16: spin-orbit-coupling assembly (complex H, (2 nao)^2 spin-orbital blocks, real and imaginary planes).
+ *
+ * su2 basis -- replaces E3TensorDecomposition.get_H (hamgnn/nn/tensor_decomposition.py:575-627, spinful) +
+ * reorder_matrix + the (spin, orbital) interleave, symmetrize_{on,off}site_hamiltonian_soc, the per-spin-block
+ * orbital masks and +H0/+iH0 of HamGNNPlusPlusOut.forward (hamgnn/models/hamgnn_output.py:3146-3178, 3603-3608):
+ *   1. hgb_csr_rows applies the host-built sparse map (w3j(L,1,L') recoupling x w3j(l1,l2,L) x oyzx2spin, reorder
+ *      folded in) to the used head outputs:  y[r, o] = sum_nnz val * x[r, col],  y = [rows][2][2nao][2nao];
+ *   2. hgb_ham_finalize_su2:  H = sym ? 0.5 (raw[r] + conj(raw[partner[r]])^T) : raw[r];  zero where an orbital is
+ *      absent for z[node_a[r]] (rows) / z[node_b[r]] (columns);  += h0_re / h0_im;  written to row out_row[r] of
+ *      out_re / out_im ([*, (2nao)^2] each).
+ * so3 basis -- replaces the xi.L construction (hamgnn_output.py:3026-3144) and symmetrize_orbital_coefficients
+ * (:2367-2431): hgb_ksi_shell_average averages ksi over the m components of each shell [lo, hi) (rows, then
+ * columns, in place); hgb_ham_finalize_so3 builds  re: uu = dd = hns, ud = du = A_1;  im: uu = A_2, dd = -A_2,
+ * ud = A_0, du = -A_0  with A_c = sym ? 0.5 (ksi L_c - (ksi L_c)[partner]^T) : ksi L_c, lmat = [rows][nao^2][3];
+ * h0_offdiag_only != 0 skips h0_re on the uu/dd blocks (add_H_nonsoc, :3028-3049).
+ */
+int hgb_csr_rows(const int32_t* row_ptr, const int32_t* col, const float* val, int32_t n_out, int32_t n_in,
+                 const float* x, int64_t n_rows, float* y, void* stream);
+int hgb_ham_finalize_su2(int32_t nao, const uint8_t* orb_mask, const float* raw, const int64_t* partner,
+                         const float* h0_re, const float* h0_im, const int64_t* z, const int64_t* node_a,
+                         const int64_t* node_b, const int64_t* out_row, int64_t n_rows, int32_t symmetrize,
+                         float* out_re, float* out_im, void* stream);
+int hgb_ksi_shell_average(int32_t nao, const int32_t* blk_lo_host, const int32_t* blk_hi_host, int32_t n_blocks,
+                          float* ksi, int64_t n_rows, void* stream);
+int hgb_ham_finalize_so3(int32_t nao, const float* hns, const float* ksi, const float* lmat, const int64_t* partner,
+                         const float* h0_re, const float* h0_im, const int64_t* out_row, int64_t n_rows,
+                         int32_t symmetrize, int32_t h0_offdiag_only, float* out_re, float* out_im, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 GEMM building block (TMEM accumulator, interleaved K-major shared-memory

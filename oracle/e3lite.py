@@ -335,6 +335,9 @@ class Linear(torch.nn.Module):
                       for o, (_, io) in enumerate(self.irreps_out) if ii == io]
         self.weight_numel = sum(self.irreps_in[i][0] * self.irreps_out[o][0] for i, o in self.instr)
         self.weight = torch.nn.Parameter(torch.randn(self.weight_numel))
+        self._fan = {}
+        for i, o in self.instr:
+            self._fan[o] = self._fan.get(o, 0) + self.irreps_in[i][0]
 
     def forward(self, x):
         sin, sout = self.irreps_in.slices(), self.irreps_out.slices()
@@ -345,7 +348,7 @@ class Linear(torch.nn.Module):
             mo, _ = self.irreps_out[o]
             w = self.weight[off:off + mi * mo].view(mi, mo)
             off += mi * mo
-            fan = sum(self.irreps_in[a][0] for a, b in self.instr if b == o)
+            fan = self._fan[o]
             xi = x[:, sin[i]].reshape(-1, mi, ir.dim)
             y = torch.einsum("uw,zui->zwi", w, xi) / math.sqrt(fan)
             out[o] = y if out[o] is None else out[o] + y

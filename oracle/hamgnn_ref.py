@@ -20,6 +20,13 @@ with the same parameter names so that a reference state_dict maps 1:1:
   HamLayer / HamGNNOut       hamgnn/models/hamgnn_output.py:38-58, 258-272, 345-526, 851-891,
                              1056-1096, 1187-1285, 2288-2365, 2784-2872, 2916-2990, 3771-3799,
                              3966-4021  (non-SOC, non-magnetic branch)
+  SU2Decomposition           hamgnn/nn/tensor_decomposition.py:39-86 (irreps_from_l1l2), 439-627
+                             (E3TensorDecomposition, spinful=True: __init__ + get_H)
+  SOC branches of HamGNNOut  hamgnn/models/hamgnn_output.py:150-153, 188-211, 281-293 (ctor),
+                             3026-3144 (so3: xi.L construction), 3146-3178 (su2), 2367-2431
+                             (symmetrize_orbital_coefficients), 1231-1285 (is_soc / anti-hermitian
+                             symmetrisation), 3603-3625 (+H0, real;imag stacking), 3889-3931 (result dict)
+  overlap head               hamgnn/models/hamgnn_output.py:2996-3019, 4006-4014
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import it.
 """
@@ -364,6 +371,67 @@ def openmx_basis(nao_max):
     return idx, Irreps(row), bd
 
 
+class SU2Decomposition:
+    """E3TensorDecomposition(None, out_js_list, spinful=True) of hamgnn/nn/tensor_decomposition.py:439-627.
+
+    Per (l1, l2) block the network output holds the irreps  (+)_L L  followed by, for every L, (L x 1) =
+    (+)_{L'=|L-1|}^{L+1} L'  (irreps_from_l1l2, :39-86), all with parity (-1)^(l1+l2); the whole list is then
+    repeated once more (real half | imaginary half, :543-544).  get_H (:575-627) recouples (L x 1) with
+    w3j(L, 1, L'), couples (L, n) back to the orbital pair with w3j(l1, l2, L) and maps the spin index
+    n = (scalar; y, z, x) to the four spin blocks (uu, ud, du, dd) with `oyzx2spin` (:557-564)."""
+
+    def __init__(self, out_js_list, nao_max):
+        self.out_js_list, self.nao_max = list(out_js_list), nao_max
+        base = []
+        self.in_slices, self.in_slices_sp, self.wms, self.wms_sp = [0], [], [], []
+        dim = 0
+        for l1, l2 in self.out_js_list:
+            p = (-1) ** (l1 + l2)
+            Ls = list(range(abs(l1 - l2), l1 + l2 + 1))
+            base += [(1, (L, p)) for L in Ls]
+            sl = [0, sum(2 * L + 1 for L in Ls)]
+            wm_sp = [None]
+            for L in Ls:
+                L1s = list(range(abs(L - 1), L + 2))
+                base += [(1, (Lp, p)) for Lp in L1s]
+                sl.append(sl[-1] + sum(2 * Lp + 1 for Lp in L1s))
+                wm_sp.append(torch.cat([wigner_3j(L, 1, Lp, dtype=torch.float64) for Lp in L1s], dim=-1))
+            dim += sl[-1]
+            self.in_slices.append(dim)
+            self.in_slices_sp.append(sl)
+            self.wms.append(torch.cat([wigner_3j(l1, l2, L, dtype=torch.float64) for L in Ls], dim=-1))
+            self.wms_sp.append(wm_sp)
+        self.base_irreps = Irreps(base)
+        self.required_irreps_out = Irreps(base + base)          # :543-544
+        s2 = math.sqrt(2.0)
+        self.oyzx2spin = torch.tensor([[1, 0, 1, 0], [0, -1j, 0, 1], [0, 1j, 0, 1], [1, 0, -1, 0]],
+                                      dtype=torch.complex128) / s2
+
+    def get_H(self, net_out):
+        cdt = torch.complex128 if net_out.dtype == torch.float64 else torch.complex64
+        half = net_out.shape[-1] // 2
+        c = torch.complex(net_out[:, :half], net_out[:, half:])
+        n = c.shape[0]
+        block = torch.zeros(n, 4, self.nao_max, self.nao_max, dtype=cdt)
+        nrow = int(math.isqrt(len(self.out_js_list)))
+        si = sj = 0
+        for i, (l1, l2) in enumerate(self.out_js_list):
+            blk = c[:, self.in_slices[i]:self.in_slices[i + 1]]
+            d1, d2 = 2 * l1 + 1, 2 * l2 + 1
+            sl = self.in_slices_sp[i]
+            parts = []
+            for j in range(1, len(self.wms_sp[i])):
+                parts.append(torch.einsum("jkl,il->ijk", self.wms_sp[i][j].to(cdt), blk[:, sl[j]:sl[j + 1]]))
+            Hb = torch.cat([blk[:, sl[0]:sl[1]].unsqueeze(-1), torch.cat(parts, dim=-2)], dim=-1)   # [n, d1*d2, 4]
+            Hb = torch.einsum("imn,klm,jn->ijkl", Hb, self.wms[i].to(cdt), self.oyzx2spin.to(cdt))
+            block[:, :, si:si + d1, sj:sj + d2] += Hb
+            if (i + 1) % nrow == 0:
+                si, sj = si + d1, 0
+            else:
+                sj += d2
+        return block
+
+
 class HamLayer(nn.Module):
     def __init__(self, irreps_in, feature_irreps_hidden, irreps_out):
         super().__init__()
@@ -375,14 +443,17 @@ class HamLayer(nn.Module):
 
 
 class HamGNNPlusPlusOut(nn.Module):
-    """Non-SOC / non-magnetic branch of hamgnn/models/hamgnn_output.py (openmx basis)."""
+    """hamgnn/models/hamgnn_output.py (openmx basis): the non-SOC branch, the two SOC branches (soc_basis 'su2' and
+    'so3', non-collinear, not spin-constrained) and the overlap head (ham_only=False)."""
 
     def __init__(self, irreps_in_node, irreps_in_edge, nao_max=19, ham_type="openmx", ham_only=True,
-                 symmetrize=True, add_H0=False, zero_point_shift=False, calculate_sparsity=True):
+                 symmetrize=True, add_H0=False, zero_point_shift=False, calculate_sparsity=True,
+                 soc_switch=False, soc_basis="so3", add_H_nonsoc=False):
         super().__init__()
         assert ham_type.lower() == "openmx"
         self.nao_max, self.symmetrize, self.add_H0 = nao_max, symmetrize, add_H0
         self.ham_only, self.zero_point_shift, self.calculate_sparsity = ham_only, zero_point_shift, calculate_sparsity
+        self.soc_switch, self.soc_basis, self.add_H_nonsoc = soc_switch, soc_basis.lower(), add_H_nonsoc
         idx, self.row, self.basis_def = openmx_basis(nao_max)
         self.col = self.row
         self.index_change = torch.tensor(idx, dtype=torch.long)
@@ -395,6 +466,23 @@ class HamGNNPlusPlusOut(nn.Module):
         self.ham_dims = [ir.dim for _, ir in self.hamiltonian_irreps]
         self.onsite_hamiltonian_network = HamLayer(irreps_in_node, irreps_in_node, self.hamiltonian_irreps)
         self.offsite_hamiltonian_network = HamLayer(irreps_in_edge, irreps_in_edge, self.hamiltonian_irreps)
+        if soc_switch:
+            if self.soc_basis == "su2":                                    # :190-198, 281-293
+                js = [(li.l, lj.l) for _, li in self.row for _, lj in self.col]
+                self.hamiltonian_decomposition = SU2Decomposition(js, nao_max)
+                self.hamiltonian_irreps_su2 = self.hamiltonian_decomposition.required_irreps_out
+                head = 2 * self.hamiltonian_irreps_su2                     # list repetition, as `2*o3.Irreps`
+                self.onsite_hamiltonian_network = HamLayer(irreps_in_node, irreps_in_node, head)
+                self.offsite_hamiltonian_network = HamLayer(irreps_in_edge, irreps_in_edge, head)
+            elif self.soc_basis == "so3":                                  # :200-209
+                ksi = Irreps([(nao_max ** 2, (0, 1))])
+                self.onsite_ksi_network = HamLayer(irreps_in_node, irreps_in_node, ksi)
+                self.offsite_ksi_network = HamLayer(irreps_in_edge, irreps_in_edge, ksi)
+            else:
+                raise NotImplementedError(f"SOC basis '{soc_basis}' not supported!")
+        if not ham_only:                                                   # :245-254
+            self.onsite_overlap_network = HamLayer(irreps_in_node, irreps_in_node, self.hamiltonian_irreps)
+            self.offsite_overlap_network = HamLayer(irreps_in_edge, irreps_in_edge, self.hamiltonian_irreps)
 
     def merge_tensor_components(self, comps):
         B = comps[0].shape[0]
@@ -416,15 +504,31 @@ class HamGNNPlusPlusOut(nn.Module):
         m = m[:, self.index_change[:, None], self.index_change[None, :]]
         return m.reshape(-1, self.nao_max ** 2)
 
-    def _sym(self, M, inv=None):
+    def _sym(self, M, inv=None, hermitian=True):
+        """symmetrize_hamiltonian :1231-1285 (real blocks): 0.5 (H +- H[inv]^T)."""
         if not self.symmetrize:
             return M
         m = M.reshape(-1, self.nao_max, self.nao_max)
         other = m if inv is None else m[inv]
-        return (0.5 * (m + other.permute(0, 2, 1))).reshape(-1, self.nao_max ** 2)
+        sgn = 1.0 if hermitian else -1.0
+        return (0.5 * (m + sgn * other.permute(0, 2, 1))).reshape(-1, self.nao_max ** 2)
+
+    def symmetrize_orbital_coefficients(self, M):
+        """:2367-2431 -- average over the m components of every p/d/f shell, rows first, then columns."""
+        m = M.reshape(-1, self.nao_max, self.nao_max).clone()
+        blocks = [(3, 6), (6, 9), (9, 14)] if self.nao_max >= 14 else []
+        if self.nao_max >= 19:
+            blocks.append((14, 19))
+        if self.nao_max == 26:
+            blocks.append((19, 26))
+        for a, b in blocks:
+            m[:, a:b] = m[:, a:b].mean(dim=1, keepdim=True).expand(-1, b - a, -1)
+        for a, b in blocks:
+            m[:, :, a:b] = m[:, :, a:b].mean(dim=2, keepdim=True).expand(-1, -1, b - a)
+        return m.reshape(M.shape[0], -1)
 
     def _mask(self, Hon, Hoff, data):
-        tab = torch.zeros(99, self.nao_max, dtype=Hon.dtype)
+        tab = torch.zeros(99, self.nao_max, dtype=Hon.real.dtype)
         for Z, orb in self.basis_def.items():
             tab[Z, orb] = 1
         z = data["z"]
@@ -477,22 +581,110 @@ class HamGNNPlusPlusOut(nn.Module):
         off0 = torch.cumsum(epc, 0) - epc
         inv = data["inv_edge_idx"] + off0[data["batch"][src]]
 
-        c_on = torch.split(self.onsite_hamiltonian_network(rep["node_attr"]), self.ham_dims, dim=-1)
-        Hon = self._sym(self.reorder_matrix(self.merge_tensor_components(c_on)))
-        if self.add_H0:
-            Hon = Hon + data["Hon0"]
-        c_off = torch.split(self.offsite_hamiltonian_network(rep["edge_attr"]), self.ham_dims, dim=-1)
-        Hoff = self._sym(self.reorder_matrix(self.merge_tensor_components(c_off)), inv)
-        if self.add_H0:
-            Hoff = Hoff + data["Hoff0"]
-        Hon, Hoff = self._mask(Hon, Hoff, data)
-        H = self.concat_by_crystal(data, Hon, Hoff)
-        if self.zero_point_shift:
-            S = data["overlap"]
-            sel = S > 1e-6
-            shift = (H - data["hamiltonian"])[sel].sum() / S[sel].sum()
-            H = H - shift * S
-        res = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+        nao = self.nao_max
+        overlap = None
+        if not self.ham_only:                                              # :2996-3019
+            s_on = torch.split(self.onsite_overlap_network(rep["node_attr"]), self.ham_dims, dim=-1)
+            Son = self._sym(self.reorder_matrix(self.merge_tensor_components(s_on)))
+            s_off = torch.split(self.offsite_overlap_network(rep["edge_attr"]), self.ham_dims, dim=-1)
+            Soff = self._sym(self.reorder_matrix(self.merge_tensor_components(s_off)), inv)
+            Son, Soff = self._mask(Son, Soff, data)
+            overlap = self.concat_by_crystal(data, Son, Soff)
+
+        if self.soc_switch:
+            if self.soc_basis == "su2":                                    # :3146-3178
+                dec = self.hamiltonian_decomposition
+
+                def spin_matrix(net_out):
+                    Hc = dec.get_H(net_out)                                # [n, 4, nao, nao] complex
+                    Hc = Hc.reshape(-1, nao, nao)[:, self.index_change[:, None], self.index_change[None, :]]
+                    Hc = Hc.reshape(-1, 2, 2, nao, nao).transpose(2, 3)    # [n, s1, a, s2, b]
+                    return Hc.reshape(-1, 2 * nao, 2 * nao)
+
+                Hon = spin_matrix(self.onsite_hamiltonian_network(rep["node_attr"]))
+                Hoff = spin_matrix(self.offsite_hamiltonian_network(rep["edge_attr"]))
+                if self.symmetrize:
+                    Hon = 0.5 * (Hon + Hon.conj().transpose(1, 2))
+                    Hoff = 0.5 * (Hoff + Hoff[inv].conj().transpose(1, 2))
+                Hon, Hoff = Hon.reshape(-1, 2, nao, 2, nao).clone(), Hoff.reshape(-1, 2, nao, 2, nao).clone()
+                for a in range(2):
+                    for b in range(2):
+                        Hon[:, a, :, b, :], Hoff[:, a, :, b, :] = self._mask(Hon[:, a, :, b, :], Hoff[:, a, :, b, :], data)
+                Hon, Hoff = Hon.reshape(-1, (2 * nao) ** 2), Hoff.reshape(-1, (2 * nao) ** 2)
+                on_re, on_im, off_re, off_im = Hon.real, Hon.imag, Hoff.real, Hoff.imag
+            else:                                                          # so3, :3026-3144
+                if self.add_H_nonsoc:
+                    Hon_ns, Hoff_ns = data["Hon_nonsoc"], data["Hoff_nonsoc"]
+                    for key in ("Hon0", "Hoff0"):
+                        h0 = data[key].reshape(-1, 2 * nao, 2 * nao).clone()
+                        h0[:, :nao, :nao] = 0
+                        h0[:, nao:, nao:] = 0
+                        data[key] = h0.reshape(-1, (2 * nao) ** 2)
+                else:
+                    c_on = torch.split(self.onsite_hamiltonian_network(rep["node_attr"]), self.ham_dims, dim=-1)
+                    Hon_ns = self._sym(self.reorder_matrix(self.merge_tensor_components(c_on)))
+                    c_off = torch.split(self.offsite_hamiltonian_network(rep["edge_attr"]), self.ham_dims, dim=-1)
+                    Hoff_ns = self._sym(self.reorder_matrix(self.merge_tensor_components(c_off)), inv)
+                    Hon_ns, Hoff_ns = self._mask(Hon_ns, Hoff_ns, data)
+                ksi_on = self.symmetrize_orbital_coefficients(self.onsite_ksi_network(rep["node_attr"]))
+                ksi_off = self.symmetrize_orbital_coefficients(self.offsite_ksi_network(rep["edge_attr"]))
+
+                def build(Hns, ksi, Lmat, inv_):
+                    A = [self._sym(ksi * Lmat[:, :, c], inv_, hermitian=False).reshape(-1, nao, nao) for c in range(3)]
+                    re = Hns.new_zeros(Hns.shape[0], 2 * nao, 2 * nao)
+                    im = torch.zeros_like(re)
+                    re[:, :nao, :nao] = Hns.reshape(-1, nao, nao)
+                    re[:, nao:, nao:] = Hns.reshape(-1, nao, nao)
+                    re[:, :nao, nao:] = A[1]
+                    re[:, nao:, :nao] = A[1]
+                    im[:, :nao, :nao] = A[2]
+                    im[:, nao:, nao:] = -A[2]
+                    im[:, :nao, nao:] = A[0]
+                    im[:, nao:, :nao] = -A[0]
+                    return re.reshape(-1, (2 * nao) ** 2), im.reshape(-1, (2 * nao) ** 2)
+
+                on_re, on_im = build(Hon_ns, ksi_on, data["Lon"], None)
+                off_re, off_im = build(Hoff_ns, ksi_off, data["Loff"], inv)
+            if self.add_H0:                                                # :3603-3608
+                on_re, off_re = on_re + data["Hon0"], off_re + data["Hoff0"]
+                on_im, off_im = on_im + data["iHon0"], off_im + data["iHoff0"]
+            H_re = self.concat_by_crystal(data, on_re, off_re)
+            H_im = self.concat_by_crystal(data, on_im, off_im)
+            if "Hon" in data and "iHon" in data:                           # :3618-3625
+                data["hamiltonian_real"] = self.concat_by_crystal(data, data["Hon"], data["Hoff"])
+                data["hamiltonian_imag"] = self.concat_by_crystal(data, data["iHon"], data["iHoff"])
+                data["hamiltonian"] = torch.cat((data["hamiltonian_real"], data["hamiltonian_imag"]), dim=0)
+            if self.zero_point_shift:                                      # :3893-3919
+                S = data["overlap"].reshape(-1, nao, nao)
+                Hr = H_re.reshape(-1, 2, nao, 2, nao).clone()
+                Tr = data["hamiltonian_real"].reshape(-1, 2, nao, 2, nao)
+                sel = S > 1e-6
+                diff = (Hr[:, 0, :, 0, :] + Hr[:, 1, :, 1, :]) - (Tr[:, 0, :, 0, :] + Tr[:, 1, :, 1, :])
+                shift = diff[sel].sum() / (2.0 * S[sel].sum())
+                Hr[:, 0, :, 0, :] = Hr[:, 0, :, 0, :] - shift * S
+                Hr[:, 1, :, 1, :] = Hr[:, 1, :, 1, :] - shift * S
+                H_re = Hr.reshape(-1, (2 * nao) ** 2)
+            res = {"hamiltonian": torch.cat((H_re, H_im), dim=0), "hamiltonian_real": H_re, "hamiltonian_imag": H_im,
+                   "band_energy": None, "wavefunction": None}
+        else:
+            c_on = torch.split(self.onsite_hamiltonian_network(rep["node_attr"]), self.ham_dims, dim=-1)
+            Hon = self._sym(self.reorder_matrix(self.merge_tensor_components(c_on)))
+            if self.add_H0:
+                Hon = Hon + data["Hon0"]
+            c_off = torch.split(self.offsite_hamiltonian_network(rep["edge_attr"]), self.ham_dims, dim=-1)
+            Hoff = self._sym(self.reorder_matrix(self.merge_tensor_components(c_off)), inv)
+            if self.add_H0:
+                Hoff = Hoff + data["Hoff0"]
+            Hon, Hoff = self._mask(Hon, Hoff, data)
+            H = self.concat_by_crystal(data, Hon, Hoff)
+            if self.zero_point_shift:
+                S = data["overlap"]
+                sel = S > 1e-6
+                shift = (H - data["hamiltonian"])[sel].sum() / S[sel].sum()
+                H = H - shift * S
+            res = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+        if overlap is not None:
+            res["overlap"] = overlap
         if self.calculate_sparsity:
             res["sparsity_ratio"] = self.sparsity_ratio(data)
         return res

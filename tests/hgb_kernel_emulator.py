@@ -180,3 +180,74 @@ def emulate_msgpack_tc(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, sh,
     if out_rows is None:
         return msg
     return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)
+
+
+# ------------------------------------------------------------------------------------------------ SOC (a16)
+def emulate_sorted_head(head, weight, x):
+    """SortedHeadOp.forward: one emulate_linear per column chunk on the gathered weights."""
+    y = torch.zeros(x.shape[0], head.out_dim, dtype=x.dtype)
+    flat = weight.detach().reshape(-1).to(x.dtype)
+    for op, col0, gather in head.chunks:
+        y[:, col0:col0 + op.irreps_out.dim] = emulate_linear(op, flat[torch.from_numpy(gather)], x)
+    return y
+
+
+def emulate_csr_rows(row_ptr, col, val, n_out, x):
+    y = torch.zeros(x.shape[0], n_out, dtype=x.dtype)
+    v = torch.from_numpy(val).to(x.dtype)
+    rows = np.repeat(np.arange(n_out), np.diff(row_ptr))
+    y.index_add_(1, torch.from_numpy(rows).long(), x[:, torch.from_numpy(col).long()] * v)
+    return y
+
+
+def emulate_finalize_su2(nao, mask_tab, raw, partner, h0_re, h0_im, z, na, nb, symmetrize=True):
+    """ham_finalize_su2_kernel: raw = [rows][2][M][M]; returns (real rows, imaginary rows)."""
+    M = 2 * nao
+    re, im = raw[:, :M * M].reshape(-1, M, M), raw[:, M * M:].reshape(-1, M, M)
+    if symmetrize:
+        o_re, o_im = (re, im) if partner is None else (re[partner], im[partner])
+        re, im = 0.5 * (re + o_re.transpose(1, 2)), 0.5 * (im - o_im.transpose(1, 2))
+    mask = torch.from_numpy(mask_tab).to(raw.dtype)
+    za = z if na is None else z[na]
+    zb = z if nb is None else z[nb]
+    m2 = (mask[za].repeat(1, 2)[:, :, None] * mask[zb].repeat(1, 2)[:, None, :])
+    re, im = (re * m2).reshape(-1, M * M), (im * m2).reshape(-1, M * M)
+    if h0_re is not None:
+        re = re + h0_re
+    if h0_im is not None:
+        im = im + h0_im
+    return re, im
+
+
+def emulate_ksi_shell_average(nao, shells, ksi):
+    m = ksi.reshape(-1, nao, nao).clone()
+    for a, b in shells:
+        m[:, a:b] = m[:, a:b].mean(dim=1, keepdim=True).expand(-1, b - a, -1)
+    for a, b in shells:
+        m[:, :, a:b] = m[:, :, a:b].mean(dim=2, keepdim=True).expand(-1, -1, b - a)
+    return m.reshape(ksi.shape[0], -1)
+
+
+def emulate_finalize_so3(nao, hns, ksi, lmat, partner, h0_re, h0_im, symmetrize=True, h0_offdiag_only=False):
+    M = 2 * nao
+    A = []
+    for c in range(3):
+        a = (ksi * lmat[:, :, c]).reshape(-1, nao, nao)
+        if symmetrize:
+            o = a if partner is None else a[partner]
+            a = 0.5 * (a - o.transpose(1, 2))
+        A.append(a)
+    h = hns.reshape(-1, nao, nao)
+    re = torch.zeros(h.shape[0], M, M, dtype=hns.dtype)
+    im = torch.zeros_like(re)
+    re[:, :nao, :nao], re[:, nao:, nao:], re[:, :nao, nao:], re[:, nao:, :nao] = h, h, A[1], A[1]
+    im[:, :nao, :nao], im[:, nao:, nao:], im[:, :nao, nao:], im[:, nao:, :nao] = A[2], -A[2], A[0], -A[0]
+    if h0_re is not None:
+        h0 = h0_re.reshape(-1, M, M).clone()
+        if h0_offdiag_only:
+            h0[:, :nao, :nao] = 0
+            h0[:, nao:, nao:] = 0
+        re = re + h0
+    if h0_im is not None:
+        im = im + h0_im.reshape(-1, M, M)
+    return re.reshape(-1, M * M), im.reshape(-1, M * M)
