@@ -358,7 +358,7 @@ constexpr int GN = 128;   // W3 column tile
 
 constexpr int GATE_SMEM_FLOATS = GE * 65 + 64 * (GE + 4) + 64 * GN;
 
-__global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant__ GateArgs a) {
+__global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_constant__ GateArgs a) {
   extern __shared__ __align__(16) float gsm[];
   float (*sH)[GE + 4] = reinterpret_cast<float (*)[GE + 4]>(gsm);                       // h2, K-major: sH[h][z]
   float (*sB)[GN] = reinterpret_cast<float (*)[GN]>(gsm + 64 * (GE + 4));              // W3 tile
@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant_
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
       for (int h = 0; h < a.h2dim; ++h) {
         const float4 av = *reinterpret_cast<const float4*>(&sH[h][ty * 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&sB[h][tx * 8]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&sB[h][tx * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&sB[h][tx * 4]);        // columns tx*4.. and 64+tx*4..: the 16 lanes of
+        const float4 b1 = *reinterpret_cast<const float4*>(&sB[h][64 + tx * 4]);   // a half warp read 256 contiguous bytes (no bank conflict)
         const float ar[4] = {av.x, av.y, av.z, av.w};
         const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -437,10 +437,12 @@ __global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant_
       for (int i = 0; i < 4; ++i) {
         const int z = ty * 4 + i;
         if (z < ne) {
-          float* gr = gb + (size_t)z * a.gstride + n0 + tx * 8;
+          float* gr = gb + (size_t)z * a.gstride + n0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (n0 + tx * 8 + j < nch) gr[j] = acc[i][j];
+          for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+            if (n0 + c < nch) gr[c] = acc[i][j];
+          }
         }
       }
       __syncthreads();
@@ -449,8 +451,66 @@ __global__ void __launch_bounds__(256) radial_gate_kernel(const __grid_constant_
 }
 
 #include "msgpack_tcr_kernel.cuh"
+#include "radial_gate_tc_kernel.cuh"
+
+// Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
+// MLP widths fit its tiling, the fp32-FMA kernel otherwise.
+int launch_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int32_t* w3_off, const int32_t* nch,
+                       const int32_t* w3img_off, int32_t gstride, float* g_ws, int64_t n_edges, cudaStream_t st) {
+  for (int b = 0; b < plan->n_branches; ++b)
+    HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "radial gate: width %d exceeds stride %d", nch[b], gstride);
+  const bool tc_ok = w3img_off != nullptr && plan->h2 % 8 == 0 && plan->h2 <= gtc::KMAX && plan->h1 % 4 == 0 &&
+                     plan->h1 <= 64 && plan->rbf_dim <= 64 && gstride % 4 == 0;
+  if (tc_ok) {
+    gtc::Args ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.rbf_dim = plan->rbf_dim; ga.h1 = plan->h1; ga.h2dim = plan->h2;
+    ga.gstride = gstride; ga.act_const = plan->act_const;
+    for (int b = 0; b < plan->n_branches; ++b) {
+      HGB_CHECK_ARG(w3img_off[b] >= 0 && w3img_off[b] % 4 == 0, "radial gate: packed W3 tiles of branch %d are not 16-byte aligned", b);
+      ga.w1[b] = plan->wbuf + plan->fc1_off[b];
+      ga.w2[b] = plan->wbuf + plan->fc2_off[b];
+      ga.w3img[b] = plan->wbuf + w3img_off[b];
+      ga.nch[b] = nch[b];
+    }
+    constexpr size_t smem = (size_t)gtc::Sm::TOTAL * sizeof(float);
+    static_assert(smem <= 200 * 1024, "radial_gate_tc_kernel shared memory");
+    HGB_CUDA_OK(cudaFuncSetAttribute(gtc::radial_gate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n_edges + ROWS - 1) / ROWS), (unsigned)plan->n_branches);
+    gtc::radial_gate_tc_kernel<<<grid, gtc::NT, smem, st>>>(ga);
+    HGB_LAUNCH_OK("radial_gate_tc_kernel");
+    return 0;
+  }
+  GateArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.n_branches = plan->n_branches; ga.rbf_dim = plan->rbf_dim;
+  ga.h1 = plan->h1; ga.h2dim = plan->h2; ga.gstride = gstride; ga.act_const = plan->act_const;
+  for (int b = 0; b < plan->n_branches; ++b) {
+    ga.w1[b] = plan->wbuf + plan->fc1_off[b];
+    ga.w2[b] = plan->wbuf + plan->fc2_off[b];
+    ga.w3[b] = plan->wbuf + w3_off[b];
+    ga.nch[b] = nch[b];
+  }
+  constexpr size_t gate_smem = (size_t)GATE_SMEM_FLOATS * sizeof(float);
+  HGB_CUDA_OK(cudaFuncSetAttribute(radial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
+  radial_gate_kernel<<<(unsigned)((n_edges + GE - 1) / GE), 256, gate_smem, st>>>(ga);
+  HGB_LAUNCH_OK("radial_gate_kernel");
+  return 0;
+}
 
 }  // namespace
+
+// The radial gate alone (for tests and for callers that keep g): g_ws[b][e][c], c < nch[b], row stride gstride.
+extern "C" int hgb_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int32_t* w3_off, const int32_t* nch,
+                               const int32_t* w3img_off, int32_t gstride, float* g_ws, int64_t n_edges, void* stream) {
+  HGB_CHECK_ARG(plan && rbf && g_ws && w3_off && nch, "hgb_radial_gate: NULL argument");
+  HGB_CHECK_ARG(plan->n_branches >= 1 && plan->n_branches <= 2, "hgb_radial_gate: bad branch count");
+  HGB_CHECK_ARG(plan->h2 <= 64 && plan->h1 <= 64 && plan->rbf_dim <= 64,
+                "hgb_radial_gate: radial MLP [%d,%d,%d] unsupported (all widths <= 64)", plan->rbf_dim, plan->h1, plan->h2);
+  HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_radial_gate: bad edge count");
+  if (n_edges == 0) return 0;
+  return launch_radial_gate(plan, rbf, w3_off, nch, w3img_off, gstride, g_ws, n_edges, (cudaStream_t)stream);
+}
 
 // g_ws: device workspace of n_branches * n_edges * gstride floats (gstride >= max n_channels).  w3_off[b] / nch[b]:
 // offset (floats, into plan->wbuf) of the pre-scaled last radial layer [h2][nch_b] and its width.  paths[].pad0
@@ -459,6 +519,15 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
                                        const int64_t* const* src_rows, const float* sh, const float* rbf,
                                        const int32_t* w3_off, const int32_t* nch, int32_t gstride, float* g_ws,
                                        int64_t n_edges, float* out, const int64_t* out_index, void* stream) {
+  return hgb_msgpack_tcg_forward_v2(plan, src, src_rows, sh, rbf, w3_off, nch, nullptr, gstride, g_ws, n_edges, out, out_index, stream);
+}
+
+// w3img_off (nullable): offsets into plan->wbuf of the per-branch packed W3 tiles for the tensor-core gate pre-pass.
+extern "C" int hgb_msgpack_tcg_forward_v2(const hgb_msgpack_plan* plan, const float* const* src,
+                                          const int64_t* const* src_rows, const float* sh, const float* rbf,
+                                          const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off,
+                                          int32_t gstride, float* g_ws, int64_t n_edges, float* out,
+                                          const int64_t* out_index, void* stream) {
   HGB_CHECK_ARG(plan && src && sh && rbf && out && g_ws && w3_off && nch, "hgb_msgpack_tcg_forward: NULL argument");
   HGB_CHECK_ARG(plan->types_host && plan->paths_host, "hgb_msgpack_tcg_forward: host copies of the type/path tables are required");
   HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
@@ -470,17 +539,8 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
   if (n_edges == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
 
-  GateArgs ga;
-  memset(&ga, 0, sizeof(ga));
-  ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.n_branches = plan->n_branches; ga.rbf_dim = plan->rbf_dim;
-  ga.h1 = plan->h1; ga.h2dim = plan->h2; ga.gstride = gstride; ga.act_const = plan->act_const;
-  for (int b = 0; b < plan->n_branches; ++b) {
+  for (int b = 0; b < plan->n_branches; ++b)
     HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "hgb_msgpack_tcg_forward: gate width %d exceeds stride %d", nch[b], gstride);
-    ga.w1[b] = plan->wbuf + plan->fc1_off[b];
-    ga.w2[b] = plan->wbuf + plan->fc2_off[b];
-    ga.w3[b] = plan->wbuf + w3_off[b];
-    ga.nch[b] = nch[b];
-  }
   // slot classes: 0 = scalar slots (d3 == 1, up to 64 channels) on msgpack_tcg_kernel<64,256,32>;
   // 1 / 2 = l >= 1 slots padded to 16 / 32 channels on the rows-in-lanes pipeline msgpack_tcr_kernel<16 / 32>
   // (HGB_TCG_ROWS=0 keeps them on msgpack_tcg_kernel<32,128,16>, the r01j kernel, for A/B measurements).
@@ -544,10 +604,10 @@ extern "C" int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan, const float
     }
     a.sh = sh; a.g = g_ws; a.gstride = gstride; a.n_edges = n_edges; a.out = out; a.out_index = out_index;
   }
-  constexpr size_t gate_smem = (size_t)GATE_SMEM_FLOATS * sizeof(float);
-  HGB_CUDA_OK(cudaFuncSetAttribute(radial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
-  radial_gate_kernel<<<(unsigned)((n_edges + GE - 1) / GE), 256, gate_smem, st>>>(ga);
-  HGB_LAUNCH_OK("radial_gate_kernel");
+  {
+    const int rc = launch_radial_gate(plan, rbf, w3_off, nch, w3img_off, gstride, g_ws, n_edges, st);
+    if (rc != 0) return rc;
+  }
 
   if (ctas[0] > 0) {
     constexpr size_t smem = (size_t)SmemG<64, 32>::TOTAL * sizeof(float);

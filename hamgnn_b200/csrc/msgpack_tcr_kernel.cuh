@@ -289,23 +289,25 @@ __global__ void __launch_bounds__(NTHR, (RW == 16 ? 4 : 2)) msgpack_tcr_kernel(c
     };
     // gate of gated path number qg: B_q <- (B_q . g) hi in place, (B.g) lo block; then hand over to the MMA warp
     auto do_gate = [&](int branch, int goff, int qg) {
+      // the gate values are fetched BEFORE the barrier waits so that their latency overlaps the drain of GEMM1
+      // (the row segment was pulled into L2 when the path started, see the prefetch below)
+      const float* gp = a.g + ((size_t)branch * a.n_edges + (size_t)(e0 + my_z)) * a.gstride + goff;
+      float gv[mp];
+#pragma unroll
+      for (int j = 0; j < mp; ++j) gv[j] = (live && j < ty.mul) ? __ldg(gp + j) : 0.f;
       warp_wait(&bfull[qg & 1], (uint32_t)((qg >> 1) & 1));
       if (qg >= 1) warp_wait(&gdone, (uint32_t)((qg - 1) & 1));   // GEMM2 of the previous gated path has read (B.g) lo
       tc::fence_after_sync();
-      const float* gp = a.g + ((size_t)branch * a.n_edges + (size_t)(e0 + my_z)) * a.gstride + goff;
       const uint32_t bq = tmem + lane_base + ((qg & 1) ? TM::B1 : TM::B0);
 #pragma unroll
       for (int c0 = 0; c0 < mp; c0 += 8) {
-        float gv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gv[j] = (live && c0 + j < ty.mul) ? __ldg(gp + c0 + j) : 0.f;
         uint32_t rb[8], hi[8], lo[8];
         tc::tmem_ld8(bq + c0, rb);
         tc::tmem_ld_wait8(rb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float h, l;
-          tc::split_tf32(__uint_as_float(rb[j]) * gv[j], h, l);
+          tc::split_tf32(__uint_as_float(rb[j]) * gv[c0 + j], h, l);
           hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
         }
         tc::tmem_st8(bq + c0, hi);
@@ -375,15 +377,34 @@ __global__ void __launch_bounds__(NTHR, (RW == 16 ? 4 : 2)) msgpack_tcr_kernel(c
         c_tkey = tkey;
         if (!t_same)
           for (int i = 0; i < c_d1; ++i) tcol[i * NPROD] = 0.f;
+        if (live && c_kind == 0 && my_k == 0) {
+          // pull this path's gate row segment (mp floats of the [E, n_channels] gate tensor, streamed from HBM)
+          // into L2 now; do_gate reads it one path later
+          const float* gp = a.g + ((size_t)c_branch * a.n_edges + (size_t)(e0 + my_z)) * a.gstride + c_goff;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + ty.mul - 1));
+        }
         if (live && !t_same) {
           if (c_kind == 0) {
             const float* yz = a.sh + (e0 + my_z) * S + pa.sh_off;
             const int* cij = P.cg_ij + pa.cg_off;
             const float* cval = P.cg_val + pa.cg_off;
-            const int n0 = P.cg_kstart[pa.cg_kstart + my_k], n1 = P.cg_kstart[pa.cg_kstart + my_k + 1];
-            for (int c = n0; c < n1; ++c) {
-              const int ij = cij[c];
-              tcol[(ij & 255) * NPROD] += cval[c] * __ldg(yz + (ij >> 8));
+            const int n0 = __ldg(P.cg_kstart + pa.cg_kstart + my_k), n1 = __ldg(P.cg_kstart + pa.cg_kstart + my_k + 1);
+            // four table entries per round: all index/value loads, then all Y loads, then the accumulations, so a
+            // round costs one dependent-load chain instead of four
+            for (int c = n0; c < n1; c += 4) {
+              int ij[4];
+              float cv[4], yv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const bool ok = c + u < n1;
+                ij[u] = ok ? __ldg(cij + c + u) : 0;
+                cv[u] = ok ? __ldg(cval + c + u) : 0.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) yv[u] = __ldg(yz + (ij[u] >> 8));
+#pragma unroll
+              for (int u = 0; u < 4; ++u) tcol[(ij[u] & 255) * NPROD] += cv[u] * yv[u];
             }
           } else {
             tcol[my_k * NPROD] = 1.f;   // d1 == d3

@@ -238,6 +238,8 @@ PROFILER: Optional[KernelProfiler] = None
 # which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
 BACKEND = os.environ.get("HGB_MSGPACK", "tcg")
+# radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
+GATE_BACKEND = os.environ.get("HGB_GATE", "simt")
 
 
 @dataclass
@@ -552,6 +554,21 @@ class MessagePackOp:
             self.tc_w3_off.append(wcur)
             add(wcur + np.arange(n3), base[("fc2", b)] + np.arange(n3), 1.0 / math.sqrt(self.h2), 2)
             wcur += (n3 + 3) // 4 * 4
+        # the same layer as tensor-core tiles for radial_gate_tc_kernel: per tile of 64 gate columns a (hi | lo) pair of
+        # K-major images [h2/4][64][4]
+        self.tc_w3img_off = None
+        if self.h2 % 8 == 0 and self.h1 % 4 == 0:
+            TNG = 64
+            self.tc_w3img_off = []
+            for b in range(len(self.branches)):
+                nchb = self.n_channels[b]
+                wcur = (wcur + 3) // 4 * 4
+                self.tc_w3img_off.append(wcur)
+                for t0 in range(0, nchb, TNG):
+                    cols = np.arange(t0, min(t0 + TNG, nchb))
+                    hh, cc = np.meshgrid(np.arange(self.h2), cols, indexing="ij")
+                    add_image(wcur, TNG, hh, cc - t0, base[("fc2", b)] + hh * nchb + cc, 1.0 / math.sqrt(self.h2), self.h2)
+                    wcur += 2 * self.h2 * TNG
         # reuse the CG tables of the SIMT plan (offsets are identical)
         types = (L.TypeT * len(self.irreps_out))()
         plist = []
@@ -690,9 +707,12 @@ class MessagePackOp:
             g_ws = torch.empty(nb * int(n_edges) * gstride, device=out.device, dtype=torch.float32)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
             nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
-            rc = L.load().hgb_msgpack_tcg_forward(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
-                                                  w3o, nch, gstride, g_ws.data_ptr(), int(n_edges), out.data_ptr(),
-                                                  L.ptr(out_index), L.stream_ptr(out.device))
+            w3i = None
+            if GATE_BACKEND == "tc" and self.tc_w3img_off is not None:
+                w3i = (C.c_int32 * 2)(*(list(self.tc_w3img_off) + [0] * (2 - nb)))
+            rc = L.load().hgb_msgpack_tcg_forward_v2(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
+                                                     w3o, nch, w3i, gstride, g_ws.data_ptr(), int(n_edges), out.data_ptr(),
+                                                     L.ptr(out_index), L.stream_ptr(out.device))
         elif use_tc:
             h2 = torch.empty(len(self.branches) * int(n_edges) * self.h2, device=out.device, dtype=torch.float32)
             rc = L.load().hgb_msgpack_tc_forward(C.byref(st["tc_plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
@@ -705,6 +725,25 @@ class MessagePackOp:
             prof.end(out.device)
         L.check(rc, "hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward")
         return out
+
+    def radial_gate(self, weights: dict, rbf: torch.Tensor, backend: str = "tc") -> torch.Tensor:
+        """g[b, e, c] = FullyConnectedNet_b(rbf[e])[c] through hgb_radial_gate (the 'tcg' backend's pre-pass)."""
+        L.require_cuda(rbf)
+        st = self.pack_tc(weights)
+        nb, n = len(self.branches), rbf.shape[0]
+        gstride = (max(self.n_channels) + 3) // 4 * 4
+        g = torch.zeros(nb, n, gstride, device=rbf.device, dtype=torch.float32)
+        w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
+        nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
+        w3i = None
+        if backend == "tc":
+            if self.tc_w3img_off is None:
+                raise NotImplementedError("radial MLP widths outside the tensor-core gate kernel's tiling")
+            w3i = (C.c_int32 * 2)(*(list(self.tc_w3img_off) + [0] * (2 - nb)))
+        rc = L.load().hgb_radial_gate(C.byref(st["tc_plan"]), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride, g.data_ptr(), n,
+                                      L.stream_ptr(rbf.device))
+        L.check(rc, "hgb_radial_gate")
+        return g
 
     # FLOP / byte accounting for bench.py (per edge, algorithmic minimum of this formulation)
     def flops_per_edge(self) -> int:

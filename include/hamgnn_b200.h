@@ -123,6 +123,20 @@ int hgb_msgpack_tcg_forward(const hgb_msgpack_plan* plan_host, const float* cons
                             const int64_t* const* src_rows_host, const float* sh, const float* rbf,
                             const int32_t* w3_off_host, const int32_t* nch_host, int32_t gstride, float* g_ws,
                             int64_t n_edges, float* out, const int64_t* out_index, void* stream);
+/* v2: w3img_off_host (nullable) = per-branch offsets into plan->wbuf of the last radial layer packed as tensor-core
+ * tiles -- per tile of 64 gate columns a (hi | lo) pair of images [h2/4][64][4] (K-major, tf32 split, scaled by
+ * 1/sqrt(h2), zero padded).  When given (and h2 % 8 == 0, h1 % 4 == 0) the gate pre-pass runs as a tcgen05 GEMM
+ * (radial_gate_tc_kernel) instead of the fp32-FMA kernel. */
+int hgb_msgpack_tcg_forward_v2(const hgb_msgpack_plan* plan_host, const float* const* src_host,
+                               const int64_t* const* src_rows_host, const float* sh, const float* rbf,
+                               const int32_t* w3_off_host, const int32_t* nch_host, const int32_t* w3img_off_host,
+                               int32_t gstride, float* g_ws, int64_t n_edges, float* out, const int64_t* out_index,
+                               void* stream);
+/* the radial gate alone: g_ws[b][e][c] = FullyConnectedNet_b(rbf[e])[c] (hamgnn/nn/message_passing.py:173-189),
+ * c < nch_host[b], row stride gstride; same selection rule between the two kernels as above. */
+int hgb_radial_gate(const hgb_msgpack_plan* plan_host, const float* rbf, const int32_t* w3_off_host,
+                    const int32_t* nch_host, const int32_t* w3img_off_host, int32_t gstride, float* g_ws,
+                    int64_t n_edges, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].

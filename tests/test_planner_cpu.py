@@ -164,6 +164,18 @@ def test_tensor_core_packing_matches_oracle(small):
     assert rel_err(got, ref_emb) < 2e-6
 
 
+def test_radial_gate_tiles_match_oracle(small):
+    """The W3 tiles of the tensor-core gate pre-pass decode to the oracle's FullyConnectedNet (both branches)."""
+    pre, out, opre, oout, g, d, rep, res = small
+    cb, ocb = pre.convolutions[1].conv_tp, opre.convolutions[1].conv_tp
+    st = cb.op.pack_tc(cb.weights())
+    rbf = d["edge_embedding"]
+    got = EM.emulate_radial_gate_tc(cb.op, st["tc_wbuf"].double(), rbf)
+    with torch.no_grad():
+        ref_n, ref_e = ocb.node_weight_generator(rbf), ocb.edge_weight_generator(rbf)
+    assert rel_err(got[0, :, :ref_n.shape[1]], ref_n) < 2e-6 and rel_err(got[1, :, :ref_e.shape[1]], ref_e) < 2e-6
+
+
 @pytest.mark.parametrize("cfg_name", ["small", "default"])
 def test_tensor_core_launcher_accepts_every_message_plan(cfg_name):
     """Host-side validation of hgb_msgpack_tcg_forward (slot classes, staging-buffer limits of both message kernels)
