@@ -41,6 +41,25 @@ class MsgpackPlan(C.Structure):
                 ("cg_ij", vp), ("cg_val", vp), ("cg_kstart", vp), ("wbuf", vp)]
 
 
+class RotBlockT(C.Structure):
+    """One (source group, in-slot) block of the rotated + packed input of the 'rot' message kernel."""
+    _fields_ = [("src0", i32), ("nsrc", i32), ("in_off", i32), ("mul", i32), ("l1", i32), ("kpad", i32), ("xoff", i32),
+                ("pad", i32)]
+
+
+class RotStepT(C.Structure):
+    """One (path, m1) step of the 'rot' message kernel: B = X'_{m1} W_p, gated by scale * g, C_{m3} += (B.g) L'_p."""
+    _fields_ = [("a_off", i32), ("w_off", i32), ("lf_off", i32), ("g_off", i32), ("scale", f32), ("kpad", C.c_int16),
+                ("kind", C.c_int8), ("branch", C.c_int8), ("m3", C.c_int8), ("new_path", C.c_int8), ("pad", C.c_int16),
+                ("pad2", i32)]
+
+
+class RotPlan(C.Structure):
+    _fields_ = [("n_blocks", i32), ("tile_stride", i32), ("lmax", i32), ("dstride", i32), ("doff", i32 * 12),
+                ("step_begin", i32 * 33), ("pad", i32), ("blocks", vp), ("steps", vp), ("blocks_host", vp), ("steps_host", vp),
+                ("wigner_j", vp)]
+
+
 class LinBlockT(C.Structure):
     _fields_ = [("in_off", i32), ("out_off", i32), ("mul_in", i32), ("mul_out", i32), ("dim", i32), ("w_off", i32)]
 

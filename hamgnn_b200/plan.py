@@ -363,6 +363,7 @@ class MessagePackOp:
         self.tp_numel = [sum(p.mul_in_total * p.mul_out for p in ps) for ps in self.paths_by_branch]
         self._build_pack_program()
         self._build_tc_program()
+        self._build_rot_program()
         self._dev: Dict[str, dict] = {}
 
     # -------------------------------------------------------------------------------- packing program
@@ -629,6 +630,107 @@ class MessagePackOp:
         self._tc_src = np.concatenate(src)
         self._tc_scale = np.concatenate(scale)
         self._tc_part = np.concatenate(part)
+
+    # -------------------------------------------------------------------------------- rotated-frame program
+    ROT_TILE = 128    # edges per tile = MMA rows
+    ROT_KC = 32       # channels per operand chunk
+
+    def _build_rot_program(self):
+        """Tables of the edge-aligned ('rot') message kernel (csrc/msgpack_rot.cu).
+
+        In the frame where the edge points along the polar axis, Y_l2 = sqrt(2 l2 + 1) delta_{m2,0}, so
+        T[i,k] = sum_j w3j[i,j,k] Y[j] has ONE non-zero per output component m3: at m1 = m3 when l1+l2+l3 is even,
+        at m1 = -m3 (m3 != 0) when it is odd.  A path therefore decomposes into <= min(d1, d3) "steps"
+            C'_{m3} += ((X'_{m1} W_p) * (scale * g_p)) L'_p
+        whose A operand X'_{m1}[z, u] = (D^{l1}(R_z) x_z)[u, m1] is plain data: the rotated inputs are produced once
+        per call by the rotate-pack kernel as ready-made (hi | lo) operand images, and the message is rotated back
+        (C = D^{l3}(R_z)^T C') in the epilogue.  Reuses the W / L' images and the path order of the tcgen05 packing."""
+        T, KC = self.ROT_TILE, self.ROT_KC
+        blocks: List[L.RotBlockT] = []
+        bkey: Dict[Tuple[int, int, int, int, int], int] = {}
+        xcur = 0
+
+        def block_of(src0, nsrc, in_off, mul, l1):
+            nonlocal xcur
+            key = (src0, nsrc, in_off, mul, l1)
+            if key not in bkey:
+                kpad = (nsrc * mul + 7) // 8 * 8
+                bkey[key] = len(blocks)
+                blocks.append(L.RotBlockT(src0, nsrc, in_off, mul, l1, kpad, xcur, 0))
+                xcur += (2 * l1 + 1) * 2 * kpad * T
+            return blocks[bkey[key]]
+
+        steps: List[L.RotStepT] = []
+        step_begin = [0]
+        lmax = 0
+        for t, m in enumerate(self.irreps_out):
+            ty = self.tc_types_c[t]
+            l3 = ty.l
+            lmax = max(lmax, l3)
+            for p in range(ty.path_begin, ty.path_end):
+                pa = self.tc_paths_c[p]
+                l1 = pa.l1
+                lmax = max(lmax, l1)
+                blk = block_of(pa.src0, pa.nsrc, pa.in_off, pa.mul_in, l1)
+                per_m = 2 * blk.kpad * T
+                first = True
+                if pa.kind == 0:
+                    w = so3.wigner_3j(l1, pa.l2, l3)
+                    even = (l1 + pa.l2 + l3) % 2 == 0
+                    for m1 in range(-l1, l1 + 1):
+                        m3 = m1 if even else -m1
+                        if abs(m3) > l3:
+                            continue
+                        c = float(w[l1 + m1, pa.l2, l3 + m3]) * math.sqrt(2 * pa.l2 + 1)
+                        if c == 0.0:
+                            continue
+                        steps.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.w_off, pa.lf_off, pa.pad0, c, blk.kpad, 0,
+                                                pa.branch, l3 + m3, 1 if first else 0, 0, 0))
+                        first = False
+                    # every non-zero of T0 must be covered by exactly those steps
+                    t0 = w[:, pa.l2, :]
+                    assert int((t0 != 0).sum()) == sum(1 for m1 in range(-l1, l1 + 1)
+                                                       if abs(m1) <= l3 and t0[l1 + m1, l3 + (m1 if even else -m1)] != 0)
+                else:
+                    assert l1 == l3
+                    for m1 in range(-l1, l1 + 1):
+                        steps.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.lf_off, 0, 0, 1.0, blk.kpad, 1, 0, l3 + m1,
+                                                0, 0, 0))
+            step_begin.append(len(steps))
+        self.rot_blocks_c = (L.RotBlockT * max(1, len(blocks)))(*blocks)
+        self.rot_steps_c = (L.RotStepT * max(1, len(steps)))(*steps)
+        self.rot_n_blocks, self.rot_n_steps = len(blocks), len(steps)
+        self.rot_step_begin = step_begin
+        self.rot_tile_stride = xcur
+        self.rot_lmax = lmax
+        self.rot_doff, self.rot_dstride = so3.wigner_offsets(lmax)
+        jt = np.zeros(self.rot_dstride, dtype=np.float64)
+        for l in range(lmax + 1):
+            d = 2 * l + 1
+            jt[self.rot_doff[l]:self.rot_doff[l] + d * d] = so3.wigner_J(l).reshape(-1)
+        self.rot_wigner_j = jt
+
+    def rot_supported(self) -> bool:
+        return self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32
+
+    def rot_plan(self, device) -> "L.RotPlan":
+        st = self._device_state(device)
+        if "rot_plan" not in st:
+            st["rot_blocks"] = torch.from_numpy(np.frombuffer(bytes(self.rot_blocks_c), dtype=np.uint8).copy()).to(device)
+            st["rot_steps"] = torch.from_numpy(np.frombuffer(bytes(self.rot_steps_c), dtype=np.uint8).copy()).to(device)
+            st["rot_j"] = torch.from_numpy(self.rot_wigner_j).to(device)
+            rp = L.RotPlan()
+            rp.n_blocks, rp.tile_stride, rp.lmax, rp.dstride = self.rot_n_blocks, self.rot_tile_stride, self.rot_lmax, self.rot_dstride
+            for l, o in enumerate(self.rot_doff):
+                rp.doff[l] = o
+            for t, b in enumerate(self.rot_step_begin):
+                rp.step_begin[t] = b
+            rp.blocks, rp.steps = st["rot_blocks"].data_ptr(), st["rot_steps"].data_ptr()
+            rp.blocks_host = C.cast(self.rot_blocks_c, C.c_void_p).value
+            rp.steps_host = C.cast(self.rot_steps_c, C.c_void_p).value
+            rp.wigner_j = st["rot_j"].data_ptr()
+            st["rot_plan"] = rp
+        return st["rot_plan"]
 
     def tc_supported(self) -> bool:
         return (max((m.mul for m in self.irreps_out), default=0) <= 64 and self.h2 % 16 == 0 and self.h2 <= 64

@@ -109,3 +109,74 @@ def _n2m(name: str) -> float:
     else:
         raise ValueError(name)
     return float(f.pow(2).mean().pow(-0.5))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Wigner-D constants for the edge-aligned ("rotated frame") message kernel.
+#
+# Basis: the real spherical harmonics the kernels use (csrc/edge_embed.cu): polar axis z, index l+m,
+# Y_{l,+m} ~ Re (x+iy)^m, Y_{l,-m} ~ Im (x+iy)^m, component normalisation.  D^l(R) is defined by
+# Y_l(R v) = D^l(R) Y_l(v).  A rotation about z by psi is sparse in this basis ("Z(psi)"):
+#     Y'_{+m} = cos(m psi) Y_{+m} - sin(m psi) Y_{-m},   Y'_{-m} = sin(m psi) Y_{+m} + cos(m psi) Y_{-m}
+# and a rotation about y is  D(R_y(psi)) = J Z(psi) J^T  with the constant matrix J = D(S), S = R_x(-90 deg)
+# (S maps z -> y).  The kernels build D(R_y(-theta) R_z(-phi)) per edge from these two pieces.
+def real_sh(l: int, v: np.ndarray) -> np.ndarray:
+    """Standard real spherical harmonics of unit vectors v[...,3] in fp64, component normalisation (|Y_l|^2 = 2l+1)."""
+    v = np.asarray(v, dtype=np.float64)
+    x, y, z = v[..., 0], v[..., 1], v[..., 2]
+    out = np.zeros(v.shape[:-1] + (2 * l + 1,))
+    cm, sm = [np.ones_like(x)], [np.zeros_like(x)]
+    for m in range(1, l + 1):
+        cm.append(cm[-1] * x - sm[-1] * y)
+        sm.append(sm[-1] * x + cm[-2] * y)
+    for m in range(0, l + 1):
+        qmm = 1.0
+        for k in range(1, m + 1):
+            qmm *= 2 * k - 1
+        q2, q1 = None, None
+        for ll in range(m, l + 1):
+            if ll == m:
+                q = qmm * np.ones_like(z)
+            elif ll == m + 1:
+                q = (2 * m + 1) * z * q1
+            else:
+                q = ((2 * ll - 1) * z * q1 - (ll + m - 1) * q2) / (ll - m)
+            q2, q1 = q1, q
+        n = math.sqrt((2 * l + 1) * math.factorial(l - m) / math.factorial(l + m))
+        if m == 0:
+            out[..., l] = n * q1
+        else:
+            out[..., l + m] = math.sqrt(2.0) * n * q1 * cm[m]
+            out[..., l - m] = math.sqrt(2.0) * n * q1 * sm[m]
+    return out
+
+
+def wigner_D_numeric(l: int, R: np.ndarray) -> np.ndarray:
+    """D^l(R) with Y_l(R v) = D Y_l(v), by a least-squares fit on fixed sample directions (fp64, ~1e-14)."""
+    rng = np.random.default_rng(12345 + l)
+    v = rng.normal(size=(6 * (2 * l + 1) + 8, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    A = real_sh(l, v)                    # [n, d]
+    B = real_sh(l, v @ np.asarray(R, dtype=np.float64).T)
+    X, *_ = np.linalg.lstsq(A, B, rcond=None)   # A X = B  ->  D = X^T
+    return X.T
+
+
+@lru_cache(maxsize=None)
+def wigner_J(l: int) -> np.ndarray:
+    """J = D^l(S), S = rotation about x by -90 degrees (z -> y): D(R_y(psi)) = J Z(psi) J^T."""
+    S = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, -1.0, 0.0]])
+    J = wigner_D_numeric(l, S)
+    J[np.abs(J) < 1e-13] = 0.0
+    J.setflags(write=False)
+    return J
+
+
+def wigner_offsets(lmax: int):
+    """Float offsets of the per-edge D^l blocks (row-major d x d, each block starting on a multiple of 4) and
+    the padded row length."""
+    offs, cur = [], 0
+    for l in range(lmax + 1):
+        offs.append(cur)
+        cur += ((2 * l + 1) ** 2 + 3) // 4 * 4
+    return offs, cur

@@ -270,3 +270,125 @@ def emulate_radial_gate_tc(op: MessagePackOp, wbuf: torch.Tensor, rbf: torch.Ten
             out[b, :, n0:n1] = (h2 @ W)[:, :n1 - n0]
             assert float(W[:, n1 - n0:].abs().max()) == 0 if n1 - n0 < 64 else True            # zero padding
     return out
+
+
+# ------------------------------------------------------------------------------------------------ rotated frame
+def emulate_wigner(vec: np.ndarray, op: MessagePackOp) -> np.ndarray:
+    """wigner_kernel: per-edge D^l(R), R = R_y(-theta) R_z(-phi) taking the unit edge vector to the polar axis z,
+    built as J Z(-theta) J^T Z(-phi) from the vector components (no angles), fp64 -> [E, dstride]."""
+    v = np.asarray(vec, dtype=np.float64)
+    E = v.shape[0]
+    n = np.sqrt((v * v).sum(1))
+    x, y, z = v[:, 0] / n, v[:, 1] / n, v[:, 2] / n
+    rho = np.sqrt(x * x + y * y)
+    ok = rho > 1e-30
+    cp, sp = np.where(ok, x / np.where(ok, rho, 1.0), 1.0), np.where(ok, y / np.where(ok, rho, 1.0), 0.0)
+    ct, st = z, rho
+    lmax = op.rot_lmax
+    # cos / sin of m * (-phi) and m * (-theta) by the angle-addition recurrence
+    ca, sa, cb, sb = [np.ones(E)], [np.zeros(E)], [np.ones(E)], [np.zeros(E)]
+    for m in range(1, lmax + 1):
+        ca.append(ca[-1] * cp - sa[-1] * (-sp)); sa.append(sa[-1] * cp + ca[-2] * (-sp))
+        cb.append(cb[-1] * ct - sb[-1] * (-st)); sb.append(sb[-1] * ct + cb[-2] * (-st))
+    out = np.zeros((E, op.rot_dstride))
+    for l in range(lmax + 1):
+        d = 2 * l + 1
+        J = op.rot_wigner_j[op.rot_doff[l]:op.rot_doff[l] + d * d].reshape(d, d)
+        Jt = J.T
+        N = np.zeros((E, d, d))
+        N[:, :, l] = Jt[:, l]
+        for m in range(1, l + 1):   # N = J^T Z(-phi): column mixing
+            N[:, :, l + m] = Jt[None, :, l + m] * ca[m][:, None] + Jt[None, :, l - m] * sa[m][:, None]
+            N[:, :, l - m] = -Jt[None, :, l + m] * sa[m][:, None] + Jt[None, :, l - m] * ca[m][:, None]
+        M2 = np.zeros((E, d, d))
+        M2[:, l, :] = N[:, l, :]
+        for m in range(1, l + 1):   # M2 = Z(-theta) N: row mixing
+            M2[:, l + m, :] = cb[m][:, None] * N[:, l + m, :] - sb[m][:, None] * N[:, l - m, :]
+            M2[:, l - m, :] = sb[m][:, None] * N[:, l + m, :] + cb[m][:, None] * N[:, l - m, :]
+        Dl = np.einsum("ri,eij->erj", J, M2)
+        out[:, op.rot_doff[l]:op.rot_doff[l] + d * d] = Dl.reshape(E, d * d)
+    return out
+
+
+def emulate_rotate_pack(op: MessagePackOp, sources, rows, Dw: torch.Tensor) -> torch.Tensor:
+    """rotate_pack_kernel: XP[tile][block xoff + m1 * 2 kpad T + chunk c * 2 KC T + (hi: (u%KC)/4 slab, z, u%4 | lo)].
+    Returns [n_tiles, tile_stride] holding the un-split rotated values in the hi image and zeros in the lo image
+    (the emulation keeps full precision; the device writes hi = tf32(x'), lo = x' - hi)."""
+    T, KC = op.ROT_TILE, op.ROT_KC
+    E = Dw.shape[0]
+    nt = (E + T - 1) // T
+    XP = torch.zeros(nt, op.rot_tile_stride, dtype=Dw.dtype)
+    gathered = [s if r is None else s[r] for s, r in zip(sources, rows)]
+    zz = torch.arange(E)
+    tile, zl = zz // T, zz % T
+    for bi in range(op.rot_n_blocks):
+        b = op.rot_blocks_c[bi]
+        d1 = 2 * b.l1 + 1
+        K = b.nsrc * b.mul
+        x = torch.cat([gathered[b.src0 + s][:, b.in_off:b.in_off + b.mul * d1] for s in range(b.nsrc)], dim=1).reshape(E, K, d1)
+        Dl = Dw[:, op.rot_doff[b.l1]:op.rot_doff[b.l1] + d1 * d1].reshape(E, d1, d1)
+        xr = torch.einsum("zmi,zui->zum", Dl, x)      # x'[u][m] = sum_i D[m][i] x[u][i]
+        for m in range(d1):
+            base = b.xoff + m * 2 * b.kpad * T
+            for u in range(K):
+                c, ul = u // KC, u % KC
+                off = base + c * 2 * KC * T + (ul // 4) * (T * 4) + zl * 4 + (ul % 4)
+                XP[tile, off] = xr[:, u, m]
+    return XP
+
+
+def _decode_a(XP, a_off, kpad, E, T, KC):
+    """[E, kpad] operand (hi + lo) of one step from the packed rotated input."""
+    zz = torch.arange(E)
+    tile, zl = zz // T, zz % T
+    cols = []
+    for u in range(kpad):
+        c, ul = u // KC, u % KC
+        kc = min(KC, kpad - c * KC)
+        off = a_off + c * 2 * KC * T + (ul // 4) * (T * 4) + zl * 4 + (ul % 4)
+        cols.append(XP[tile, off] + XP[tile, off + kc * T])
+    return torch.stack(cols, dim=1)
+
+
+def emulate_msgpack_rot(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, vec, rbf, out_rows=None, n_out=None):
+    """Mirrors the 'rot' pipeline: wigner_kernel -> rotate_pack_kernel -> radial gate -> msgpack_rot_kernel
+    (steps from rot_steps_c, W / L' images from the tensor-core packing, rotation back in the epilogue)."""
+    from hamgnn_b200 import so3
+    T, KC = op.ROT_TILE, op.ROT_KC
+    E = rbf.shape[0]
+    dt = wbuf.dtype
+    D = op.irreps_out.dim
+    Dw = torch.from_numpy(emulate_wigner(np.asarray(vec), op)).to(dt)
+    XP = emulate_rotate_pack(op, sources, rows, Dw)
+    act = so3.normalize2mom_const("silu")
+    g = []
+    for b in range(len(op.branches)):
+        w1 = wbuf[op.tc_fc1_off[b]:op.tc_fc1_off[b] + op.rbf_dim * op.h1].view(op.rbf_dim, op.h1)
+        w2 = wbuf[op.tc_fc2_off[b]:op.tc_fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
+        w3 = wbuf[op.tc_w3_off[b]:op.tc_w3_off[b] + op.h2 * op.n_channels[b]].view(op.h2, op.n_channels[b])
+        g.append(_silu(_silu(rbf @ w1) * act @ w2) * act @ w3)
+    msg = torch.zeros(E, D, dtype=dt)
+    for t in range(len(op.irreps_out)):
+        ty = op.tc_types_c[t]
+        d3, mp = 2 * ty.l + 1, ty.mpad
+        Cacc = torch.zeros(E, d3, mp, dtype=dt)
+        Lf = None
+        for si in range(op.rot_step_begin[t], op.rot_step_begin[t + 1]):
+            st = op.rot_steps_c[si]
+            A = _decode_a(XP, st.a_off, st.kpad, E, T, KC)
+            W = torch.cat([_decode_image(wbuf, st.w_off + 2 * mp * KC * c, mp, min(KC, st.kpad - u0))
+                           for c, u0 in enumerate(range(0, st.kpad, KC))], dim=0)
+            if st.kind == 0:
+                if st.new_path:
+                    Lf = _decode_image(wbuf, st.lf_off, mp, mp)
+                gv = torch.zeros(E, mp, dtype=dt)
+                gv[:, :ty.mul] = g[st.branch][:, st.g_off:st.g_off + ty.mul]
+                Cacc[:, st.m3, :] += ((A @ W) * (gv * st.scale)) @ Lf
+            else:
+                Cacc[:, st.m3, :] += A @ W
+        D3 = Dw[:, op.rot_doff[ty.l]:op.rot_doff[ty.l] + d3 * d3].reshape(E, d3, d3)
+        out = torch.einsum("zmk,zmw->zwk", D3, Cacc[:, :, :ty.mul])     # C = D^T C'
+        msg[:, ty.out_off:ty.out_off + ty.mul * d3] = out.reshape(E, ty.mul * d3)
+    if out_rows is None:
+        return msg
+    return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)

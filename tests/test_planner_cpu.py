@@ -1,5 +1,6 @@
 """CPU tests of the host planners: the packed tables that drive the CUDA kernels, executed by the
 arithmetic emulator (tests/kernel_emulator.py), must reproduce the oracle."""
+import numpy as np
 import pytest
 import torch
 
@@ -158,6 +159,51 @@ def test_tensor_core_packing_matches_oracle(small):
     h = EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_src.weight), onehot[s]) + EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_dst.weight), onehot[r])
     st = pe.conv_tp.op.pack_tc(pe.conv_tp.weights())
     got = EM.emulate_msgpack_tc(pe.conv_tp.op, st["tc_wbuf"].double(), [h], [None], d["edge_attrs"], d["edge_embedding"])
+    dd2 = dict(dd); dd2["node_features"] = onehot
+    with torch.no_grad():
+        ref_emb = opre.pair_embedding(dd2)
+    assert rel_err(got, ref_emb) < 2e-6
+
+
+def test_rotated_frame_program_matches_oracle(small):
+    """The edge-aligned ('rot') pipeline -- per-edge Wigner matrices built the way wigner_kernel builds them, rotated +
+    packed operand images, the (path, m1) step tables and the rotation back -- reproduces the oracle's messages."""
+    pre, out, opre, oout, g, d, rep, res = small
+    torch.manual_seed(7)
+    E, N, D = g.edge_index.shape[1], g.num_nodes, pre.irreps_node_features.dim
+    x, e = torch.randn(N, D).double(), torch.randn(E, D).double()
+    dd = {"edge_index": g.edge_index, "node_features": x, "edge_features": e, "edge_attrs": d["edge_attrs"],
+          "edge_embedding": d["edge_embedding"]}
+    s, r = g.edge_index
+    vec = d["edge_vectors"].double().numpy()
+    with torch.no_grad():
+        ref_pair = opre.pair_interactions[1](dict(dd))
+        ref_msg = opre.convolutions[0].conv_tp(x[s], x[r], e, d["edge_attrs"], d["edge_embedding"])
+    # the Wigner matrices take Y(edge) to the polar axis: D^l Y_l = sqrt(2l+1) e_{m=0}, and are orthogonal
+    cb = pre.convolutions[0].conv_tp
+    Dw = EM.emulate_wigner(vec, cb.op)
+    from hamgnn_b200 import so3
+    for l in range(cb.op.rot_lmax + 1):
+        dl = 2 * l + 1
+        Dl = Dw[:, cb.op.rot_doff[l]:cb.op.rot_doff[l] + dl * dl].reshape(E, dl, dl)
+        y0 = np.einsum("emi,ei->em", Dl, so3.real_sh(l, vec))
+        want = np.zeros(dl); want[l] = np.sqrt(dl)
+        assert np.abs(y0 - want).max() < 1e-12
+        assert np.abs(np.einsum("emi,eni->emn", Dl, Dl) - np.eye(dl)).max() < 1e-12
+    pb = pre.pair_interactions[1]
+    xs = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_src.weight), x)
+    xt = EM.emulate_linear(pb.up_op, _dbl(pb.linear_up_tar.weight), x)
+    st = pb.conv_tp.op.pack_tc(pb.conv_tp.weights(pb.skip_linear.weight))
+    got = EM.emulate_msgpack_rot(pb.conv_tp.op, st["tc_wbuf"].double(), [xs, xt, e], [s, r, None], vec, d["edge_embedding"])
+    assert rel_err(got, ref_pair) < 2e-6
+    st = cb.op.pack_tc(cb.weights())
+    got = EM.emulate_msgpack_rot(cb.op, st["tc_wbuf"].double(), [x, x, e], [s, r, None], vec, d["edge_embedding"])
+    assert rel_err(got, ref_msg) < 2e-6
+    pe = pre.pair_embedding
+    onehot = torch.nn.functional.one_hot(g.z, opre.num_types).double()
+    h = EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_src.weight), onehot[s]) + EM.emulate_linear(pe.up_op, _dbl(pe.linear_up_dst.weight), onehot[r])
+    st = pe.conv_tp.op.pack_tc(pe.conv_tp.weights())
+    got = EM.emulate_msgpack_rot(pe.conv_tp.op, st["tc_wbuf"].double(), [h], [None], vec, d["edge_embedding"])
     dd2 = dict(dd); dd2["node_features"] = onehot
     with torch.no_grad():
         ref_emb = opre.pair_embedding(dd2)
