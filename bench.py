@@ -290,7 +290,8 @@ def main():
         "e2e": {"value": MSG_PER_EDGE * E_total / (ms_e2e * 1e-3), "unit": "messages/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": h_host.numel() * 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": {"tc": "msgpack_tc_kernel (fused MessagePackBlock, tcgen05 3xTF32)", "tcg": "radial_gate_kernel + msgpack_tcg_kernel (fused MessagePackBlock, tcgen05 3xTF32, gate pre-pass)"}.get(P.BACKEND, "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)"), "bound": "tensor",
+        "roofline": {"kernel": {"tc": "msgpack_tc_kernel (fused MessagePackBlock, tcgen05 3xTF32)", "tcg": "radial_gate_kernel + msgpack_tcg_kernel/msgpack_tcr_kernel (fused MessagePackBlock, tcgen05 3xTF32, gate pre-pass)",
+                                 "rot": "radial_gate_kernel + rotate_pack_kernel + msgpack_rot_kernel (fused MessagePackBlock in the edge-aligned frame, TMA + tcgen05 3xTF32)"}.get(P.BACKEND, "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)"), "bound": "tensor",
                      "achieved": k_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k_tflops / bf16_peak,
                      "peak_source": peak_src, "traffic": None, "avg_launch_ms": k_ms, "launches_timed": ksum["launches"],
                      "kernel_share_of_step": ksum["total_ms"] / (ms_step * args.steps),

@@ -1,0 +1,488 @@
+// Edge-aligned ("rotated frame") fused MessagePackBlock.  Included by msgpack_tcg.cu (same packed W / L' images, same
+// radial-gate pre-pass).
+//
+// Why: in the frame where the edge vector is the polar axis the real spherical harmonics reduce to
+// Y_l2 = sqrt(2 l2 + 1) delta_{m2,0}, so the per-edge CG contraction T[i,k] = sum_j w3j[i,j,k] Y[j] has ONE non-zero per
+// output component m3 (at m1 = m3 for even l1+l2+l3, at m1 = -m3 for odd).  The SIMT "A generation" of the other
+// message kernels (K d1 d3 FMAs per edge and path, 95 % of their instructions, profiles/r01l_*) disappears: a path is
+// <= min(d1, d3) steps
+//     C'_{m3} += ((X'_{m1} W_p) * (scale * g_p)) L'_p
+// whose A operand X'_{m1}[z, u] = (D^{l1}(R_z) x_z)[u, m1] is plain data.  Three kernels:
+//   wigner_kernel       D^l(R_z) per edge, l <= 6, fp64 arithmetic (once per forward)
+//   rotate_pack_kernel  gathers the input rows, rotates every irrep block, splits hi/lo and writes ready-made UMMA
+//                       operand images (tile of 128 edges = 128 MMA rows)
+//   msgpack_rot_kernel  one CTA per (tile, output slot): warp 5 streams A / W chunks and L' images with TMA bulk
+//                       copies into an mbarrier ring, warp 4 issues the tcgen05 3xTF32 MMAs, warps 0-3 (thread = edge =
+//                       TMEM lane) apply the gate between the two GEMMs in TMEM and finally rotate the message back,
+//                       C = D^{l3}(R_z)^T C', before the store / receiver scatter-add.
+#pragma once
+
+namespace rot {
+using namespace tcmsg;
+
+constexpr int TILE = 128;   // edges per tile = MMA rows
+constexpr int KC = 32;      // channels per operand chunk (host: MessagePackOp.ROT_KC)
+constexpr int NTHR = 192;
+constexpr int LMAX = 6;
+
+using tcr::mbar_arrive;
+using tcr::mbar_wait_suspend;
+using tcr::warp_wait;
+
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `mbar` (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc::smem_u32(mbar))
+               : "memory");
+}
+
+// ===================================================================================================== wigner
+struct WigArgs {
+  const float* vec;
+  const double* J;
+  float* dw;
+  int64_t n_edges;
+  int dstride;
+  int doff[12];
+};
+
+// D = J Z(-theta) J^T Z(-phi);  Z(psi): Y'_{+m} = cos(m psi) Y_{+m} - sin(m psi) Y_{-m}, Y'_{-m} = sin(m psi) Y_{+m} + cos(m psi) Y_{-m}
+template <int L>
+__device__ void wigner_l(const double* __restrict__ J, double cp, double sp, double ct, double st, float* __restrict__ out) {
+  constexpr int d = 2 * L + 1;
+  double ca[L + 1], sa[L + 1], cb[L + 1], sb[L + 1];   // cos / sin of m * (-phi), m * (-theta)
+  ca[0] = 1.0; sa[0] = 0.0; cb[0] = 1.0; sb[0] = 0.0;
+#pragma unroll
+  for (int m = 1; m <= L; ++m) {
+    ca[m] = ca[m - 1] * cp + sa[m - 1] * sp;
+    sa[m] = sa[m - 1] * cp - ca[m - 1] * sp;
+    cb[m] = cb[m - 1] * ct + sb[m - 1] * st;
+    sb[m] = sb[m - 1] * ct - cb[m - 1] * st;
+  }
+  double M[d * d];
+  // N = J^T Z(-phi)  (column mixing)
+  for (int i = 0; i < d; ++i) {
+    M[i * d + L] = __ldg(J + L * d + i);
+#pragma unroll
+    for (int m = 1; m <= L; ++m) {
+      const double jp = __ldg(J + (L + m) * d + i), jm = __ldg(J + (L - m) * d + i);
+      M[i * d + L + m] = jp * ca[m] + jm * sa[m];
+      M[i * d + L - m] = -jp * sa[m] + jm * ca[m];
+    }
+  }
+  // M2 = Z(-theta) N  (row mixing)
+#pragma unroll
+  for (int m = 1; m <= L; ++m)
+    for (int j = 0; j < d; ++j) {
+      const double u = M[(L + m) * d + j], v = M[(L - m) * d + j];
+      M[(L + m) * d + j] = cb[m] * u - sb[m] * v;
+      M[(L - m) * d + j] = sb[m] * u + cb[m] * v;
+    }
+  // D = J M2
+  for (int r = 0; r < d; ++r) {
+    double acc[d];
+#pragma unroll
+    for (int j = 0; j < d; ++j) acc[j] = 0.0;
+    for (int i = 0; i < d; ++i) {
+      const double jr = __ldg(J + r * d + i);
+#pragma unroll
+      for (int j = 0; j < d; ++j) acc[j] = fma(jr, M[i * d + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < d; ++j) out[r * d + j] = (float)acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(128) wigner_kernel(const __grid_constant__ WigArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (e >= a.n_edges) return;
+  const int l = blockIdx.y;
+  double x = a.vec[3 * e], y = a.vec[3 * e + 1], z = a.vec[3 * e + 2];
+  const double n = sqrt(x * x + y * y + z * z);
+  x /= n; y /= n; z /= n;
+  const double rho = sqrt(x * x + y * y);
+  const bool ok = rho > 1e-30;
+  const double cp = ok ? x / rho : 1.0, sp = ok ? y / rho : 0.0;
+  float* out = a.dw + e * a.dstride + a.doff[l];
+  const double* J = a.J + a.doff[l];
+  switch (l) {
+    case 0: out[0] = 1.f; break;
+    case 1: wigner_l<1>(J, cp, sp, z, rho, out); break;
+    case 2: wigner_l<2>(J, cp, sp, z, rho, out); break;
+    case 3: wigner_l<3>(J, cp, sp, z, rho, out); break;
+    case 4: wigner_l<4>(J, cp, sp, z, rho, out); break;
+    case 5: wigner_l<5>(J, cp, sp, z, rho, out); break;
+    default: wigner_l<6>(J, cp, sp, z, rho, out); break;
+  }
+}
+
+// ================================================================================================ rotate + pack
+struct RpArgs {
+  const hgb_rot_block_t* blocks;
+  int n_blocks, blocks_per_cta;
+  int tile_stride, dstride;
+  int doff[12];
+  const float* src[4];
+  const int64_t* src_rows[4];
+  int src_dim[4];
+  const float* dw;
+  int64_t e_lo, n_chunk;
+  float* xp;
+};
+
+template <int L1>
+__device__ __forceinline__ void rotpack_block(const RpArgs& a, const hgb_rot_block_t& b, int tile, int z, int64_t e, bool live) {
+  constexpr int d1 = 2 * L1 + 1;
+  const int K = b.nsrc * b.mul, kpad = b.kpad;
+  const float* r0 = nullptr;
+  const float* r1 = nullptr;
+  const float* Dz = nullptr;
+  if (live) {
+    const int s0 = b.src0, s1 = b.src0 + b.nsrc - 1;
+    const int64_t row0 = a.src_rows[s0] ? a.src_rows[s0][e] : e;
+    const int64_t row1 = a.src_rows[s1] ? a.src_rows[s1][e] : e;
+    r0 = a.src[s0] + row0 * a.src_dim[s0] + b.in_off;
+    r1 = a.src[s1] + row1 * a.src_dim[s1] + b.in_off;
+    Dz = a.dw + e * a.dstride + a.doff[L1];
+  }
+  float* xo = a.xp + (size_t)tile * a.tile_stride + b.xoff + z * 4;
+  const size_t per_m = (size_t)2 * kpad * TILE;
+  for (int q = 0; q < (kpad >> 2); ++q) {
+    float x[4][d1];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int u = 4 * q + c;
+      const bool okc = live && u < K;
+      const bool second = u >= b.mul;
+      const float* p = okc ? ((second ? r1 : r0) + (u - (second ? b.mul : 0)) * d1) : nullptr;
+#pragma unroll
+      for (int i = 0; i < d1; ++i) x[c][i] = okc ? __ldg(p + i) : 0.f;
+    }
+    const int chunk = (4 * q) / KC, ul = (4 * q) - chunk * KC, kc = min(KC, kpad - chunk * KC);
+    float* base = xo + (size_t)chunk * 2 * KC * TILE + (size_t)(ul >> 2) * (TILE * 4);
+#pragma unroll
+    for (int m = 0; m < d1; ++m) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        if (L1 == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = x[c][0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < d1; ++i) {
+            const float dmi = __ldg(Dz + m * d1 + i);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = fmaf(dmi, x[c][i], v[c]);
+          }
+        }
+      }
+      float4 h, l;
+      tc::split_tf32(v[0], h.x, l.x); tc::split_tf32(v[1], h.y, l.y);
+      tc::split_tf32(v[2], h.z, l.z); tc::split_tf32(v[3], h.w, l.w);
+      float* dst = base + m * per_m;
+      *reinterpret_cast<float4*>(dst) = h;
+      *reinterpret_cast<float4*>(dst + (size_t)kc * TILE) = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TILE) rotate_pack_kernel(const __grid_constant__ RpArgs a) {
+  const int tile = blockIdx.x, z = threadIdx.x;
+  const int64_t el = (int64_t)tile * TILE + z;
+  const bool live = el < a.n_chunk;
+  const int64_t e = a.e_lo + el;
+  const int b0 = blockIdx.y * a.blocks_per_cta, b1 = min(a.n_blocks, b0 + a.blocks_per_cta);
+  for (int bi = b0; bi < b1; ++bi) {
+    const hgb_rot_block_t b = a.blocks[bi];
+    switch (b.l1) {
+      case 0: rotpack_block<0>(a, b, tile, z, e, live); break;
+      case 1: rotpack_block<1>(a, b, tile, z, e, live); break;
+      case 2: rotpack_block<2>(a, b, tile, z, e, live); break;
+      case 3: rotpack_block<3>(a, b, tile, z, e, live); break;
+      case 4: rotpack_block<4>(a, b, tile, z, e, live); break;
+      case 5: rotpack_block<5>(a, b, tile, z, e, live); break;
+      default: rotpack_block<6>(a, b, tile, z, e, live); break;
+    }
+  }
+}
+
+// ================================================================================================= message kernel
+struct RotArgs {
+  hgb_msgpack_plan plan;
+  const hgb_rot_step_t* steps;
+  int step_begin[33];
+  const float* xp;
+  int tile_stride;
+  const float* dw;
+  int dstride;
+  int doff[12];
+  const float* g;       // [n_branches][n_chunk][gstride]
+  int gstride;
+  int64_t e_lo, n_chunk;
+  float* out;
+  const int64_t* out_index;
+  int n_slots;
+  int slot[32];
+};
+
+// C[z][w][k] = sum_m3 D^{l3}_z[m3][k] C'[z][m3][w]; thread = edge z = TMEM lane; C' blocks of mp columns per m3 at `tc0`
+template <int L3>
+__device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mp, int mul, bool any, const float* __restrict__ Dz, float* __restrict__ op,
+                                             bool live, bool atomic) {
+  constexpr int d3 = 2 * L3 + 1;
+  for (int c0 = 0; c0 < mul; c0 += 8) {   // warp-uniform
+    uint32_t c[d3][8];
+    if (any) {
+#pragma unroll
+      for (int m = 0; m < d3; ++m) tc::tmem_ld8(tc0 + m * mp + c0, c[m]);
+#pragma unroll
+      for (int m = 0; m < d3; ++m) tc::tmem_ld_wait8(c[m]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < d3; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[m][j] = 0u;
+    }
+    if (!live) continue;
+#pragma unroll
+    for (int k = 0; k < d3; ++k) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int m = 0; m < d3; ++m) {
+        const float dmk = (L3 == 0) ? 1.f : __ldg(Dz + m * d3 + k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(dmk, __uint_as_float(c[m][j]), acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int w = c0 + j;
+        if (w < mul) {
+          if (atomic) atomicAdd(op + w * d3 + k, acc[j]);
+          else op[w * d3 + k] = acc[j];
+        }
+      }
+    }
+  }
+}
+
+// RW = padded-multiplicity capacity of the class (gate registers, stage size); the slot's own padded multiplicity
+// ty.mpad <= RW is the MMA N.  NST = depth of the operand ring.
+template <int RW, int NST>
+__global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(const __grid_constant__ RotArgs a) {
+  constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
+  extern __shared__ __align__(128) float smem[];
+  float* sStage = smem;
+  float* sL = smem + NST * STG;                       // 2 x (hi | lo) L' images
+  __shared__ uint64_t full[NST], empty[NST], lfull[2], ldone[2], bfull[2], gfull, gdone, cdone;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x / a.n_slots;
+  const int t = a.slot[blockIdx.x - tile * a.n_slots];
+  const hgb_type_t ty = a.plan.types[t];
+  const int d3 = 2 * ty.l + 1, mp = ty.mpad;
+  const int sb = a.step_begin[t], se = a.step_begin[t + 1];
+  const bool any = se > sb;
+  uint32_t ncols = 32;
+  while ((int)ncols < (d3 + 3) * mp) ncols <<= 1;
+  const uint32_t TC = 0, TB0 = (uint32_t)(d3 * mp), TB1 = TB0 + mp, TGL = TB0 + 2 * mp;
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&lfull[i], 1); tc::mbar_init(&ldone[i], 1); tc::mbar_init(&bfull[i], 1); }
+    tc::mbar_init(&gfull, 4); tc::mbar_init(&gdone, 1); tc::mbar_init(&cdone, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const float* __restrict__ wbuf = a.plan.wbuf;
+
+  if (warp == 5) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const float* xt = a.xp + (size_t)tile * a.tile_stride;
+      int n = 0, qp = 0;
+      for (int si = sb; si < se; ++si) {
+        const hgb_rot_step_t st = a.steps[si];
+        if (st.kind == 0 && (st.new_path & 1)) {
+          const int lb = qp & 1;
+          if (qp >= 2) mbar_wait_suspend(&ldone[lb], (uint32_t)(((qp >> 1) - 1) & 1));
+          const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
+          mbar_expect_tx(&lfull[lb], lbytes);
+          bulk_g2s(sL + lb * (2 * RW * RW), wbuf + st.lf_off, lbytes, &lfull[lb]);
+          ++qp;
+        }
+        const int kpad = st.kpad;
+        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++n) {
+          const int kc = min(KC, kpad - u0), s = n % NST;
+          if (n >= NST) mbar_wait_suspend(&empty[s], (uint32_t)(((n / NST) - 1) & 1));
+          float* sa = sStage + s * STG;
+          const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
+          mbar_expect_tx(&full[s], ab + wb);
+          bulk_g2s(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, &full[s]);
+          bulk_g2s(sa + 2 * KC * TILE, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_tf32_m128(mp);
+      const uint32_t dhi = tc::smem_desc_hi(128);
+      const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
+      const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
+      int n = 0, qs = 0, qp = 0;
+      uint32_t cmask = 0;                   // bit m3: C'_{m3} holds data
+      int pend = -1, pend_m3 = 0, pend_lb = 0, pend_lphase = 0, pend_flags = 0;
+      int cur_lb = 0, cur_lphase = 0;
+      auto gemm2 = [&]() {
+        mbar_wait_suspend(&gfull, (uint32_t)(pend & 1));
+        if (pend_flags & 1) mbar_wait_suspend(&lfull[pend_lb], (uint32_t)pend_lphase);
+        tc::fence_after_sync();
+        const uint32_t bq = tmem + ((pend & 1) ? TB1 : TB0);
+        const uint32_t lh = tc::smem_desc_lo(tc::smem_u32(sL + pend_lb * (2 * RW * RW)), lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
+        const uint32_t ccol = tmem + TC + (uint32_t)(pend_m3 * mp);
+        const uint32_t started = (cmask >> pend_m3) & 1u;
+        for (int k8 = 0; k8 < (mp >> 3); ++k8) {
+          const uint64_t bh = tc::desc64(lh + k8 * bstep, dhi), bl = tc::desc64(ll + k8 * bstep, dhi);
+          tc::mma_tf32_ts(ccol, tmem + TGL + k8 * 8, bh, idesc, started | (uint32_t)(k8 > 0));
+          tc::mma_tf32_ts(ccol, bq + k8 * 8, bl, idesc, 1);
+          tc::mma_tf32_ts(ccol, bq + k8 * 8, bh, idesc, 1);
+        }
+        tc::mma_commit(&gdone);
+        if (pend_flags & 2) tc::mma_commit(&ldone[pend_lb]);
+        cmask |= 1u << pend_m3;
+        pend = -1;
+      };
+      for (int si = sb; si < se; ++si) {
+        const hgb_rot_step_t st = a.steps[si];
+        const bool gated = st.kind == 0;
+        if (gated && (st.new_path & 1)) { cur_lb = qp & 1; cur_lphase = (qp >> 1) & 1; ++qp; }
+        const uint32_t dcol = tmem + (gated ? ((qs & 1) ? TB1 : TB0) : TC + (uint32_t)(st.m3 * mp));
+        const uint32_t base_acc = gated ? 0u : ((cmask >> st.m3) & 1u);
+        const int kpad = st.kpad;
+        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++n) {
+          const int kc = min(KC, kpad - u0), s = n % NST;
+          mbar_wait_suspend(&full[s], (uint32_t)((n / NST) & 1));
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(sStage + s * STG);
+          const uint32_t ah = tc::smem_desc_lo(sa, lbo_a), al = ah + (((uint32_t)kc * TILE * 4) >> 4);
+          const uint32_t wh = tc::smem_desc_lo(sa + 2 * KC * TILE * 4, lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
+          for (int k8 = 0; k8 < (kc >> 3); ++k8) {
+            const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
+            const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl = tc::desc64(wl + k8 * bstep, dhi);
+            tc::mma_tf32(dcol, dal, dbh, idesc, base_acc | (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+            tc::mma_tf32(dcol, dah, dbl, idesc, 1);
+            tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+          }
+          tc::mma_commit(&empty[s]);
+          if (c == 0 && pend >= 0) gemm2();   // GEMM2 of the previous gated step, behind the first chunk of this one
+        }
+        if (gated) {
+          tc::mma_commit(&bfull[qs & 1]);
+          pend = qs; pend_m3 = st.m3; pend_lb = cur_lb; pend_lphase = cur_lphase; pend_flags = st.new_path;
+          ++qs;
+        } else {
+          cmask |= 1u << st.m3;
+        }
+      }
+      if (pend >= 0) gemm2();
+      if (any) tc::mma_commit(&cdone);
+    }
+    __syncwarp();
+  } else {
+    // =============================== gate + final rotation (thread = edge = TMEM lane) ===============================
+    const int64_t el = (int64_t)tile * TILE + tid;
+    const bool live = el < a.n_chunk;
+    const int64_t e = a.e_lo + el;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const size_t g_bstride = (size_t)a.n_chunk * a.gstride;
+    const float* grow = a.g + (size_t)(live ? el : 0) * a.gstride;
+    float gv[RW];
+#pragma unroll
+    for (int j = 0; j < RW; ++j) gv[j] = 0.f;
+    int qs = 0;
+    for (int si = sb; si < se; ++si) {
+      const hgb_rot_step_t st = a.steps[si];
+      if (st.kind != 0) continue;
+      if (st.new_path & 1) {
+        const float* gp = grow + (size_t)st.branch * g_bstride + st.g_off;
+#pragma unroll
+        for (int j = 0; j < RW; ++j) gv[j] = (live && j < ty.mul) ? __ldg(gp + j) : 0.f;
+        if (live && st.pad2 >= 0) {   // next path's gate segment -> L2
+          const hgb_rot_step_t* nx = a.steps + st.pad2;
+          const float* np = grow + (size_t)nx->branch * g_bstride + nx->g_off;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(np + ty.mul - 1));
+        }
+      }
+      const float sc = st.scale;
+      warp_wait(&bfull[qs & 1], (uint32_t)((qs >> 1) & 1));
+      if (qs >= 1) warp_wait(&gdone, (uint32_t)((qs - 1) & 1));   // GEMM2 of the previous step has read (B.g) lo
+      tc::fence_after_sync();
+      const uint32_t bq = tmem + lane_base + ((qs & 1) ? TB1 : TB0);
+#pragma unroll
+      for (int c0 = 0; c0 < RW; c0 += 8) {
+        if (c0 < mp) {   // warp-uniform
+          uint32_t rb[8], hi[8], lo[8];
+          tc::tmem_ld8(bq + c0, rb);
+          tc::tmem_ld_wait8(rb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float h, l;
+            tc::split_tf32(__uint_as_float(rb[j]) * (gv[c0 + j] * sc), h, l);
+            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
+          }
+          tc::tmem_st8(bq + c0, hi);
+          tc::tmem_st8(tmem + lane_base + TGL + c0, lo);
+        }
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gfull);
+      ++qs;
+    }
+    if (any) { warp_wait(&cdone, 0); tc::fence_after_sync(); }
+    {
+      const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
+      float* op = a.out + (live ? orow : 0) * a.plan.out_dim + ty.out_off;
+      const float* Dz = a.dw + (live ? e : 0) * a.dstride + a.doff[ty.l];
+      const uint32_t tc0 = tmem + lane_base + TC;
+      const bool atomic = a.out_index != nullptr;
+      switch (ty.l) {
+        case 0: rot_epilogue<0>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 1: rot_epilogue<1>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 2: rot_epilogue<2>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 3: rot_epilogue<3>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 4: rot_epilogue<4>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 5: rot_epilogue<5>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        default: rot_epilogue<6>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
+}
+
+template <int RW, int NST>
+constexpr size_t rot_smem_bytes() { return (size_t)(NST * (2 * KC * TILE + 2 * RW * KC) + 2 * 2 * RW * RW) * sizeof(float); }
+
+}  // namespace rot

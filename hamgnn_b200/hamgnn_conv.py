@@ -146,7 +146,7 @@ class ConvBlockE3(nn.Module):
         skip = linear_forward(self.skip_op, self.skip_linear.weight, x)
         agg = torch.zeros_like(x)
         self.conv_tp.op.forward(self.conv_tp.weights(), [x, x, e], [sender, receiver, None], data["edge_attrs"],
-                                data["edge_embedding"], e.shape[0], agg, out_index=receiver)
+                                data["edge_embedding"], e.shape[0], agg, out_index=receiver, edge_vec=data["edge_vectors"])
         if self.reduce_fn is not None:
             agg = self.reduce_fn(agg)
         out = self.residual.forward_cuda(agg, extra=skip)
@@ -177,7 +177,7 @@ class PairInteractionBlock(nn.Module):
         out = torch.empty_like(e)
         direct = self.skip_linear.weight if self.use_skip_connections else None
         self.conv_tp.op.forward(self.conv_tp.weights(direct), [xs, xt, e], [src, dst, None], data["edge_attrs"],
-                                data["edge_embedding"], e.shape[0], out)
+                                data["edge_embedding"], e.shape[0], out, edge_vec=data["edge_vectors"])
         data["edge_features"] = out
         return out
 
@@ -217,7 +217,8 @@ class PairInteractionEmbeddingBlock(nn.Module):
         h = linear_forward(self.up_op, self.linear_up_src.weight, x, rows=src)
         linear_forward(self.up_op, self.linear_up_dst.weight, x, rows=dst, out=h, accumulate=True)
         out = torch.empty(E, self.out_dim, device=x.device, dtype=torch.float32)
-        self.conv_tp.op.forward(self.conv_tp.weights(), [h], [None], data["edge_attrs"], data["edge_embedding"], E, out)
+        self.conv_tp.op.forward(self.conv_tp.weights(), [h], [None], data["edge_attrs"], data["edge_embedding"], E, out,
+                                edge_vec=data["edge_vectors"])
         data["edge_features"] = out
         return out
 

@@ -242,6 +242,28 @@ BACKEND = os.environ.get("HGB_MSGPACK", "tcg")
 GATE_BACKEND = os.environ.get("HGB_GATE", "simt")
 
 
+# edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)
+ROT_CHUNK_EDGES = int(os.environ.get("HGB_ROT_CHUNK", str(128 * 1024)))
+_WIGNER_CACHE: Dict[Tuple, torch.Tensor] = {}
+
+
+def wigner_for(op: "MessagePackOp", edge_vec: torch.Tensor) -> torch.Tensor:
+    """Per-edge Wigner matrices D^l(R_e), l <= op.rot_lmax, [E, dstride] fp32 (hgb_wigner).  They depend on the edge
+    vectors only, so the seven message ops of one forward share them (cache of one entry keyed by the tensor)."""
+    L.require_cuda(edge_vec)
+    key = (edge_vec.data_ptr(), edge_vec._version, tuple(edge_vec.shape), op.rot_lmax, str(edge_vec.device))
+    hit = _WIGNER_CACHE.get("k")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    E = edge_vec.shape[0]
+    dw = torch.empty(E, op.rot_dstride, device=edge_vec.device, dtype=torch.float32)
+    rc = L.load().hgb_wigner(C.byref(op.rot_plan(edge_vec.device)), L.f32c(edge_vec).data_ptr(), E, dw.data_ptr(),
+                             L.stream_ptr(edge_vec.device))
+    L.check(rc, "hgb_wigner")
+    _WIGNER_CACHE["k"] = (key, dw, edge_vec)   # keeps edge_vec alive so the pointer cannot be recycled under the key
+    return dw
+
+
 @dataclass
 class Branch:
     """One tensor-product branch of a MessagePackBlock: `nsrc` input sources sharing `irreps_in`
@@ -697,6 +719,20 @@ class MessagePackOp:
                         steps.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.lf_off, 0, 0, 1.0, blk.kpad, 1, 0, l3 + m1,
                                                 0, 0, 0))
             step_begin.append(len(steps))
+        # pad2 of a path's first step = index of the next path's first gated step (gate prefetch), -1 at the end
+        nxt = -1
+        for t in range(len(self.irreps_out) - 1, -1, -1):
+            nxt = -1
+            for si in range(step_begin[t + 1] - 1, step_begin[t] - 1, -1):
+                steps[si].pad2 = nxt
+                if steps[si].kind == 0 and (steps[si].new_path & 1):
+                    nxt = si
+        # bit 1 of new_path: last step of its path
+        for si, s_ in enumerate(steps):
+            if s_.kind == 0:
+                last = (si + 1 == len(steps)) or steps[si + 1].kind != 0 or (steps[si + 1].new_path & 1) or (si + 1 in step_begin)
+                if last:
+                    s_.new_path |= 2
         self.rot_blocks_c = (L.RotBlockT * max(1, len(blocks)))(*blocks)
         self.rot_steps_c = (L.RotStepT * max(1, len(steps)))(*steps)
         self.rot_n_blocks, self.rot_n_steps = len(blocks), len(steps)
@@ -711,7 +747,8 @@ class MessagePackOp:
         self.rot_wigner_j = jt
 
     def rot_supported(self) -> bool:
-        return self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32
+        return (self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32 and self.rot_n_steps > 0
+                and all((2 * ty.l + 4) * ty.mpad <= 512 for ty in self.tc_types_c))
 
     def rot_plan(self, device) -> "L.RotPlan":
         st = self._device_state(device)
@@ -790,9 +827,10 @@ class MessagePackOp:
 
     def forward(self, weights: dict, sources: Sequence[torch.Tensor], rows: Sequence[Optional[torch.Tensor]],
                 sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
-                out_index: Optional[torch.Tensor] = None):
+                out_index: Optional[torch.Tensor] = None, edge_vec: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
-        use_tc = (BACKEND in ("tc", "tcg")) and self.tc_supported()   # configs outside the tensor-core kernels' limits run on the fp32-FMA kernel
+        use_tc = (BACKEND in ("tc", "tcg", "rot")) and self.tc_supported()   # configs outside the tensor-core kernels' limits run on the fp32-FMA kernel
+        use_rot = use_tc and BACKEND == "rot" and edge_vec is not None and self.rot_supported()
         st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
         assert len(sources) == ns and len(rows) == ns
@@ -803,7 +841,24 @@ class MessagePackOp:
         prof = PROFILER
         if prof is not None:
             prof.begin(self, int(n_edges), out.device)
-        if use_tc and BACKEND == "tcg":
+        if use_rot:
+            nb = len(self.branches)
+            E = int(n_edges)
+            dw = wigner_for(self, edge_vec)
+            chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
+            gstride = (max(self.n_channels) + 3) // 4 * 4
+            g_ws = torch.empty(nb * chunk * gstride, device=out.device, dtype=torch.float32)
+            xp_ws = torch.empty((chunk // self.ROT_TILE) * self.rot_tile_stride, device=out.device, dtype=torch.float32)
+            w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
+            nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
+            w3i = None
+            if GATE_BACKEND == "tc" and self.tc_w3img_off is not None:
+                w3i = (C.c_int32 * 2)(*(list(self.tc_w3img_off) + [0] * (2 - nb)))
+            rc = L.load().hgb_msgpack_rot_forward(C.byref(st["tc_plan"]), C.byref(self.rot_plan(out.device)), srcs, rws,
+                                                  dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride, g_ws.data_ptr(),
+                                                  xp_ws.data_ptr(), chunk, E, out.data_ptr(), L.ptr(out_index),
+                                                  L.stream_ptr(out.device))
+        elif use_tc and BACKEND in ("tcg", "rot"):
             nb = len(self.branches)
             gstride = (max(self.n_channels) + 3) // 4 * 4
             g_ws = torch.empty(nb * int(n_edges) * gstride, device=out.device, dtype=torch.float32)
@@ -825,7 +880,7 @@ class MessagePackOp:
                                               int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
         if prof is not None:
             prof.end(out.device)
-        L.check(rc, "hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward")
+        L.check(rc, "hgb_msgpack_rot_forward" if use_rot else ("hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward"))
         return out
 
     def radial_gate(self, weights: dict, rbf: torch.Tensor, backend: str = "tc") -> torch.Tensor:

@@ -139,6 +139,71 @@ int hgb_radial_gate(const hgb_msgpack_plan* plan_host, const float* rbf, const i
                     int64_t n_edges, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Edge-aligned ("rotated frame") evaluation of the same fused MessagePackBlock (csrc/msgpack_rot_kernel.cuh).
+ *
+ * In the frame where the edge vector is the polar axis, Y_l2 = sqrt(2 l2+1) delta_{m2,0} and the per-edge CG
+ * contraction T[i,k] = sum_j w3j[i,j,k] Y[j] of o3.TensorProduct (hamgnn/nn/message_passing.py:81-96) has a single
+ * non-zero per output component: a path splits into <= min(2 l1+1, 2 l3+1) "steps"
+ *     C'_{m3} += ((X'_{m1} W_p) * (scale * g_p)) L'_p,       X'_{m1}[z,u] = (D^{l1}(R_z) x_z)[u, m1],
+ * all of them tensor-core GEMMs on plain data.  hgb_wigner builds D^l(R_z) per edge (R_z takes the edge vector to
+ * the polar axis), the message call rotates + packs the inputs into (hi | lo) operand images (rotate_pack_kernel),
+ * runs the steps (msgpack_rot_kernel: TMA bulk copies -> tcgen05.mma 3xTF32 -> gate in TMEM -> tcgen05.mma) and
+ * rotates the message back, C = D^{l3}(R_z)^T C', before the store / receiver scatter-add.  Equivariance of the
+ * Wigner 3j symbols makes the result identical to the reference's up to fp32 rounding.
+ */
+typedef struct {
+  int32_t src0, nsrc;   /* input sources of the block: channel u -> source src0 + u / mul            */
+  int32_t in_off, mul;  /* first column / multiplicity of the irrep block inside a source row         */
+  int32_t l1;
+  int32_t kpad;         /* nsrc * mul rounded up to 8                                                 */
+  int32_t xoff;         /* float offset of the block inside a tile of the packed rotated input:
+                           [m1 = -l1..l1][chunk of <= 32 channels][hi | lo][k/4][128 edges][k%4]       */
+  int32_t pad;
+} hgb_rot_block_t;
+
+typedef struct {
+  int32_t a_off;        /* float offset of the step's A operand X'_{m1} inside a tile                  */
+  int32_t w_off;        /* plan->wbuf offset of the W_p images (kind 1: of the direct Linear images)   */
+  int32_t lf_off;       /* plan->wbuf offset of the L'_p image                                        */
+  int32_t g_off;        /* first gate column of the path                                              */
+  float scale;          /* w3j(l1,l2,l3)[m1, 0, m3] * sqrt(2 l2 + 1)                                  */
+  int16_t kpad;
+  int8_t kind;          /* 0: gated CG step, 1: direct (un-gated Linear of the edge features)         */
+  int8_t branch;
+  int8_t m3;            /* output component index l3 + m3                                             */
+  int8_t new_path;      /* bit 0: first step of its path, bit 1: last step of its path                */
+  int16_t pad;
+  int32_t pad2;
+} hgb_rot_step_t;
+
+typedef struct {
+  int32_t n_blocks, tile_stride, lmax, dstride;
+  int32_t doff[12];        /* float offset of D^l inside a per-edge Wigner row (row-major d x d)        */
+  int32_t step_begin[33];  /* steps of output slot t: [step_begin[t], step_begin[t+1])                 */
+  int32_t pad;
+  const hgb_rot_block_t* blocks;  /* device */
+  const hgb_rot_step_t* steps;    /* device */
+  const hgb_rot_block_t* blocks_host;
+  const hgb_rot_step_t* steps_host;
+  const double* wigner_j;         /* device: J^l = D^l(R_x(-90 deg)) at doff[l], fp64                  */
+} hgb_rot_plan;
+
+/* dw[e][doff[l] + a * (2l+1) + b] = D^l(R_e)[a][b] for l <= lmax, R_e = R_y(-theta) R_z(-phi) with (theta, phi) the
+ * polar angles of edge_vec[e] (physical unit vector, as written by hgb_edge_embed); evaluated in fp64 as
+ * J Z(-theta) J^T Z(-phi) from the vector components, stored fp32. */
+int hgb_wigner(const hgb_rot_plan* rot_host, const float* edge_vec, int64_t n_edges, float* dw, void* stream);
+
+/* The fused MessagePackBlock through the rotated frame.  plan: the tensor-core packing (as hgb_msgpack_tcg_forward);
+ * dw: hgb_wigner output for the same edges; g_ws / xp_ws: workspaces of n_branches * chunk * gstride and
+ * ceil(chunk / 128) * rot->tile_stride floats, chunk = min(chunk_edges, n_edges) (edges are processed chunk by
+ * chunk, chunk_edges a multiple of 128).  Other arguments as hgb_msgpack_tcg_forward_v2. */
+int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_plan* rot_host, const float* const* src_host,
+                            const int64_t* const* src_rows_host, const float* dw, const float* rbf,
+                            const int32_t* w3_off_host, const int32_t* nch_host, const int32_t* w3img_off_host,
+                            int32_t gstride, float* g_ws, float* xp_ws, int64_t chunk_edges, int64_t n_edges,
+                            float* out, const int64_t* out_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].
  * Replaces o3.Linear call sites (hamgnn/nn/convolution.py:112, interaction_blocks.py:126,306-309,
  * embeddings.py:286, toolbox/nequip/nn/_atomwise.py:51, hamgnn_output.py:49), ResidualBlock.forward
