@@ -237,22 +237,24 @@ struct RotArgs {
 
 // C[z][w][k] = sum_m3 D^{l3}_z[m3][k] C'[z][m3][w]; thread = edge z = TMEM lane; C' blocks of mp columns per m3 at `tc0`
 template <int L3>
-__device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mp, int mul, bool any, const float* __restrict__ Dz, float* __restrict__ op,
+__device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mp, int mul, uint32_t cmask, const float* __restrict__ Dz, float* __restrict__ op,
                                              bool live, bool atomic) {
   constexpr int d3 = 2 * L3 + 1;
   for (int c0 = 0; c0 < mul; c0 += 8) {   // warp-uniform
     uint32_t c[d3][8];
-    if (any) {
+    // cmask bit m: some step accumulated into C'_m; the other blocks were never written (stale TMEM) and count as zero
 #pragma unroll
-      for (int m = 0; m < d3; ++m) tc::tmem_ld8(tc0 + m * mp + c0, c[m]);
-#pragma unroll
-      for (int m = 0; m < d3; ++m) tc::tmem_ld_wait8(c[m]);
-    } else {
-#pragma unroll
-      for (int m = 0; m < d3; ++m)
+    for (int m = 0; m < d3; ++m) {
+      if ((cmask >> m) & 1u) {
+        tc::tmem_ld8(tc0 + m * mp + c0, c[m]);
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[m][j] = 0u;
+      }
     }
+#pragma unroll
+    for (int m = 0; m < d3; ++m)
+      if ((cmask >> m) & 1u) tc::tmem_ld_wait8(c[m]);
     if (!live) continue;
 #pragma unroll
     for (int k = 0; k < d3; ++k) {
@@ -418,8 +420,10 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
 #pragma unroll
     for (int j = 0; j < RW; ++j) gv[j] = 0.f;
     int qs = 0;
+    uint32_t cmask = 0;   // output components some step writes
     for (int si = sb; si < se; ++si) {
       const hgb_rot_step_t st = a.steps[si];
+      cmask |= 1u << st.m3;
       if (st.kind != 0) continue;
       if (st.new_path & 1) {
         const float* gp = grow + (size_t)st.branch * g_bstride + st.g_off;
@@ -467,13 +471,13 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
       const uint32_t tc0 = tmem + lane_base + TC;
       const bool atomic = a.out_index != nullptr;
       switch (ty.l) {
-        case 0: rot_epilogue<0>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        case 1: rot_epilogue<1>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        case 2: rot_epilogue<2>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        case 3: rot_epilogue<3>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        case 4: rot_epilogue<4>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        case 5: rot_epilogue<5>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
-        default: rot_epilogue<6>(tc0, mp, ty.mul, any, Dz, op, live, atomic); break;
+        case 0: rot_epilogue<0>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 1: rot_epilogue<1>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 2: rot_epilogue<2>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 3: rot_epilogue<3>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 4: rot_epilogue<4>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 5: rot_epilogue<5>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        default: rot_epilogue<6>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
       }
     }
   }
