@@ -26,8 +26,35 @@ constexpr int NTHR = 192;
 constexpr int LMAX = 6;
 
 using tcr::mbar_arrive;
-using tcr::mbar_wait_suspend;
-using tcr::warp_wait;
+
+// Barrier waits sit on the critical path of every step here (three hops per step), so they spin on try_wait -- which
+// itself suspends the thread for a hardware time slice -- without the nanosleep back-off of the rows-in-lanes kernel
+// (measured: 14 % of stall samples in nanosleep, ~3000 cycles per step, profiles/r01o_*).  Bounded: ~2 s, then trap.
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* mbar, uint32_t parity) {
+  const uint32_t addr = tc::smem_u32(mbar);
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ((++spins) & 1023) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void warp_wait(uint64_t* mbar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_suspend(mbar, parity);
+  __syncwarp();
+}
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_slot)), "r"(ncols) : "memory");
