@@ -260,42 +260,59 @@ struct RotArgs {
   const int64_t* out_index;
   int n_slots;
   int slot[32];
+  int dbl;              // 1: the gated-product lo block and the per-step GEMM2 accumulator are double buffered
 };
 
-// C[z][w][k] = sum_m3 D^{l3}_z[m3][k] C'[z][m3][w]; thread = edge z = TMEM lane; C' blocks of mp columns per m3 at `tc0`
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait1(uint32_t& r) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r)::"memory"); }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(r) : "memory");
+}
+
+// C[z][w][k] = sum_m3 D^{l3}_z[m3][k] C'[z][m3][w]; thread = edge z = TMEM lane; C'[m3][w] is TMEM column tc0 + m3 * mul + w
+// (exact stride, written by the accumulate phase); bit m3 of cmask: the component received contributions.
 template <int L3>
-__device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mp, int mul, uint32_t cmask, const float* __restrict__ Dz, float* __restrict__ op,
+__device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mul, uint32_t cmask, const float* __restrict__ Dz, float* __restrict__ op,
                                              bool live, bool atomic) {
   constexpr int d3 = 2 * L3 + 1;
-  for (int c0 = 0; c0 < mul; c0 += 8) {   // warp-uniform
-    uint32_t c[d3][8];
-    // cmask bit m: some step accumulated into C'_m; the other blocks were never written (stale TMEM) and count as zero
-#pragma unroll
-    for (int m = 0; m < d3; ++m) {
-      if ((cmask >> m) & 1u) {
-        tc::tmem_ld8(tc0 + m * mp + c0, c[m]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c[m][j] = 0u;
-      }
-    }
+  for (int c0 = 0; c0 < mul; c0 += 4) {   // warp-uniform
+    uint32_t c[d3][4];
 #pragma unroll
     for (int m = 0; m < d3; ++m)
-      if ((cmask >> m) & 1u) tc::tmem_ld_wait8(c[m]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[m][j] = 0u;
+        if (((cmask >> m) & 1u) && c0 + j < mul) tmem_ld1(tc0 + m * mul + c0 + j, c[m][j]);
+      }
+#pragma unroll
+    for (int m = 0; m < d3; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld_wait1(c[m][j]);
     if (!live) continue;
 #pragma unroll
     for (int k = 0; k < d3; ++k) {
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int m = 0; m < d3; ++m) {
         const float dmk = (L3 == 0) ? 1.f : __ldg(Dz + m * d3 + k);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(dmk, __uint_as_float(c[m][j]), acc[j]);
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(dmk, __uint_as_float(c[m][j]), acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const int w = c0 + j;
         if (w < mul) {
           if (atomic) atomicAdd(op + w * d3 + k, acc[j]);
@@ -306,32 +323,42 @@ __device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mp, int mul, uint
   }
 }
 
-// RW = padded-multiplicity capacity of the class (gate registers, stage size); the slot's own padded multiplicity
-// ty.mpad <= RW is the MMA N.  NST = depth of the operand ring.
+// One CTA = one (tile of 128 edges, output slot).  Steps are ordered by output component m3; every step is
+//   GEMM1  B[n&1]  = X'_{m1} W_p            warp 4 (A / W chunks from the TMA ring filled by warp 5)
+//   gate   B <- (B * scale * g) hi, GL <- lo warps 0-3, thread = edge = TMEM lane
+//   GEMM2  S       = (B.g) L'_p             warp 6 (fresh accumulator: accumulate = 0)
+//   acc   += S                              warps 0-3, fp32 round-to-nearest in registers
+// and at the end of an m3 group the registers go to C'[m3] in TMEM.  The tensor core's own accumulation chains stay
+// short (K/8 and mp/8 instructions x 3): its accumulator adds truncate, and a chain over all ~50 paths of a slot
+// cost 4x the fp32 rounding error of the whole network (scripts/error_budget.py, profiles/r01o_error_budget.log).
+// RW = padded-multiplicity capacity of the class (registers, stage size); ty.mpad <= RW is the MMA N.
+constexpr int NTHR2 = 224;
 template <int RW, int NST>
-__global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(const __grid_constant__ RotArgs a) {
+__global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(const __grid_constant__ RotArgs a) {
   constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
   extern __shared__ __align__(128) float smem[];
   float* sStage = smem;
   float* sL = smem + NST * STG;                       // 2 x (hi | lo) L' images
-  __shared__ uint64_t full[NST], empty[NST], lfull[2], ldone[2], bfull[2], gfull, gdone, cdone;
+  __shared__ uint64_t full[NST], empty[NST], lfull[2], bfull[2], gfull[2], s2done[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x / a.n_slots;
   const int t = a.slot[blockIdx.x - tile * a.n_slots];
   const hgb_type_t ty = a.plan.types[t];
-  const int d3 = 2 * ty.l + 1, mp = ty.mpad;
+  const int d3 = 2 * ty.l + 1, mp = ty.mpad, mul = ty.mul;
   const int sb = a.step_begin[t], se = a.step_begin[t + 1];
-  const bool any = se > sb;
+  const int dbl = a.dbl;
+  // TMEM columns: B0 | B1 | GL0 (| GL1) | S0 (| S1) | C' (d3 x mul, exact stride)
+  const uint32_t TB0 = 0, TGL0 = 2 * mp, TS0 = (uint32_t)((3 + dbl) * mp), TC = (uint32_t)((4 + 2 * dbl) * mp);
   uint32_t ncols = 32;
-  while ((int)ncols < (d3 + 3) * mp) ncols <<= 1;
-  const uint32_t TC = 0, TB0 = (uint32_t)(d3 * mp), TB1 = TB0 + mp, TGL = TB0 + 2 * mp;
+  while (ncols < TC + (uint32_t)(d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&lfull[i], 1); tc::mbar_init(&ldone[i], 1); tc::mbar_init(&bfull[i], 1); }
-    tc::mbar_init(&gfull, 4); tc::mbar_init(&gdone, 1); tc::mbar_init(&cdone, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&lfull[i], 1); tc::mbar_init(&bfull[i], 1); tc::mbar_init(&gfull[i], 4); tc::mbar_init(&s2done[i], 1);
+    }
     tc::mbar_fence_init();
   }
   if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
@@ -340,26 +367,29 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const float* __restrict__ wbuf = a.plan.wbuf;
+  const uint32_t idesc = tc::idesc_tf32_m128(mp);
+  const uint32_t dhi = tc::smem_desc_hi(128);
+  const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
+  const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
 
   if (warp == 5) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const float* xt = a.xp + (size_t)tile * a.tile_stride;
-      int n = 0, qp = 0;
-      for (int si = sb; si < se; ++si) {
+      int n = 0, c_all = 0;
+      for (int si = sb; si < se; ++si, ++n) {
         const hgb_rot_step_t st = a.steps[si];
-        if (st.kind == 0 && (st.new_path & 1)) {
-          const int lb = qp & 1;
-          if (qp >= 2) mbar_wait_suspend(&ldone[lb], (uint32_t)(((qp >> 1) - 1) & 1));
+        {
+          const int lb = n & 1;
+          if (n >= 2) mbar_wait_suspend(&s2done[lb], (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read sL[lb]
           const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
           mbar_expect_tx(&lfull[lb], lbytes);
           bulk_g2s(sL + lb * (2 * RW * RW), wbuf + st.lf_off, lbytes, &lfull[lb]);
-          ++qp;
         }
         const int kpad = st.kpad;
-        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++n) {
-          const int kc = min(KC, kpad - u0), s = n % NST;
-          if (n >= NST) mbar_wait_suspend(&empty[s], (uint32_t)(((n / NST) - 1) & 1));
+        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
+          const int kc = min(KC, kpad - u0), s = c_all % NST;
+          if (c_all >= NST) mbar_wait_suspend(&empty[s], (uint32_t)(((c_all / NST) - 1) & 1));
           float* sa = sStage + s * STG;
           const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
           mbar_expect_tx(&full[s], ab + wb);
@@ -370,104 +400,112 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
     }
     __syncwarp();
   } else if (warp == 4) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = tc::idesc_tf32_m128(mp);
-      const uint32_t dhi = tc::smem_desc_hi(128);
-      const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
-      const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
-      int n = 0, qs = 0, qp = 0;
-      uint32_t cmask = 0;                   // bit m3: C'_{m3} holds data
-      int pend = -1, pend_m3 = 0, pend_lb = 0, pend_lphase = 0, pend_flags = 0;
-      int cur_lb = 0, cur_lphase = 0;
-      auto gemm2 = [&]() {
-        mbar_wait_suspend(&gfull, (uint32_t)(pend & 1));
-        if (pend_flags & 1) mbar_wait_suspend(&lfull[pend_lb], (uint32_t)pend_lphase);
+    // =============================== GEMM1 issuer ===============================
+    int n = 0, c_all = 0;
+    for (int si = sb; si < se; ++si, ++n) {
+      const int kpad = a.steps[si].kpad;
+      if (n >= 2) warp_wait(&s2done[n & 1], (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read B[n&1]
+      const uint32_t dcol = tmem + TB0 + (uint32_t)((n & 1) * mp);
+      for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
+        const int kc = min(KC, kpad - u0), s = c_all % NST;
+        warp_wait(&full[s], (uint32_t)((c_all / NST) & 1));
         tc::fence_after_sync();
-        const uint32_t bq = tmem + ((pend & 1) ? TB1 : TB0);
-        const uint32_t lh = tc::smem_desc_lo(tc::smem_u32(sL + pend_lb * (2 * RW * RW)), lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
-        const uint32_t ccol = tmem + TC + (uint32_t)(pend_m3 * mp);
-        const uint32_t started = (cmask >> pend_m3) & 1u;
-        for (int k8 = 0; k8 < (mp >> 3); ++k8) {
-          const uint64_t bh = tc::desc64(lh + k8 * bstep, dhi), bl = tc::desc64(ll + k8 * bstep, dhi);
-          tc::mma_tf32_ts(ccol, tmem + TGL + k8 * 8, bh, idesc, started | (uint32_t)(k8 > 0));
-          tc::mma_tf32_ts(ccol, bq + k8 * 8, bl, idesc, 1);
-          tc::mma_tf32_ts(ccol, bq + k8 * 8, bh, idesc, 1);
-        }
-        tc::mma_commit(&gdone);
-        if (pend_flags & 2) tc::mma_commit(&ldone[pend_lb]);
-        cmask |= 1u << pend_m3;
-        pend = -1;
-      };
-      for (int si = sb; si < se; ++si) {
-        const hgb_rot_step_t st = a.steps[si];
-        const bool gated = st.kind == 0;
-        if (gated && (st.new_path & 1)) { cur_lb = qp & 1; cur_lphase = (qp >> 1) & 1; ++qp; }
-        const uint32_t dcol = tmem + (gated ? ((qs & 1) ? TB1 : TB0) : TC + (uint32_t)(st.m3 * mp));
-        const uint32_t base_acc = gated ? 0u : ((cmask >> st.m3) & 1u);
-        const int kpad = st.kpad;
-        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++n) {
-          const int kc = min(KC, kpad - u0), s = n % NST;
-          mbar_wait_suspend(&full[s], (uint32_t)((n / NST) & 1));
-          tc::fence_after_sync();
+        if (elect_one()) {
           const uint32_t sa = tc::smem_u32(sStage + s * STG);
           const uint32_t ah = tc::smem_desc_lo(sa, lbo_a), al = ah + (((uint32_t)kc * TILE * 4) >> 4);
           const uint32_t wh = tc::smem_desc_lo(sa + 2 * KC * TILE * 4, lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
           for (int k8 = 0; k8 < (kc >> 3); ++k8) {
             const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
-            const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl = tc::desc64(wl + k8 * bstep, dhi);
-            tc::mma_tf32(dcol, dal, dbh, idesc, base_acc | (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
-            tc::mma_tf32(dcol, dah, dbl, idesc, 1);
+            const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl_ = tc::desc64(wl + k8 * bstep, dhi);
+            tc::mma_tf32(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+            tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
             tc::mma_tf32(dcol, dah, dbh, idesc, 1);
           }
           tc::mma_commit(&empty[s]);
-          if (c == 0 && pend >= 0) gemm2();   // GEMM2 of the previous gated step, behind the first chunk of this one
+          if (u0 + KC >= kpad) tc::mma_commit(&bfull[n & 1]);
         }
-        if (gated) {
-          tc::mma_commit(&bfull[qs & 1]);
-          pend = qs; pend_m3 = st.m3; pend_lb = cur_lb; pend_lphase = cur_lphase; pend_flags = st.new_path;
-          ++qs;
-        } else {
-          cmask |= 1u << st.m3;
-        }
+        __syncwarp();
       }
-      if (pend >= 0) gemm2();
-      if (any) tc::mma_commit(&cdone);
     }
-    __syncwarp();
+  } else if (warp == 6) {
+    // =============================== GEMM2 issuer ===============================
+    int n = 0;
+    for (int si = sb; si < se; ++si, ++n) {
+      const int gi = dbl ? (n & 1) : 0;
+      warp_wait(&gfull[gi], (uint32_t)((dbl ? (n >> 1) : n) & 1));
+      warp_wait(&lfull[n & 1], (uint32_t)((n >> 1) & 1));
+      tc::fence_after_sync();
+      if (elect_one()) {
+        const uint32_t bq = tmem + TB0 + (uint32_t)((n & 1) * mp);
+        const uint32_t gl = tmem + TGL0 + (uint32_t)(gi * mp);
+        const uint32_t sc = tmem + TS0 + (uint32_t)(gi * mp);
+        const uint32_t lh = tc::smem_desc_lo(tc::smem_u32(sL + (n & 1) * (2 * RW * RW)), lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
+        for (int k8 = 0; k8 < (mp >> 3); ++k8) {
+          const uint64_t bh = tc::desc64(lh + k8 * bstep, dhi), bl = tc::desc64(ll + k8 * bstep, dhi);
+          tc::mma_tf32_ts(sc, gl + k8 * 8, bh, idesc, (uint32_t)(k8 > 0));
+          tc::mma_tf32_ts(sc, bq + k8 * 8, bl, idesc, 1);
+          tc::mma_tf32_ts(sc, bq + k8 * 8, bh, idesc, 1);
+        }
+        tc::mma_commit(&s2done[n & 1]);
+      }
+      __syncwarp();
+    }
   } else {
-    // =============================== gate + final rotation (thread = edge = TMEM lane) ===============================
+    // =============================== gate, accumulate, final rotation (thread = edge = TMEM lane) ===============================
     const int64_t el = (int64_t)tile * TILE + tid;
     const bool live = el < a.n_chunk;
     const int64_t e = a.e_lo + el;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const size_t g_bstride = (size_t)a.n_chunk * a.gstride;
     const float* grow = a.g + (size_t)(live ? el : 0) * a.gstride;
-    float gv[RW];
+    float gv[RW], acc[RW];
 #pragma unroll
-    for (int j = 0; j < RW; ++j) gv[j] = 0.f;
-    int qs = 0;
+    for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
     uint32_t cmask = 0;   // output components some step writes
-    for (int si = sb; si < se; ++si) {
-      const hgb_rot_step_t st = a.steps[si];
-      cmask |= 1u << st.m3;
-      if (st.kind != 0) continue;
-      if (st.new_path & 1) {
+    auto load_gate = [&](const hgb_rot_step_t& st) {   // gv = scale * g_p[z, :]; branch < 0: un-gated (direct Linear of the edge features)
+      const float sc = st.scale;
+      if (st.branch < 0) {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) gv[j] = (j < mul) ? sc : 0.f;
+      } else {
         const float* gp = grow + (size_t)st.branch * g_bstride + st.g_off;
 #pragma unroll
-        for (int j = 0; j < RW; ++j) gv[j] = (live && j < ty.mul) ? __ldg(gp + j) : 0.f;
-        if (live && st.pad2 >= 0) {   // next path's gate segment -> L2
-          const hgb_rot_step_t* nx = a.steps + st.pad2;
-          const float* np = grow + (size_t)nx->branch * g_bstride + nx->g_off;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(np + ty.mul - 1));
+        for (int j = 0; j < RW; ++j) gv[j] = (live && j < mul) ? __ldg(gp + j) * sc : 0.f;
+      }
+    };
+    // acc += S of step (n, flags, m3); at the end of an m3 group the registers move to C'[m3]
+    auto accumulate = [&](int n, int flags, int m3) {
+      const int gi = dbl ? (n & 1) : 0;
+      warp_wait(&s2done[n & 1], (uint32_t)((n >> 1) & 1));
+      tc::fence_after_sync();
+      const uint32_t sc = tmem + lane_base + TS0 + (uint32_t)(gi * mp);
+#pragma unroll
+      for (int c0 = 0; c0 < RW; c0 += 8) {
+        if (c0 < mp) {   // warp-uniform
+          uint32_t rs[8];
+          tc::tmem_ld8(sc + c0, rs);
+          tc::tmem_ld_wait8(rs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c0 + j] += __uint_as_float(rs[j]);
         }
       }
-      const float sc = st.scale;
-      warp_wait(&bfull[qs & 1], (uint32_t)((qs >> 1) & 1));
-      if (qs >= 1) warp_wait(&gdone, (uint32_t)((qs - 1) & 1));   // GEMM2 of the previous step has read (B.g) lo
+      if (flags & 4) {
+        const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul);
+#pragma unroll
+        for (int j = 0; j < RW; ++j) {
+          if (j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));   // warp-uniform predicate
+          acc[j] = 0.f;
+        }
+        tc::tmem_st_wait();
+      }
+      tc::fence_before_sync();   // the S block may be overwritten by a later GEMM2 once gfull of a later step is signalled
+    };
+    auto gate = [&](int n) {
+      const int gi = dbl ? (n & 1) : 0;
+      warp_wait(&bfull[n & 1], (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
-      const uint32_t bq = tmem + lane_base + ((qs & 1) ? TB1 : TB0);
+      const uint32_t bq = tmem + lane_base + TB0 + (uint32_t)((n & 1) * mp);
+      const uint32_t gl = tmem + lane_base + TGL0 + (uint32_t)(gi * mp);
 #pragma unroll
       for (int c0 = 0; c0 < RW; c0 += 8) {
         if (c0 < mp) {   // warp-uniform
@@ -477,20 +515,31 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float h, l;
-            tc::split_tf32(__uint_as_float(rb[j]) * (gv[c0 + j] * sc), h, l);
+            tc::split_tf32(__uint_as_float(rb[j]) * gv[c0 + j], h, l);
             hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
           }
           tc::tmem_st8(bq + c0, hi);
-          tc::tmem_st8(tmem + lane_base + TGL + c0, lo);
+          tc::tmem_st8(gl + c0, lo);
         }
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&gfull);
-      ++qs;
+      if (lane == 0) mbar_arrive(&gfull[gi]);
+    };
+    int n = 0, pflags = 0, pm3 = 0;
+    if (se > sb) load_gate(a.steps[sb]);
+    for (int si = sb; si < se; ++si, ++n) {
+      const int flags = a.steps[si].new_path, m3 = a.steps[si].m3;
+      cmask |= 1u << m3;
+      if (!dbl && n > 0) accumulate(n - 1, pflags, pm3);
+      gate(n);
+      if (si + 1 < se) load_gate(a.steps[si + 1]);   // next step's gate values travel while the accumulate phase runs
+      if (dbl && n > 0) accumulate(n - 1, pflags, pm3);
+      pflags = flags; pm3 = m3;
     }
-    if (any) { warp_wait(&cdone, 0); tc::fence_after_sync(); }
+    if (n > 0) accumulate(n - 1, pflags, pm3);
+    tc::fence_after_sync();
     {
       const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
       float* op = a.out + (live ? orow : 0) * a.plan.out_dim + ty.out_off;
@@ -498,13 +547,13 @@ __global__ void __launch_bounds__(NTHR, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(c
       const uint32_t tc0 = tmem + lane_base + TC;
       const bool atomic = a.out_index != nullptr;
       switch (ty.l) {
-        case 0: rot_epilogue<0>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        case 1: rot_epilogue<1>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        case 2: rot_epilogue<2>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        case 3: rot_epilogue<3>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        case 4: rot_epilogue<4>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        case 5: rot_epilogue<5>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
-        default: rot_epilogue<6>(tc0, mp, ty.mul, cmask, Dz, op, live, atomic); break;
+        case 0: rot_epilogue<0>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 1: rot_epilogue<1>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 2: rot_epilogue<2>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 3: rot_epilogue<3>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 4: rot_epilogue<4>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 5: rot_epilogue<5>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        default: rot_epilogue<6>(tc0, mul, cmask, Dz, op, live, atomic); break;
       }
     }
   }

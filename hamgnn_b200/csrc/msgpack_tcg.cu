@@ -668,7 +668,7 @@ int launch_rot_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
   constexpr size_t smem = rot::rot_smem_bytes<RW, NST>();
   static_assert(smem <= 227 * 1024, "msgpack_rot_kernel shared memory");
   HGB_CUDA_OK(cudaFuncSetAttribute(rot::msgpack_rot_kernel<RW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rot::msgpack_rot_kernel<RW, NST><<<(unsigned)(n_tiles * ra.n_slots), rot::NTHR, smem, st>>>(ra);
+  rot::msgpack_rot_kernel<RW, NST><<<(unsigned)(n_tiles * ra.n_slots), rot::NTHR2, smem, st>>>(ra);
   HGB_LAUNCH_OK("msgpack_rot_kernel");
   return 0;
 }
@@ -712,27 +712,31 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
   for (int t = 0; t < plan->n_types; ++t) {
     const hgb_type_t& ty = plan->types_host[t];
     const int d3 = 2 * ty.l + 1;
-    HGB_CHECK_ARG(ty.l >= 0 && ty.l <= rp->lmax && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX && (d3 + 3) * ty.mpad <= 512,
+    HGB_CHECK_ARG(ty.l >= 0 && ty.l <= rp->lmax && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
                   "hgb_msgpack_rot_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
     klass[t] = ty.mpad <= 16 ? 0 : (ty.mpad <= 32 ? 1 : 2);
+    {
+      const int dbl = (klass[t] == 1) ? 0 : 1;   // TMEM: B0 B1 GL (GL) S (S) + d3 x mul
+      HGB_CHECK_ARG((4 + 2 * dbl) * ty.mpad + d3 * ty.mul <= 512, "hgb_msgpack_rot_forward: slot %d needs more than 512 TMEM columns", t);
+    }
     HGB_CHECK_ARG(rp->step_begin[t] >= 0 && rp->step_begin[t] <= rp->step_begin[t + 1], "hgb_msgpack_rot_forward: bad step range of slot %d", t);
     double c = 0;
-    int npath_open = 0;
+    int last_m3 = -1, open_group = 0;
     for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si) {
       const hgb_rot_step_t& s = rp->steps_host[si];
-      HGB_CHECK_ARG(s.kpad >= 8 && s.kpad % 8 == 0 && s.m3 >= 0 && s.m3 < d3 && (s.kind == 0 || s.kind == 1) && s.a_off >= 0 && s.a_off % 4 == 0 &&
-                        (int64_t)s.a_off + (int64_t)2 * s.kpad * rot::TILE <= rp->tile_stride && s.w_off >= 0 && s.w_off % 4 == 0,
+      HGB_CHECK_ARG(s.kpad >= 8 && s.kpad % 8 == 0 && s.m3 >= 0 && s.m3 < d3 && s.kind == 0 && s.a_off >= 0 && s.a_off % 4 == 0 &&
+                        (int64_t)s.a_off + (int64_t)2 * s.kpad * rot::TILE <= rp->tile_stride && s.w_off >= 0 && s.w_off % 4 == 0 &&
+                        s.lf_off >= 0 && s.lf_off % 4 == 0 && (s.new_path & 1),
                     "hgb_msgpack_rot_forward: bad step %d", si);
-      if (s.kind == 0) {
-        HGB_CHECK_ARG(s.branch >= 0 && s.branch < plan->n_branches && s.g_off >= 0 && s.g_off + ty.mul <= nch[s.branch] && s.lf_off >= 0 && s.lf_off % 4 == 0,
-                      "hgb_msgpack_rot_forward: gate columns / L' image of step %d out of range", si);
-        HGB_CHECK_ARG(((s.new_path & 1) != 0) == (npath_open == 0), "hgb_msgpack_rot_forward: path flags of step %d inconsistent", si);
-        npath_open = (s.new_path & 2) ? 0 : 1;
-        HGB_CHECK_ARG(s.pad2 < rp->step_begin[t + 1], "hgb_msgpack_rot_forward: prefetch link of step %d out of range", si);
-      }
-      c += (double)(s.kpad + (s.kind == 0 ? ty.mpad : 0)) * ty.mpad + 600.0;
+      HGB_CHECK_ARG(s.branch < plan->n_branches && (s.branch < 0 || (s.g_off >= 0 && s.g_off + ty.mul <= nch[s.branch])),
+                    "hgb_msgpack_rot_forward: gate columns of step %d out of range", si);
+      // steps are grouped by output component (the kernel keeps one component in registers at a time)
+      HGB_CHECK_ARG(open_group ? (s.m3 == last_m3) : (s.m3 > last_m3), "hgb_msgpack_rot_forward: step %d breaks the m3 grouping", si);
+      last_m3 = s.m3;
+      open_group = (s.new_path & 4) ? 0 : 1;
+      c += (double)(s.kpad + ty.mpad) * ty.mpad + 600.0;
     }
-    HGB_CHECK_ARG(npath_open == 0, "hgb_msgpack_rot_forward: slot %d ends inside a path", t);
+    HGB_CHECK_ARG(open_group == 0, "hgb_msgpack_rot_forward: slot %d ends inside an m3 group", t);
     cost[t] = c;
     order[t] = t;
   }
@@ -758,6 +762,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       a.slot[ns++] = t;
     }
     a.n_slots = ns;
+    a.dbl = (k == 1) ? 0 : 1;
   }
   rot::RpArgs pa;
   memset(&pa, 0, sizeof(pa));

@@ -645,6 +645,15 @@ class MessagePackOp:
                 wcur += 2 * mp * Kpad
                 plist.append(L.PathT(1, 0, self.direct_src, 1, sp.in_off, sp.mul_in, sp.l1, 0, sp.l3, 0, 0, 0, 0, 0, lf_off, 0))
             types[t] = L.TypeT(m.mul, mp, m.ir.l, out_offs[t], begin, len(plist), 0, 0)
+        # identity L' images (hi = I, lo = 0), one per padded multiplicity: the rotated-frame kernel runs the un-gated
+        # direct Linear through the same GEMM1 -> gate -> GEMM2 pipeline with g = 1 and L' = I
+        self.tc_ident_off = {}
+        for mp in sorted({int(ty.mpad) for ty in types}):
+            wcur = (wcur + 3) // 4 * 4
+            self.tc_ident_off[mp] = wcur
+            kk = np.arange(mp)
+            add_image(wcur, mp, kk, kk, np.full(mp, self.src_total, dtype=np.int64), 1.0, mp)
+            wcur += 2 * mp * mp
         self.tc_w_total = wcur
         self.tc_types_c = types
         self.tc_paths_c = (L.PathT * max(1, len(plist)))(*plist)
@@ -689,50 +698,43 @@ class MessagePackOp:
             ty = self.tc_types_c[t]
             l3 = ty.l
             lmax = max(lmax, l3)
-            for p in range(ty.path_begin, ty.path_end):
-                pa = self.tc_paths_c[p]
-                l1 = pa.l1
-                lmax = max(lmax, l1)
-                blk = block_of(pa.src0, pa.nsrc, pa.in_off, pa.mul_in, l1)
-                per_m = 2 * blk.kpad * T
-                first = True
-                if pa.kind == 0:
-                    w = so3.wigner_3j(l1, pa.l2, l3)
-                    even = (l1 + pa.l2 + l3) % 2 == 0
-                    for m1 in range(-l1, l1 + 1):
-                        m3 = m1 if even else -m1
-                        if abs(m3) > l3:
+            # steps are ordered by output component m3 (the kernel accumulates one component at a time in registers);
+            # within a component by path.  Flags (new_path): bit 0 = L' image to load (every step), bit 2 = last step
+            # of its m3 group.  branch = -1: un-gated direct Linear (W = its images, L' = identity).
+            for m3 in range(-l3, l3 + 1):
+                group: List[L.RotStepT] = []
+                for p in range(ty.path_begin, ty.path_end):
+                    pa = self.tc_paths_c[p]
+                    l1 = pa.l1
+                    lmax = max(lmax, l1)
+                    blk = block_of(pa.src0, pa.nsrc, pa.in_off, pa.mul_in, l1)
+                    per_m = 2 * blk.kpad * T
+                    if pa.kind == 0:
+                        w = so3.wigner_3j(l1, pa.l2, l3)
+                        even = (l1 + pa.l2 + l3) % 2 == 0
+                        m1 = m3 if even else -m3
+                        if abs(m1) > l1:
                             continue
                         c = float(w[l1 + m1, pa.l2, l3 + m3]) * math.sqrt(2 * pa.l2 + 1)
                         if c == 0.0:
                             continue
-                        steps.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.w_off, pa.lf_off, pa.pad0, c, blk.kpad, 0,
-                                                pa.branch, l3 + m3, 1 if first else 0, 0, 0))
-                        first = False
-                    # every non-zero of T0 must be covered by exactly those steps
-                    t0 = w[:, pa.l2, :]
-                    assert int((t0 != 0).sum()) == sum(1 for m1 in range(-l1, l1 + 1)
-                                                       if abs(m1) <= l3 and t0[l1 + m1, l3 + (m1 if even else -m1)] != 0)
-                else:
-                    assert l1 == l3
-                    for m1 in range(-l1, l1 + 1):
-                        steps.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.lf_off, 0, 0, 1.0, blk.kpad, 1, 0, l3 + m1,
-                                                0, 0, 0))
+                        # the aligned-frame T has no other non-zero in this column
+                        col = w[:, pa.l2, l3 + m3]
+                        assert int((col != 0).sum()) == 1
+                        group.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.w_off, pa.lf_off, pa.pad0, c, blk.kpad, 0,
+                                                pa.branch, l3 + m3, 1, 0, 0))
+                    else:
+                        assert l1 == l3
+                        group.append(L.RotStepT(blk.xoff + (l1 + m3) * per_m, pa.lf_off, self.tc_ident_off[int(ty.mpad)], 0, 1.0,
+                                                blk.kpad, 0, -1, l3 + m3, 1, 0, 0))
+                if group:
+                    group[-1].new_path |= 4
+                steps.extend(group)
             step_begin.append(len(steps))
-        # pad2 of a path's first step = index of the next path's first gated step (gate prefetch), -1 at the end
-        nxt = -1
-        for t in range(len(self.irreps_out) - 1, -1, -1):
-            nxt = -1
-            for si in range(step_begin[t + 1] - 1, step_begin[t] - 1, -1):
-                steps[si].pad2 = nxt
-                if steps[si].kind == 0 and (steps[si].new_path & 1):
-                    nxt = si
-        # bit 1 of new_path: last step of its path
-        for si, s_ in enumerate(steps):
-            if s_.kind == 0:
-                last = (si + 1 == len(steps)) or steps[si + 1].kind != 0 or (steps[si + 1].new_path & 1) or (si + 1 in step_begin)
-                if last:
-                    s_.new_path |= 2
+            # every non-zero of every path's aligned-frame T is covered exactly once
+            n_nz = sum(int((so3.wigner_3j(self.tc_paths_c[p].l1, self.tc_paths_c[p].l2, l3)[:, self.tc_paths_c[p].l2, :] != 0).sum())
+                       for p in range(ty.path_begin, ty.path_end) if self.tc_paths_c[p].kind == 0)
+            assert n_nz == sum(1 for s_ in steps[step_begin[-2]:] if s_.branch >= 0)
         self.rot_blocks_c = (L.RotBlockT * max(1, len(blocks)))(*blocks)
         self.rot_steps_c = (L.RotStepT * max(1, len(steps)))(*steps)
         self.rot_n_blocks, self.rot_n_steps = len(blocks), len(steps)
@@ -748,7 +750,7 @@ class MessagePackOp:
 
     def rot_supported(self) -> bool:
         return (self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32 and self.rot_n_steps > 0
-                and all((2 * ty.l + 4) * ty.mpad <= 512 for ty in self.tc_types_c))
+                and all((4 if 16 < ty.mpad <= 32 else 6) * ty.mpad + (2 * ty.l + 1) * ty.mul <= 512 for ty in self.tc_types_c))
 
     def rot_plan(self, device) -> "L.RotPlan":
         st = self._device_state(device)
@@ -796,6 +798,7 @@ class MessagePackOp:
                               weights["fc"][b][2].reshape(-1), self._fold(b, weights["lin_mid"][b], weights["lin_out"][b])]
                 if self.direct_src is not None:
                     parts.append(weights["direct"].reshape(-1))
+                parts.append(torch.ones(1, device=dev))   # constant source element (identity images)
                 cat = torch.cat(parts).float()
                 vals = cat[st["tc_src"]] * st["tc_scale"]
                 hi = _tf32_round(vals)                                              # round-to-nearest tf32

@@ -379,10 +379,10 @@ def emulate_msgpack_rot(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, ve
             W = torch.cat([_decode_image(wbuf, st.w_off + 2 * mp * KC * c, mp, min(KC, st.kpad - u0))
                            for c, u0 in enumerate(range(0, st.kpad, KC))], dim=0)
             if st.kind == 0:
-                if st.new_path:
+                if st.new_path & 1:
                     Lf = _decode_image(wbuf, st.lf_off, mp, mp)
                 gv = torch.zeros(E, mp, dtype=dt)
-                gv[:, :ty.mul] = g[st.branch][:, st.g_off:st.g_off + ty.mul]
+                gv[:, :ty.mul] = g[st.branch][:, st.g_off:st.g_off + ty.mul] if st.branch >= 0 else 1.0
                 Cacc[:, st.m3, :] += ((A @ W) * (gv * st.scale)) @ Lf
             else:
                 Cacc[:, st.m3, :] += A @ W
