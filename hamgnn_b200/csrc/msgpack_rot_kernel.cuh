@@ -32,24 +32,26 @@ using tcr::mbar_arrive;
 // (measured: 14 % of stall samples in nanosleep, ~3000 cycles per step, profiles/r01o_*).  Bounded: ~2 s, then trap.
 __device__ __forceinline__ void mbar_wait_suspend(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = tc::smem_u32(mbar);
-  uint32_t done;
-  long long t0 = 0;
-  int spins = 0;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ((++spins) & 1023) == 0) {
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 4000000000ll) __trap();
-    }
-  } while (!done);
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "mov.u32 %0, 1;\n"
+      "HGB_ROT_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra HGB_ROT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 0x4000000;\n\t"
+      "@p bra HGB_ROT_WAIT;\n\t"
+      "mov.u32 %0, 0;\n"
+      "HGB_ROT_DONE:\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (!ok) __trap();   // a pipeline bug must surface as a kernel error, never as a hung GPU
 }
 __device__ __forceinline__ void warp_wait(uint64_t* mbar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait_suspend(mbar, parity);
@@ -65,6 +67,10 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols)
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA bulk prefetch of a contiguous global block into L2 (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `mbar` (16-byte aligned, size % 16 == 0)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
@@ -253,7 +259,7 @@ struct RotArgs {
   const float* dw;
   int dstride;
   int doff[12];
-  const float* g;       // [n_branches][n_chunk][gstride]
+  const float* g;       // [n_branches][tile][gstride][128]: tile-major radial gate of this chunk
   int gstride;
   int64_t e_lo, n_chunk;
   float* out;
@@ -376,9 +382,22 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const float* xt = a.xp + (size_t)tile * a.tile_stride;
+      // gate block of a step: mul columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 GPF steps
+      // before the epilogue warps load it (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident)
+      constexpr int GPF = 3;
+      const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+      const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+      auto prefetch_gate = [&](int sj) {
+        if (sj < se) {
+          const hgb_rot_step_t* ps = a.steps + sj;
+          if (ps->branch >= 0) bulk_prefetch_l2(gt + (size_t)ps->branch * g_bstride + (size_t)ps->g_off * TILE, (uint32_t)(mul * TILE) * 4u);
+        }
+      };
+      for (int j = 0; j < GPF; ++j) prefetch_gate(sb + j);
       int n = 0, c_all = 0;
       for (int si = sb; si < se; ++si, ++n) {
         const hgb_rot_step_t st = a.steps[si];
+        prefetch_gate(si + GPF);
         {
           const int lb = n & 1;
           if (n >= 2) mbar_wait_suspend(&s2done[lb], (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read sL[lb]
@@ -456,8 +475,8 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     const bool live = el < a.n_chunk;
     const int64_t e = a.e_lo + el;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const size_t g_bstride = (size_t)a.n_chunk * a.gstride;
-    const float* grow = a.g + (size_t)(live ? el : 0) * a.gstride;
+    const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + tid;                            // column c of this edge: grow[c * TILE]
     float gv[RW], acc[RW];
 #pragma unroll
     for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
@@ -468,9 +487,9 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
 #pragma unroll
         for (int j = 0; j < RW; ++j) gv[j] = (j < mul) ? sc : 0.f;
       } else {
-        const float* gp = grow + (size_t)st.branch * g_bstride + st.g_off;
+        const float* gp = grow + (size_t)st.branch * g_bstride + (size_t)st.g_off * TILE;
 #pragma unroll
-        for (int j = 0; j < RW; ++j) gv[j] = (live && j < mul) ? __ldg(gp + j) * sc : 0.f;
+        for (int j = 0; j < RW; ++j) gv[j] = (live && j < mul) ? __ldg(gp + j * TILE) * sc : 0.f;   // a warp reads 128 contiguous bytes
       }
     };
     // acc += S of step (n, flags, m3); at the end of an m3 group the registers move to C'[m3]

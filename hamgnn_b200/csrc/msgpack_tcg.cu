@@ -352,6 +352,7 @@ struct GateArgs {
   int64_t n_edges;
   int n_branches, rbf_dim, h1, h2dim, gstride;
   float act_const;
+  int tmajor;           // 1: g is [n_branches][tile of 128 edges][gstride][128] (see gtc::Args)
 };
 constexpr int GE = 64;    // edges per CTA
 constexpr int GN = 128;   // W3 column tile
@@ -433,6 +434,16 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
       }
+      if (a.tmajor) {
+        // rows ty*4 .. ty*4+3 of one column are 16 contiguous bytes of the tile-major layout (padding rows included)
+        const int64_t n_tiles = (a.n_edges + 127) / 128;
+        float* gt = a.g + ((size_t)b * n_tiles + (size_t)(e0 >> 7)) * (size_t)a.gstride * 128 + (e0 & 127) + ty * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+          if (c < nch) *reinterpret_cast<float4*>(gt + (size_t)c * 128) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+        }
+      } else
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int z = ty * 4 + i;
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
 // MLP widths fit its tiling, the fp32-FMA kernel otherwise.
 int launch_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int32_t* w3_off, const int32_t* nch,
-                       const int32_t* w3img_off, int32_t gstride, float* g_ws, int64_t n_edges, cudaStream_t st) {
+                       const int32_t* w3img_off, int32_t gstride, float* g_ws, int64_t n_edges, cudaStream_t st, int tmajor = 0) {
   for (int b = 0; b < plan->n_branches; ++b)
     HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "radial gate: width %d exceeds stride %d", nch[b], gstride);
   const bool tc_ok = w3img_off != nullptr && plan->h2 % 8 == 0 && plan->h2 <= gtc::KMAX && plan->h1 % 4 == 0 &&
@@ -466,7 +477,7 @@ int launch_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int
     gtc::Args ga;
     memset(&ga, 0, sizeof(ga));
     ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.rbf_dim = plan->rbf_dim; ga.h1 = plan->h1; ga.h2dim = plan->h2;
-    ga.gstride = gstride; ga.act_const = plan->act_const;
+    ga.gstride = gstride; ga.act_const = plan->act_const; ga.tmajor = tmajor;
     for (int b = 0; b < plan->n_branches; ++b) {
       HGB_CHECK_ARG(w3img_off[b] >= 0 && w3img_off[b] % 4 == 0, "radial gate: packed W3 tiles of branch %d are not 16-byte aligned", b);
       ga.w1[b] = plan->wbuf + plan->fc1_off[b];
@@ -485,7 +496,7 @@ int launch_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int
   GateArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.rbf = rbf; ga.g = g_ws; ga.n_edges = n_edges; ga.n_branches = plan->n_branches; ga.rbf_dim = plan->rbf_dim;
-  ga.h1 = plan->h1; ga.h2dim = plan->h2; ga.gstride = gstride; ga.act_const = plan->act_const;
+  ga.h1 = plan->h1; ga.h2dim = plan->h2; ga.gstride = gstride; ga.act_const = plan->act_const; ga.tmajor = tmajor;
   for (int b = 0; b < plan->n_branches; ++b) {
     ga.w1[b] = plan->wbuf + plan->fc1_off[b];
     ga.w2[b] = plan->wbuf + plan->fc2_off[b];
@@ -781,7 +792,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
     const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
     {
-      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st);
+      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 1);
       if (rc != 0) return rc;
     }
     pa.e_lo = e_lo; pa.n_chunk = n;

@@ -46,6 +46,8 @@ struct Args {
   int64_t n_edges;
   int rbf_dim, h1, h2dim, gstride;
   float act_const;
+  int tmajor;              // 1: g is [n_branches][tile of 128 edges][gstride][128] (edge-minor inside a tile: the layout the
+                           // rotated-frame message kernel reads, coalesced on both sides); 0: [n_branches][E][gstride]
 };
 
 // one dense layer for one row: out[j] = act(sum_r xin[r] * W[r][j]) * c, j in [j0, j0 + 16); W row-major [n_in][ldw]
@@ -196,7 +198,18 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
         const uint32_t col = tmem + lane_base + (uint32_t)((t & 1) * TN + h * 32);
         tc::tmem_ld8(col, r[0]); tc::tmem_ld8(col + 8, r[1]); tc::tmem_ld8(col + 16, r[2]); tc::tmem_ld8(col + 24, r[3]);
         tc::tmem_ld_wait8(r[0]); tc::tmem_ld_wait8(r[1]); tc::tmem_ld_wait8(r[2]); tc::tmem_ld_wait8(r[3]);
-        if (live) {
+        if (a.tmajor) {
+          // every thread (padding rows of the last tile included: the workspace is padded) writes one float per column;
+          // a warp covers 128 contiguous bytes
+          float* gt = a.g + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)a.gstride * ROWS + tid;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = n0 + h * 32 + q * 8 + j;
+              if (c < nch) gt[(size_t)c * ROWS] = __uint_as_float(r[q][j]);
+            }
+        } else if (live) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int c = n0 + h * 32 + q * 8;

@@ -850,7 +850,7 @@ class MessagePackOp:
             dw = wigner_for(self, edge_vec)
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
-            g_ws = torch.empty(nb * chunk * gstride, device=out.device, dtype=torch.float32)
+            g_ws = torch.empty(nb * chunk * gstride, device=out.device, dtype=torch.float32)   # [nb][tile][gstride][128]
             xp_ws = torch.empty((chunk // self.ROT_TILE) * self.rot_tile_stride, device=out.device, dtype=torch.float32)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
             nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
