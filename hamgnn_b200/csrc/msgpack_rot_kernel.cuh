@@ -339,14 +339,59 @@ __device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mul, uint32_t cma
 // cost 4x the fp32 rounding error of the whole network (scripts/error_budget.py, profiles/r01o_error_budget.log).
 // RW = padded-multiplicity capacity of the class (registers, stage size); ty.mpad <= RW is the MMA N.
 constexpr int NTHR2 = 224;
+
+// barrier helpers on precomputed 32-bit shared addresses (no generic -> shared conversion per use)
+__device__ __forceinline__ void wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "mov.u32 %0, 1;\n"
+      "HGB_ROT_WAIT_A:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra HGB_ROT_DONE_A;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 0x4000000;\n\t"
+      "@p bra HGB_ROT_WAIT_A;\n\t"
+      "mov.u32 %0, 0;\n"
+      "HGB_ROT_DONE_A:\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (!ok) __trap();   // a pipeline bug must surface as a kernel error, never as a hung GPU
+}
+__device__ __forceinline__ void warp_wait_a(uint32_t addr, uint32_t parity) {   // one lane waits, the warp re-converges
+  if ((threadIdx.x & 31) == 0) wait_a(addr, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void arrive_a(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void expect_tx_a(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+
 template <int RW, int NST>
 __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(const __grid_constant__ RotArgs a) {
   constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
   extern __shared__ __align__(128) float smem[];
-  float* sStage = smem;
-  float* sL = smem + NST * STG;                       // 2 x (hi | lo) L' images
-  __shared__ uint64_t full[NST], empty[NST], lfull[2], bfull[2], gfull[2], s2done[2];
+  // barriers: full[NST] | empty[NST] | lfull[2] | bfull[2] | gfull[2] | s2done[2]
+  __shared__ uint64_t bars[2 * NST + 8];
   __shared__ uint32_t tmem_slot;
+  const uint32_t bar0 = tc::smem_u32(bars);
+  const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_BFULL = B_LFULL + 16, B_GFULL = B_LFULL + 32,
+                 B_S2 = B_LFULL + 48;
+  const uint32_t stage0 = tc::smem_u32(smem);                   // ring stages, STG floats each
+  const uint32_t sl0 = stage0 + (uint32_t)(NST * STG) * 4u;     // 2 x (hi | lo) L' images, 2 RW^2 floats each
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x / a.n_slots;
@@ -361,10 +406,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
   while (ncols < TC + (uint32_t)(d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&lfull[i], 1); tc::mbar_init(&bfull[i], 1); tc::mbar_init(&gfull[i], 4); tc::mbar_init(&s2done[i], 1);
-    }
+    for (int i = 0; i < 2 * NST + 8; ++i) tc::mbar_init(&bars[i], (i >= 2 * NST + 4 && i < 2 * NST + 6) ? 4 : 1);   // gfull: one arrival per gate warp
     tc::mbar_fence_init();
   }
   if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
@@ -395,25 +437,25 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       };
       for (int j = 0; j < GPF; ++j) prefetch_gate(sb + j);
       int n = 0, c_all = 0;
+      const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
       for (int si = sb; si < se; ++si, ++n) {
         const hgb_rot_step_t st = a.steps[si];
         prefetch_gate(si + GPF);
         {
           const int lb = n & 1;
-          if (n >= 2) mbar_wait_suspend(&s2done[lb], (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read sL[lb]
-          const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
-          mbar_expect_tx(&lfull[lb], lbytes);
-          bulk_g2s(sL + lb * (2 * RW * RW), wbuf + st.lf_off, lbytes, &lfull[lb]);
+          if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read the L' buffer
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(sl0 + (uint32_t)(lb * 2 * RW * RW) * 4u, wbuf + st.lf_off, lbytes, B_LFULL + 8 * lb);
         }
         const int kpad = st.kpad;
         for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
           const int kc = min(KC, kpad - u0), s = c_all % NST;
-          if (c_all >= NST) mbar_wait_suspend(&empty[s], (uint32_t)(((c_all / NST) - 1) & 1));
-          float* sa = sStage + s * STG;
+          if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
+          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
           const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
-          mbar_expect_tx(&full[s], ab + wb);
-          bulk_g2s(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, &full[s]);
-          bulk_g2s(sa + 2 * KC * TILE, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, &full[s]);
+          expect_tx_a(B_FULL + 8 * s, ab + wb);
+          bulk_g2s_a(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
+          bulk_g2s_a(sa + 2 * KC * TILE * 4, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
         }
       }
     }
@@ -421,16 +463,17 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
   } else if (warp == 4) {
     // =============================== GEMM1 issuer ===============================
     int n = 0, c_all = 0;
+    int kpad = (sb < se) ? a.steps[sb].kpad : 0;
     for (int si = sb; si < se; ++si, ++n) {
-      const int kpad = a.steps[si].kpad;
-      if (n >= 2) warp_wait(&s2done[n & 1], (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read B[n&1]
+      const int kpad_next = (si + 1 < se) ? a.steps[si + 1].kpad : 0;   // in flight while this step is issued
+      if (n >= 2) warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read B[n&1]
       const uint32_t dcol = tmem + TB0 + (uint32_t)((n & 1) * mp);
       for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
         const int kc = min(KC, kpad - u0), s = c_all % NST;
-        warp_wait(&full[s], (uint32_t)((c_all / NST) & 1));
+        warp_wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
         tc::fence_after_sync();
         if (elect_one()) {
-          const uint32_t sa = tc::smem_u32(sStage + s * STG);
+          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
           const uint32_t ah = tc::smem_desc_lo(sa, lbo_a), al = ah + (((uint32_t)kc * TILE * 4) >> 4);
           const uint32_t wh = tc::smem_desc_lo(sa + 2 * KC * TILE * 4, lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
           for (int k8 = 0; k8 < (kc >> 3); ++k8) {
@@ -440,32 +483,33 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
             tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
             tc::mma_tf32(dcol, dah, dbh, idesc, 1);
           }
-          tc::mma_commit(&empty[s]);
-          if (u0 + KC >= kpad) tc::mma_commit(&bfull[n & 1]);
+          commit_a(B_EMPTY + 8 * s);
+          if (u0 + KC >= kpad) commit_a(B_BFULL + 8 * (n & 1));
         }
         __syncwarp();
       }
+      kpad = kpad_next;
     }
   } else if (warp == 6) {
     // =============================== GEMM2 issuer ===============================
     int n = 0;
     for (int si = sb; si < se; ++si, ++n) {
       const int gi = dbl ? (n & 1) : 0;
-      warp_wait(&gfull[gi], (uint32_t)((dbl ? (n >> 1) : n) & 1));
-      warp_wait(&lfull[n & 1], (uint32_t)((n >> 1) & 1));
+      warp_wait_a(B_GFULL + 8 * gi, (uint32_t)((dbl ? (n >> 1) : n) & 1));
+      warp_wait_a(B_LFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
       if (elect_one()) {
         const uint32_t bq = tmem + TB0 + (uint32_t)((n & 1) * mp);
         const uint32_t gl = tmem + TGL0 + (uint32_t)(gi * mp);
         const uint32_t sc = tmem + TS0 + (uint32_t)(gi * mp);
-        const uint32_t lh = tc::smem_desc_lo(tc::smem_u32(sL + (n & 1) * (2 * RW * RW)), lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
+        const uint32_t lh = tc::smem_desc_lo(sl0 + (uint32_t)((n & 1) * 2 * RW * RW) * 4u, lbo_n), ll = lh + (((uint32_t)mp * mp * 4) >> 4);
         for (int k8 = 0; k8 < (mp >> 3); ++k8) {
           const uint64_t bh = tc::desc64(lh + k8 * bstep, dhi), bl = tc::desc64(ll + k8 * bstep, dhi);
           tc::mma_tf32_ts(sc, gl + k8 * 8, bh, idesc, (uint32_t)(k8 > 0));
           tc::mma_tf32_ts(sc, bq + k8 * 8, bl, idesc, 1);
           tc::mma_tf32_ts(sc, bq + k8 * 8, bh, idesc, 1);
         }
-        tc::mma_commit(&s2done[n & 1]);
+        commit_a(B_S2 + 8 * (n & 1));
       }
       __syncwarp();
     }
@@ -476,26 +520,31 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     const int64_t e = a.e_lo + el;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
-    const float* grow = a.g + (size_t)tile * a.gstride * TILE + tid;                            // column c of this edge: grow[c * TILE]
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);            // column c of this edge: grow[c * TILE]
     float gv[RW], acc[RW];
 #pragma unroll
     for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
+    float gsc = 0.f;      // scale of the step whose gate values sit in gv
     uint32_t cmask = 0;   // output components some step writes
-    auto load_gate = [&](const hgb_rot_step_t& st) {   // gv = scale * g_p[z, :]; branch < 0: un-gated (direct Linear of the edge features)
-      const float sc = st.scale;
+    // gv = g_p[z, :] of a step (raw loads: nothing here may consume them, so that they stay in flight while the
+    // accumulate phase runs); branch < 0: un-gated (direct Linear of the edge features).  Padding rows of the last
+    // tile read row 0 of the tile: their B rows are zero and are never stored.
+    auto load_gate = [&](const hgb_rot_step_t& st) {
+      gsc = st.scale;
       if (st.branch < 0) {
 #pragma unroll
-        for (int j = 0; j < RW; ++j) gv[j] = (j < mul) ? sc : 0.f;
+        for (int j = 0; j < RW; ++j) gv[j] = 1.f;
       } else {
         const float* gp = grow + (size_t)st.branch * g_bstride + (size_t)st.g_off * TILE;
 #pragma unroll
-        for (int j = 0; j < RW; ++j) gv[j] = (live && j < mul) ? __ldg(gp + j * TILE) * sc : 0.f;   // a warp reads 128 contiguous bytes
+        for (int j = 0; j < RW; ++j)
+          if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
       }
     };
     // acc += S of step (n, flags, m3); at the end of an m3 group the registers move to C'[m3]
     auto accumulate = [&](int n, int flags, int m3) {
       const int gi = dbl ? (n & 1) : 0;
-      warp_wait(&s2done[n & 1], (uint32_t)((n >> 1) & 1));
+      warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
       const uint32_t sc = tmem + lane_base + TS0 + (uint32_t)(gi * mp);
 #pragma unroll
@@ -521,7 +570,8 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     };
     auto gate = [&](int n) {
       const int gi = dbl ? (n & 1) : 0;
-      warp_wait(&bfull[n & 1], (uint32_t)((n >> 1) & 1));
+      const float gsc_n = gsc;
+      warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
       const uint32_t bq = tmem + lane_base + TB0 + (uint32_t)((n & 1) * mp);
       const uint32_t gl = tmem + lane_base + TGL0 + (uint32_t)(gi * mp);
@@ -534,7 +584,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float h, l;
-            tc::split_tf32(__uint_as_float(rb[j]) * gv[c0 + j], h, l);
+            tc::split_tf32(__uint_as_float(rb[j]) * gsc_n * gv[c0 + j], h, l);
             hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
           }
           tc::tmem_st8(bq + c0, hi);
@@ -544,18 +594,23 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&gfull[gi]);
+      if (lane == 0) arrive_a(B_GFULL + 8 * gi);
     };
     int n = 0, pflags = 0, pm3 = 0;
-    if (se > sb) load_gate(a.steps[sb]);
+    hgb_rot_step_t cur;
+    memset(&cur, 0, sizeof(cur));
+    if (se > sb) { cur = a.steps[sb]; load_gate(cur); }
     for (int si = sb; si < se; ++si, ++n) {
-      const int flags = a.steps[si].new_path, m3 = a.steps[si].m3;
+      hgb_rot_step_t nx = cur;
+      if (si + 1 < se) nx = a.steps[si + 1];   // in flight during the gate phase
+      const int flags = cur.new_path, m3 = cur.m3;
       cmask |= 1u << m3;
       if (!dbl && n > 0) accumulate(n - 1, pflags, pm3);
       gate(n);
-      if (si + 1 < se) load_gate(a.steps[si + 1]);   // next step's gate values travel while the accumulate phase runs
+      if (si + 1 < se) load_gate(nx);   // next step's gate values travel while the accumulate phase runs
       if (dbl && n > 0) accumulate(n - 1, pflags, pm3);
       pflags = flags; pm3 = m3;
+      cur = nx;
     }
     if (n > 0) accumulate(n - 1, pflags, pm3);
     tc::fence_after_sync();

@@ -237,7 +237,7 @@ class KernelProfiler:
 PROFILER: Optional[KernelProfiler] = None
 # which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
-BACKEND = os.environ.get("HGB_MSGPACK", "tcg")
+BACKEND = os.environ.get("HGB_MSGPACK", "rot")
 # radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
 GATE_BACKEND = os.environ.get("HGB_GATE", "simt")
 
