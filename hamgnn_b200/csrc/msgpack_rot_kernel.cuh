@@ -524,22 +524,23 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     float gv[RW], acc[RW];
 #pragma unroll
     for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
-    float gsc = 0.f;      // scale of the step whose gate values sit in gv
-    uint32_t cmask = 0;   // output components some step writes
-    // gv = g_p[z, :] of a step (raw loads: nothing here may consume them, so that they stay in flight while the
-    // accumulate phase runs); branch < 0: un-gated (direct Linear of the edge features).  Padding rows of the last
-    // tile read row 0 of the tile: their B rows are zero and are never stored.
-    auto load_gate = [&](const hgb_rot_step_t& st) {
-      gsc = st.scale;
-      if (st.branch < 0) {
+    float gA = 0.f, gB = 0.f;   // gate factor of the step whose values sit in gv: B *= gv * gA + gB
+    uint32_t cmask = 0;         // output components some step writes
+    // One step record = two 16-byte words (hgb_rot_step_t): {a_off, w_off, lf_off, g_off} {scale, kpad|kind|branch, m3|flags|pad, pad2}
+    const uint4* steps4 = reinterpret_cast<const uint4*>(a.steps);
+    // gv = g_p[z, :] of a step: raw predicated loads straight into the registers, nothing here consumes them, so they
+    // stay in flight while the accumulate phase runs.  Un-gated steps (branch < 0, the direct Linear of the edge
+    // features) load the same way (any valid column) and use the factor (gA, gB) = (0, scale) instead of (scale, 0).
+    // Padding rows of the last tile read row 0 of the tile: their B rows are zero and are never stored.
+    auto load_gate = [&](const uint4& w0, const uint4& w1) {
+      const float sc = __uint_as_float(w1.x);
+      const int br = (int)(int8_t)(w1.y >> 24);
+      gA = (br < 0) ? 0.f : sc;
+      gB = (br < 0) ? sc : 0.f;
+      const float* gp = grow + (size_t)max(br, 0) * g_bstride + (size_t)((br < 0) ? 0 : (int)w0.w) * TILE;
 #pragma unroll
-        for (int j = 0; j < RW; ++j) gv[j] = 1.f;
-      } else {
-        const float* gp = grow + (size_t)st.branch * g_bstride + (size_t)st.g_off * TILE;
-#pragma unroll
-        for (int j = 0; j < RW; ++j)
-          if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
-      }
+      for (int j = 0; j < RW; ++j)
+        if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
     };
     // acc += S of step (n, flags, m3); at the end of an m3 group the registers move to C'[m3]
     auto accumulate = [&](int n, int flags, int m3) {
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     };
     auto gate = [&](int n) {
       const int gi = dbl ? (n & 1) : 0;
-      const float gsc_n = gsc;
+      const float fa = gA, fb = gB;
       warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
       const uint32_t bq = tmem + lane_base + TB0 + (uint32_t)((n & 1) * mp);
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float h, l;
-            tc::split_tf32(__uint_as_float(rb[j]) * gsc_n * gv[c0 + j], h, l);
+            tc::split_tf32(__uint_as_float(rb[j]) * fmaf(gv[c0 + j], fa, fb), h, l);
             hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
           }
           tc::tmem_st8(bq + c0, hi);
@@ -597,20 +598,24 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       if (lane == 0) arrive_a(B_GFULL + 8 * gi);
     };
     int n = 0, pflags = 0, pm3 = 0;
-    hgb_rot_step_t cur;
-    memset(&cur, 0, sizeof(cur));
-    if (se > sb) { cur = a.steps[sb]; load_gate(cur); }
+    uint32_t cur_fm = 0;   // m3 | flags << 8 of the current step
+    if (se > sb) {
+      const uint4 w0 = __ldg(steps4 + 2 * sb), w1 = __ldg(steps4 + 2 * sb + 1);
+      cur_fm = w1.z;
+      load_gate(w0, w1);
+    }
     for (int si = sb; si < se; ++si, ++n) {
-      hgb_rot_step_t nx = cur;
-      if (si + 1 < se) nx = a.steps[si + 1];   // in flight during the gate phase
-      const int flags = cur.new_path, m3 = cur.m3;
+      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+      const bool more = si + 1 < se;
+      if (more) { n0 = __ldg(steps4 + 2 * (si + 1)); n1 = __ldg(steps4 + 2 * (si + 1) + 1); }   // in flight during the gate phase
+      const int m3 = (int)(cur_fm & 0xff), flags = (int)((cur_fm >> 8) & 0xff);
       cmask |= 1u << m3;
       if (!dbl && n > 0) accumulate(n - 1, pflags, pm3);
       gate(n);
-      if (si + 1 < se) load_gate(nx);   // next step's gate values travel while the accumulate phase runs
+      if (more) load_gate(n0, n1);   // next step's gate values travel while the accumulate phase runs
       if (dbl && n > 0) accumulate(n - 1, pflags, pm3);
       pflags = flags; pm3 = m3;
-      cur = nx;
+      cur_fm = n1.z;
     }
     if (n > 0) accumulate(n - 1, pflags, pm3);
     tc::fence_after_sync();
