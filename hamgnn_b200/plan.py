@@ -239,7 +239,7 @@ PROFILER: Optional[KernelProfiler] = None
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
 BACKEND = os.environ.get("HGB_MSGPACK", "rot")
 # radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
-GATE_BACKEND = os.environ.get("HGB_GATE", "simt")
+GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND == "rot" else "simt")
 
 
 # edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)

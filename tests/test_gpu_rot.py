@@ -95,8 +95,9 @@ def test_single_message_calls(setup, chunk):
     assert em < TOL and ea < TOL and ep < TOL
 
 
-@pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si")])
-def test_full_forward_rot_backend(cfg_name, gname):
+@pytest.mark.parametrize("gate", ["simt", "tc"])
+@pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si"), ("default", "mixed")])
+def test_full_forward_rot_backend(cfg_name, gname, gate):
     cfg = SMALL_CFG if cfg_name == "small" else DEFAULT_CFG
     pre, out, opre, oout = build_pair(cfg, nao_max=19, add_H0=False)
     batch = gd.Batch.from_data_list(_graphs(gname))
@@ -105,10 +106,10 @@ def test_full_forward_rot_backend(cfg_name, gname):
     pre.to(dev)
     out.to(dev)
     errs = {}
-    old = P.BACKEND
+    old = (P.BACKEND, P.GATE_BACKEND)
     try:
         for backend in ("tcg", "rot"):
-            P.BACKEND = backend
+            P.BACKEND, P.GATE_BACKEND = backend, gate
             b = gd.Batch(**batch.to_dict()).to(dev)
             with torch.no_grad():
                 r = pre(b)
@@ -116,7 +117,7 @@ def test_full_forward_rot_backend(cfg_name, gname):
             torch.cuda.synchronize()
             errs[backend] = (rel_err(r["node_attr"].cpu(), rep["node_attr"]), rel_err(r["edge_attr"].cpu(), rep["edge_attr"]),
                              rel_err(o["hamiltonian"].cpu(), res["hamiltonian"]))
-            print(f"[{cfg_name} {backend}] rel err node {errs[backend][0]:.2e} edge {errs[backend][1]:.2e} H {errs[backend][2]:.2e}")
+            print(f"[{cfg_name} {gname} {backend} gate={gate}] rel err node {errs[backend][0]:.2e} edge {errs[backend][1]:.2e} H {errs[backend][2]:.2e}")
     finally:
-        P.BACKEND = old
+        P.BACKEND, P.GATE_BACKEND = old
     assert max(errs["rot"]) < TOL, errs
