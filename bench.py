@@ -291,7 +291,7 @@ def main():
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": h_host.numel() * 4},
         "gpu_launches": launches,
         "roofline": {"kernel": {"tc": "msgpack_tc_kernel (fused MessagePackBlock, tcgen05 3xTF32)", "tcg": "radial_gate_kernel + msgpack_tcg_kernel/msgpack_tcr_kernel (fused MessagePackBlock, tcgen05 3xTF32, gate pre-pass)",
-                                 "rot": "radial_gate_kernel + rotate_pack_kernel + msgpack_rot_kernel (fused MessagePackBlock in the edge-aligned frame, TMA + tcgen05 3xTF32)"}.get(P.BACKEND, "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)"), "bound": "tensor",
+                                 "rot": "fused MessagePackBlock call = radial_gate(_tc)_kernel + rotate_pack_kernel + msgpack_rot_kernel x3 classes per edge chunk (edge-aligned frame, TMA + tcgen05 3xTF32)"}.get(P.BACKEND, "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)"), "bound": "tensor",
                      "achieved": k_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k_tflops / bf16_peak,
                      "peak_source": peak_src, "traffic": None, "avg_launch_ms": k_ms, "launches_timed": ksum["launches"],
                      "kernel_share_of_step": ksum["total_ms"] / (ms_step * args.steps),

@@ -292,35 +292,35 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
 // (exact stride, written by the accumulate phase); bit m3 of cmask: the component received contributions.
 template <int L3>
 __device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mul, uint32_t cmask, const float* __restrict__ Dz, float* __restrict__ op,
-                                             bool live, bool atomic, int cbeg, int cend) {
+                                             bool live, bool atomic) {
   constexpr int d3 = 2 * L3 + 1;
-  for (int c0 = cbeg; c0 < cend; c0 += 2) {   // warp-uniform; [cbeg, cend) = the channels this warp accumulated itself
-    uint32_t c[d3][2];
+  for (int c0 = 0; c0 < mul; c0 += 4) {   // warp-uniform
+    uint32_t c[d3][4];
 #pragma unroll
     for (int m = 0; m < d3; ++m)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 4; ++j) {
         c[m][j] = 0u;
-        if (((cmask >> m) & 1u) && c0 + j < cend) tmem_ld1(tc0 + m * mul + c0 + j, c[m][j]);
+        if (((cmask >> m) & 1u) && c0 + j < mul) tmem_ld1(tc0 + m * mul + c0 + j, c[m][j]);
       }
 #pragma unroll
     for (int m = 0; m < d3; ++m)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) tmem_ld_wait1(c[m][j]);
+      for (int j = 0; j < 4; ++j) tmem_ld_wait1(c[m][j]);
     if (!live) continue;
 #pragma unroll
     for (int k = 0; k < d3; ++k) {
-      float acc[2] = {0.f, 0.f};
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int m = 0; m < d3; ++m) {
         const float dmk = (L3 == 0) ? 1.f : __ldg(Dz + m * d3 + k);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) acc[j] = fmaf(dmk, __uint_as_float(c[m][j]), acc[j]);
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(dmk, __uint_as_float(c[m][j]), acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const int w = c0 + j;
-        if (w < cend) {
+        if (w < mul) {
           if (atomic) atomicAdd(op + w * d3 + k, acc[j]);
           else op[w * d3 + k] = acc[j];
         }
@@ -338,7 +338,7 @@ __device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mul, uint32_t cma
 // short (K/8 and mp/8 instructions x 3): its accumulator adds truncate, and a chain over all ~50 paths of a slot
 // cost 4x the fp32 rounding error of the whole network (scripts/error_budget.py, profiles/r01o_error_budget.log).
 // RW = padded-multiplicity capacity of the class (registers, stage size); ty.mpad <= RW is the MMA N.
-constexpr int NTHR2 = 352;   // 8 gate/accumulate warps (two per TMEM lane quadrant, half of the columns each) + GEMM1, TMA, GEMM2 warps
+constexpr int NTHR2 = 224;
 
 // barrier helpers on precomputed 32-bit shared addresses (no generic -> shared conversion per use)
 __device__ __forceinline__ void wait_a(uint32_t addr, uint32_t parity) {
@@ -406,10 +406,10 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
   while (ncols < TC + (uint32_t)(d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * NST + 8; ++i) tc::mbar_init(&bars[i], (i >= 2 * NST + 4 && i < 2 * NST + 6) ? 8 : 1);   // gfull: one arrival per gate warp
+    for (int i = 0; i < 2 * NST + 8; ++i) tc::mbar_init(&bars[i], (i >= 2 * NST + 4 && i < 2 * NST + 6) ? 4 : 1);   // gfull: one arrival per gate warp
     tc::mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc_dyn(&tmem_slot, ncols);
+  if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
   const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
   const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
 
-  if (warp == 9) {
+  if (warp == 5) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const float* xt = a.xp + (size_t)tile * a.tile_stride;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == 4) {
     // =============================== GEMM1 issuer ===============================
     int n = 0, c_all = 0;
     int kpad = (sb < se) ? a.steps[sb].kpad : 0;
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       }
       kpad = kpad_next;
     }
-  } else if (warp == 10) {
+  } else if (warp == 6) {
     // =============================== GEMM2 issuer ===============================
     int n = 0;
     for (int si = sb; si < se; ++si, ++n) {
@@ -515,19 +515,15 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
     }
   } else {
     // =============================== gate, accumulate, final rotation (thread = edge = TMEM lane) ===============================
-    // warps w and w + 4 share TMEM lane quadrant w & 3 (rows 32 (w & 3) ..): each handles half of the mp columns
-    const int row = (warp & 3) * 32 + lane, wg = warp >> 2;
-    const int hc = mp >> 1, cb = wg * hc;   // this warp's columns [cb, cb + hc) of every mp-wide block
-    constexpr int HW = RW / 2;
-    const int64_t el = (int64_t)tile * TILE + row;
+    const int64_t el = (int64_t)tile * TILE + tid;
     const bool live = el < a.n_chunk;
     const int64_t e = a.e_lo + el;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
-    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? row : 0);            // column c of this edge: grow[c * TILE]
-    float gv[HW], acc[HW];
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);            // column c of this edge: grow[c * TILE]
+    float gv[RW], acc[RW];
 #pragma unroll
-    for (int j = 0; j < HW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
+    for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
     float gA = 0.f, gB = 0.f;   // gate factor of the step whose values sit in gv: B *= gv * gA + gB
     uint32_t cmask = 0;         // output components some step writes
     // One step record = two 16-byte words (hgb_rot_step_t): {a_off, w_off, lf_off, g_off} {scale, kpad|kind|branch, m3|flags|pad, pad2}
@@ -541,20 +537,20 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       const int br = (int)(int8_t)(w1.y >> 24);
       gA = (br < 0) ? 0.f : sc;
       gB = (br < 0) ? sc : 0.f;
-      const float* gp = grow + (size_t)max(br, 0) * g_bstride + (size_t)(((br < 0) ? 0 : (int)w0.w) + cb) * TILE;
+      const float* gp = grow + (size_t)max(br, 0) * g_bstride + (size_t)((br < 0) ? 0 : (int)w0.w) * TILE;
 #pragma unroll
-      for (int j = 0; j < HW; ++j)
-        if (cb + j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
+      for (int j = 0; j < RW; ++j)
+        if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
     };
     // acc += S of step (n, flags, m3); at the end of an m3 group the registers move to C'[m3]
     auto accumulate = [&](int n, int flags, int m3) {
       const int gi = dbl ? (n & 1) : 0;
       warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
-      const uint32_t sc = tmem + lane_base + TS0 + (uint32_t)(gi * mp + cb);
+      const uint32_t sc = tmem + lane_base + TS0 + (uint32_t)(gi * mp);
 #pragma unroll
-      for (int c0 = 0; c0 < HW; c0 += 8) {
-        if (c0 < hc) {   // warp-uniform
+      for (int c0 = 0; c0 < RW; c0 += 8) {
+        if (c0 < mp) {   // warp-uniform
           uint32_t rs[8];
           tc::tmem_ld8(sc + c0, rs);
           tc::tmem_ld_wait8(rs);
@@ -563,10 +559,10 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
         }
       }
       if (flags & 4) {
-        const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul + cb);
+        const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul);
 #pragma unroll
-        for (int j = 0; j < HW; ++j) {
-          if (cb + j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));   // warp-uniform predicate
+        for (int j = 0; j < RW; ++j) {
+          if (j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));   // warp-uniform predicate
           acc[j] = 0.f;
         }
         tc::tmem_st_wait();
@@ -578,11 +574,11 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       const float fa = gA, fb = gB;
       warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
-      const uint32_t bq = tmem + lane_base + TB0 + (uint32_t)((n & 1) * mp + cb);
-      const uint32_t gl = tmem + lane_base + TGL0 + (uint32_t)(gi * mp + cb);
+      const uint32_t bq = tmem + lane_base + TB0 + (uint32_t)((n & 1) * mp);
+      const uint32_t gl = tmem + lane_base + TGL0 + (uint32_t)(gi * mp);
 #pragma unroll
-      for (int c0 = 0; c0 < HW; c0 += 8) {
-        if (c0 < hc) {   // warp-uniform
+      for (int c0 = 0; c0 < RW; c0 += 8) {
+        if (c0 < mp) {   // warp-uniform
           uint32_t rb[8], hi[8], lo[8];
           tc::tmem_ld8(bq + c0, rb);
           tc::tmem_ld_wait8(rb);
@@ -630,19 +626,19 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       const uint32_t tc0 = tmem + lane_base + TC;
       const bool atomic = a.out_index != nullptr;
       switch (ty.l) {
-        case 0: rot_epilogue<0>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        case 1: rot_epilogue<1>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        case 2: rot_epilogue<2>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        case 3: rot_epilogue<3>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        case 4: rot_epilogue<4>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        case 5: rot_epilogue<5>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
-        default: rot_epilogue<6>(tc0, mul, cmask, Dz, op, live, atomic, cb, min(cb + hc, mul)); break;
+        case 0: rot_epilogue<0>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 1: rot_epilogue<1>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 2: rot_epilogue<2>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 3: rot_epilogue<3>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 4: rot_epilogue<4>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 5: rot_epilogue<5>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        default: rot_epilogue<6>(tc0, mul, cmask, Dz, op, live, atomic); break;
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc_dyn(tmem, ncols);
+  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
 
 template <int RW, int NST>

@@ -96,7 +96,7 @@ def test_single_message_calls(setup, chunk):
 
 
 @pytest.mark.parametrize("gate", ["simt", "tc"])
-@pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si"), ("default", "mixed")])
+@pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si")])
 def test_full_forward_rot_backend(cfg_name, gname, gate):
     cfg = SMALL_CFG if cfg_name == "small" else DEFAULT_CFG
     pre, out, opre, oout = build_pair(cfg, nao_max=19, add_H0=False)
