@@ -293,7 +293,12 @@ def main():
         "roofline": {"kernel": {"tc": "msgpack_tc_kernel (fused MessagePackBlock, tcgen05 3xTF32)", "tcg": "radial_gate_kernel + msgpack_tcg_kernel/msgpack_tcr_kernel (fused MessagePackBlock, tcgen05 3xTF32, gate pre-pass)",
                                  "rot": "fused MessagePackBlock call = radial_gate(_tc)_kernel + rotate_pack_kernel + msgpack_rot_kernel x3 classes per edge chunk (edge-aligned frame, TMA + tcgen05 3xTF32)"}.get(P.BACKEND, "msgpack_kernel (fused MessagePackBlock, fp32 SIMT)"), "bound": "tensor",
                      "achieved": k_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k_tflops / bf16_peak,
-                     "peak_source": peak_src, "traffic": None, "avg_launch_ms": k_ms, "launches_timed": ksum["launches"],
+                     "peak_source": peak_src, "traffic": None,
+                     # DRAM bytes of one fused-message call per edge from the ncu --set full captures of the same command on
+                     # tbg_m8 (profiles/r01v_rot_msgpack_ncu_summary.md, r01o_rotate_pack_ncu_summary.md): message kernels
+                     # 15.6 GB + rotate-pack 2.6 GB + gate 2.0 GB for 69 408 edges.  Not per launch of this workload -> "traffic" stays null.
+                     "traffic_ncu_bytes_per_edge_tbg_m8": 291e3 if P.BACKEND == "rot" else None,
+                     "avg_launch_ms": k_ms, "launches_timed": ksum["launches"],
                      "kernel_share_of_step": ksum["total_ms"] / (ms_step * args.steps),
                      "flop_per_edge": ksum["flops"] / max(1, ksum["edges"]),
                      "hbm_view": {"achieved": k_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak,

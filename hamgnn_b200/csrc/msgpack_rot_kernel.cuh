@@ -11,10 +11,12 @@
 //   wigner_kernel       D^l(R_z) per edge, l <= 6, fp64 arithmetic (once per forward)
 //   rotate_pack_kernel  gathers the input rows, rotates every irrep block, splits hi/lo and writes ready-made UMMA
 //                       operand images (tile of 128 edges = 128 MMA rows)
-//   msgpack_rot_kernel  one CTA per (tile, output slot): warp 5 streams A / W chunks and L' images with TMA bulk
-//                       copies into an mbarrier ring, warp 4 issues the tcgen05 3xTF32 MMAs, warps 0-3 (thread = edge =
-//                       TMEM lane) apply the gate between the two GEMMs in TMEM and finally rotate the message back,
-//                       C = D^{l3}(R_z)^T C', before the store / receiver scatter-add.
+//   msgpack_rot_kernel  one CTA per (tile, output slot), steps ordered by output component m3: warp 5 streams A / W chunks
+//                       and L' images with TMA bulk copies into an mbarrier ring and prefetches the gate blocks into L2,
+//                       warp 4 issues GEMM1 (tcgen05 3xTF32), warps 0-3 (thread = edge = TMEM lane) apply the gate in
+//                       TMEM, warp 6 issues GEMM2 into a fresh accumulator, warps 0-3 add it into fp32 registers, park
+//                       each finished component in TMEM and finally rotate the message back, C = D^{l3}(R_z)^T C',
+//                       before the store / receiver scatter-add.
 #pragma once
 
 namespace rot {
