@@ -210,6 +210,56 @@ def test_rotated_frame_program_matches_oracle(small):
     assert rel_err(got, ref_emb) < 2e-6
 
 
+def test_rotated_frame_tables_are_well_formed():
+    """Structure the kernel relies on: steps grouped by output component with the group-end flag on the last one,
+    operand images inside the packed tile, 16-byte aligned offsets, the identity L' image, TMEM budget, J orthogonal."""
+    import ctypes as C
+    from hamgnn_b200 import lib as L, so3
+    from hamgnn_b200.plan import Branch, MessagePackOp
+    D = Irreps("64x0e+64x0o+32x1o+16x1e+12x2o+25x2e+18x3o+9x3e+4x4o+9x4e+4x5o+4x5e+2x6e")
+    op = MessagePackOp([Branch(D, 2, 0), Branch(D, 1, 2)], "0e+1o+2e+3o+4e+5o", D, 64, [64, 64], src_dims=[877, 877, 877], direct_src=2)
+    assert C.sizeof(L.RotStepT) == 32 and C.sizeof(L.RotBlockT) == 32 and C.sizeof(L.RotPlan) == 240
+    assert op.rot_supported() and op.rot_lmax == 6 and op.rot_dstride == 476 and op.rot_doff == [0, 4, 16, 44, 96, 180, 304]
+    assert op.rot_tile_stride % 1024 == 0
+    T = op.ROT_TILE
+    for b in op.rot_blocks_c[:op.rot_n_blocks]:
+        assert b.kpad % 8 == 0 and b.kpad >= b.nsrc * b.mul and b.xoff % 4 == 0
+        assert b.xoff + (2 * b.l1 + 1) * 2 * b.kpad * T <= op.rot_tile_stride
+    n_direct = 0
+    for t in range(len(op.irreps_out)):
+        ty = op.tc_types_c[t]
+        d3 = 2 * ty.l + 1
+        steps = [op.rot_steps_c[i] for i in range(op.rot_step_begin[t], op.rot_step_begin[t + 1])]
+        assert steps, t
+        last_m3, open_group = -1, False
+        for st in steps:
+            assert st.kind == 0 and (st.new_path & 1) and 0 <= st.m3 < d3 and st.kpad % 8 == 0
+            assert st.a_off % 4 == 0 and st.w_off % 4 == 0 and st.lf_off % 4 == 0
+            assert st.a_off + 2 * st.kpad * T <= op.rot_tile_stride
+            assert (st.m3 == last_m3) if open_group else (st.m3 > last_m3)
+            last_m3, open_group = st.m3, not (st.new_path & 4)
+            if st.branch < 0:
+                n_direct += 1
+                assert st.lf_off == op.tc_ident_off[int(ty.mpad)] and st.scale == 1.0
+            else:
+                assert 0 <= st.g_off and st.g_off + ty.mul <= op.n_channels[st.branch] and st.scale != 0.0
+        assert not open_group
+        dbl = 0 if 16 < ty.mpad <= 32 else 1
+        assert (4 + 2 * dbl) * ty.mpad + d3 * ty.mul <= (512 if ty.mpad > 32 else 256)      # 2 CTAs/SM for the l >= 1 slots
+    assert n_direct == sum(m.ir.dim for m in D)                                       # one un-gated step per (slot, output component)
+    assert op.rot_n_steps == 2883
+    for l in range(op.rot_lmax + 1):
+        J = so3.wigner_J(l)
+        assert np.abs(J @ J.T - np.eye(2 * l + 1)).max() < 1e-12
+    # the identity images decode to I
+    w = {"tp": [torch.randn(n) for n in op.tp_numel], "fc": [[torch.randn(64, 64), torch.randn(64, 64), torch.randn(64, c)] for c in op.n_channels],
+         "lin_mid": [torch.randn(b[1]) for b in op.lin_mid_blocks], "lin_out": [torch.randn(b[1]) for b in op.lin_out_blocks],
+         "direct": torch.randn(op.direct_blocks[1])}
+    st = op.pack_tc(w)
+    for mp, off in op.tc_ident_off.items():
+        assert torch.equal(EM._decode_image(st["tc_wbuf"], off, mp, mp), torch.eye(mp))
+
+
 def test_radial_gate_tiles_match_oracle(small):
     """The W3 tiles of the tensor-core gate pre-pass decode to the oracle's FullyConnectedNet (both branches)."""
     pre, out, opre, oout, g, d, rep, res = small
