@@ -243,7 +243,7 @@ GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND == "rot" else "simt")
 
 
 # edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)
-ROT_CHUNK_EDGES = int(os.environ.get("HGB_ROT_CHUNK", str(128 * 1024)))
+ROT_CHUNK_EDGES = int(os.environ.get("HGB_ROT_CHUNK", str(512 * 1024)))
 _WIGNER_CACHE: Dict[Tuple, torch.Tensor] = {}
 
 
