@@ -4,7 +4,7 @@
 set -x
 N=${1:-2}
 TAG=${2:-r01h}
-BACKEND=${3:-simt}
+BACKEND=${3:-rot}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/${TAG}_gpus.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
