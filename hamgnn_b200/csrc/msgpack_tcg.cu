@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "msgpack_tcr_kernel.cuh"
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
+#include "msgpack_rot_s2_kernel.cuh"
 
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
 // MLP widths fit its tiling, the fp32-FMA kernel otherwise.
@@ -775,6 +776,20 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     a.n_slots = ns;
     a.dbl = (k == 1) ? 0 : 1;
   }
+  // experimental variant for the padded-multiplicity-16 slots (msgpack_rot_s2_kernel.cuh), opt-in
+  bool use_s2 = false;
+  {
+    const char* s2 = getenv("HGB_ROT_S2");
+    if (s2 && s2[0] == '1') {
+      use_s2 = true;
+      for (int t = 0; t < plan->n_types; ++t) {
+        if (klass[t] != 0) continue;
+        HGB_CHECK_ARG(plan->types_host[t].mpad == rot::S2_MP, "hgb_msgpack_rot_forward: HGB_ROT_S2 needs padded multiplicity 16 in slot %d", t);
+        for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si)
+          HGB_CHECK_ARG(rp->steps_host[si].pad2 > 0 && rp->steps_host[si].pad2 % 4 == 0, "hgb_msgpack_rot_forward: step %d has no fp32 L' copy", si);
+      }
+    }
+  }
   rot::RpArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.blocks = rp->blocks; pa.n_blocks = rp->n_blocks; pa.tile_stride = rp->tile_stride; pa.dstride = rp->dstride;
@@ -802,7 +817,13 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
-      if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
+      if (k == 0 && use_s2) {
+        constexpr size_t smem = rot::rot_s2_smem_bytes();
+        static_assert(smem <= 75 * 1024, "msgpack_rot_s2_kernel: 3 CTAs/SM budget");
+        HGB_CUDA_OK(cudaFuncSetAttribute(rot::msgpack_rot_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rot::msgpack_rot_s2_kernel<<<(unsigned)(n_tiles * cls[k].n_slots), rot::S2_NTHR, smem, st>>>(cls[k]);
+        HGB_LAUNCH_OK("msgpack_rot_s2_kernel");
+      } else if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
       else if (k == 1) rc = launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;

@@ -657,6 +657,33 @@ class MessagePackOp:
         self.tc_w_total = wcur
         self.tc_types_c = types
         self.tc_paths_c = (L.PathT * max(1, len(plist)))(*plist)
+        # un-split fp32 copies of every L' (row-major [mpad][mpad], rows = w, columns = w') and of the identity, for kernels
+        # that apply L' on the fp32 FMA pipes (experimental msgpack_rot_s2_kernel); keyed by the offset of the (hi | lo) image
+        self.tc_lplain_off = {}
+        for t, m in enumerate(self.irreps_out):
+            ty = types[t]
+            mp = int(ty.mpad)
+            for p in range(ty.path_begin, ty.path_end):
+                pa = plist[p]
+                if pa.kind != 0:
+                    continue
+                b = pa.branch
+                f0, rows, Mt = self.f_slices[(b, t)]
+                tpaths = [q for q in self.paths_by_branch[b] if q.ir_out == m.ir]
+                ch_type0 = tpaths[0].ch_off if tpaths else 0
+                M = int(ty.mul)
+                wcur = (wcur + 3) // 4 * 4
+                ww, wo = np.meshgrid(np.arange(M), np.arange(Mt), indexing="ij")
+                add(wcur + ww * mp + wo, base[("F", b)] + f0 + (pa.pad0 - ch_type0 + ww) * Mt + wo, 1.0, 2)
+                self.tc_lplain_off[int(pa.lf_off)] = wcur
+                wcur += mp * mp
+        for mp, off in self.tc_ident_off.items():
+            wcur = (wcur + 3) // 4 * 4
+            kk = np.arange(mp)
+            add(wcur + kk * mp + kk, np.full(mp, self.src_total, dtype=np.int64), 1.0, 2)
+            self.tc_lplain_off[int(off)] = wcur
+            wcur += mp * mp
+        self.tc_w_total = wcur
         self._tc_dst = np.concatenate(dst)
         self._tc_src = np.concatenate(src)
         self._tc_scale = np.concatenate(scale)
@@ -722,11 +749,11 @@ class MessagePackOp:
                         col = w[:, pa.l2, l3 + m3]
                         assert int((col != 0).sum()) == 1
                         group.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, pa.w_off, pa.lf_off, pa.pad0, c, blk.kpad, 0,
-                                                pa.branch, l3 + m3, 1, 0, 0))
+                                                pa.branch, l3 + m3, 1, 0, self.tc_lplain_off[int(pa.lf_off)]))
                     else:
                         assert l1 == l3
                         group.append(L.RotStepT(blk.xoff + (l1 + m3) * per_m, pa.lf_off, self.tc_ident_off[int(ty.mpad)], 0, 1.0,
-                                                blk.kpad, 0, -1, l3 + m3, 1, 0, 0))
+                                                blk.kpad, 0, -1, l3 + m3, 1, 0, self.tc_lplain_off[int(self.tc_ident_off[int(ty.mpad)])]))
                 if group:
                     group[-1].new_path |= 4
                 steps.extend(group)

@@ -258,6 +258,16 @@ def test_rotated_frame_tables_are_well_formed():
     st = op.pack_tc(w)
     for mp, off in op.tc_ident_off.items():
         assert torch.equal(EM._decode_image(st["tc_wbuf"], off, mp, mp), torch.eye(mp))
+    # the un-split fp32 copy of every step's L' agrees with its (hi | lo) image
+    wb = st["tc_wbuf"]
+    for t in range(len(op.irreps_out)):
+        mp = int(op.tc_types_c[t].mpad)
+        for i in range(op.rot_step_begin[t], op.rot_step_begin[t + 1], 7):
+            s_ = op.rot_steps_c[i]
+            assert s_.pad2 % 4 == 0 and s_.pad2 + mp * mp <= op.tc_w_total
+            plain = wb[s_.pad2:s_.pad2 + mp * mp].view(mp, mp)
+            img = EM._decode_image(wb, s_.lf_off, mp, mp)
+            assert float((plain - img).abs().max()) <= 3e-7 * float(plain.abs().max()) + 1e-30
 
 
 def test_radial_gate_tiles_match_oracle(small):
