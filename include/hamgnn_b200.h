@@ -168,12 +168,15 @@ typedef struct {
   int32_t g_off;        /* first gate column of the path                                              */
   float scale;          /* w3j(l1,l2,l3)[m1, 0, m3] * sqrt(2 l2 + 1)                                  */
   int16_t kpad;
-  int8_t kind;          /* 0: gated CG step, 1: direct (un-gated Linear of the edge features)         */
-  int8_t branch;
+  int8_t kind;          /* 0 (every step runs GEMM1 -> gate -> GEMM2)                                 */
+  int8_t branch;        /* radial-MLP branch of the gate; -1: un-gated (direct Linear of the edge features:
+                           w_off = its images, lf_off = an identity image)                              */
   int8_t m3;            /* output component index l3 + m3                                             */
-  int8_t new_path;      /* bit 0: first step of its path, bit 1: last step of its path                */
+  int8_t new_path;      /* flags: bit 0 = the L' image is to be loaded (set on every step), bit 2 = last step of its
+                           output-component (m3) group; steps of a slot are ordered by m3                 */
   int16_t pad;
-  int32_t pad2;
+  int32_t pad2;         /* plan->wbuf offset of the un-split fp32 copy of L'_p, row-major [mpad][mpad]
+                           (read only by the experimental msgpack_rot_s2_kernel)                       */
 } hgb_rot_step_t;
 
 typedef struct {
