@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(HT) ham_finalize_so3_kernel(const __grid_const
 }  // namespace
 
 extern "C" int hgb_ham_assemble(const hgb_ham_plan* plan, const float* coef, int64_t n_rows, float* raw, void* stream) {
+  HGB_DEVICE_GUARD(raw);
   HGB_CHECK_ARG(plan && coef && raw, "hgb_ham_assemble: NULL argument");
   HGB_CHECK_ARG(plan->nao > 0 && plan->nao <= 64 && plan->n_coef > 0, "hgb_ham_assemble: bad plan (nao=%d)", plan->nao);
   if (n_rows == 0) return 0;
@@ -221,6 +222,7 @@ extern "C" int hgb_ham_assemble(const hgb_ham_plan* plan, const float* coef, int
 
 extern "C" int hgb_csr_rows(const int32_t* row_ptr, const int32_t* col, const float* val, int32_t n_out, int32_t n_in,
                             const float* x, int64_t n_rows, float* y, void* stream) {
+  HGB_DEVICE_GUARD(y);
   HGB_CHECK_ARG(row_ptr && col && val && x && y, "hgb_csr_rows: NULL argument");
   HGB_CHECK_ARG(n_out > 0 && n_in > 0 && n_rows >= 0, "hgb_csr_rows: bad sizes (n_out=%d, n_in=%d)", n_out, n_in);
   const size_t smem = (size_t)HROWS * n_in * sizeof(float);
@@ -237,6 +239,7 @@ extern "C" int hgb_csr_rows(const int32_t* row_ptr, const int32_t* col, const fl
 extern "C" int hgb_ham_finalize(const hgb_ham_plan* plan, const float* raw, const int64_t* partner, const float* h0,
                                 const int64_t* z, const int64_t* node_a, const int64_t* node_b, const int64_t* out_row,
                                 int64_t n_rows, int32_t symmetrize, float* out, void* stream) {
+  HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && raw && z && out, "hgb_ham_finalize: NULL argument");
   HGB_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hgb_ham_finalize: bad row count");
   if (n_rows == 0) return 0;
@@ -252,6 +255,7 @@ extern "C" int hgb_ham_finalize_su2(int32_t nao, const uint8_t* orb_mask, const 
                                     const float* h0_re, const float* h0_im, const int64_t* z, const int64_t* node_a,
                                     const int64_t* node_b, const int64_t* out_row, int64_t n_rows, int32_t symmetrize,
                                     float* out_re, float* out_im, void* stream) {
+  HGB_DEVICE_GUARD(out_re);
   HGB_CHECK_ARG(orb_mask && raw && z && out_re && out_im, "hgb_ham_finalize_su2: NULL argument");
   HGB_CHECK_ARG(nao > 0 && nao <= 64, "hgb_ham_finalize_su2: bad nao %d", nao);
   HGB_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hgb_ham_finalize_su2: bad row count");
@@ -267,6 +271,7 @@ extern "C" int hgb_ham_finalize_su2(int32_t nao, const uint8_t* orb_mask, const 
 
 extern "C" int hgb_ksi_shell_average(int32_t nao, const int32_t* blk_lo_host, const int32_t* blk_hi_host, int32_t n_blocks,
                                      float* ksi, int64_t n_rows, void* stream) {
+  HGB_DEVICE_GUARD(ksi);
   HGB_CHECK_ARG(ksi && (n_blocks == 0 || (blk_lo_host && blk_hi_host)), "hgb_ksi_shell_average: NULL argument");
   HGB_CHECK_ARG(nao > 0 && nao <= 64 && n_blocks >= 0 && n_blocks <= 8, "hgb_ksi_shell_average: bad sizes");
   if (n_rows == 0 || n_blocks == 0) return 0;
@@ -286,6 +291,7 @@ extern "C" int hgb_ham_finalize_so3(int32_t nao, const float* hns, const float* 
                                     const int64_t* partner, const float* h0_re, const float* h0_im,
                                     const int64_t* out_row, int64_t n_rows, int32_t symmetrize, int32_t h0_offdiag_only,
                                     float* out_re, float* out_im, void* stream) {
+  HGB_DEVICE_GUARD(out_re);
   HGB_CHECK_ARG(hns && ksi && lmat && out_re && out_im, "hgb_ham_finalize_so3: NULL argument");
   HGB_CHECK_ARG(nao > 0 && nao <= 64, "hgb_ham_finalize_so3: bad nao %d", nao);
   HGB_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hgb_ham_finalize_so3: bad row count");

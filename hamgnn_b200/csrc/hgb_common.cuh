@@ -12,6 +12,27 @@ namespace hgb {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Kernels must launch on the device that owns the buffers, whatever the caller's current device is (a model moved to
+// cuda:1 without cudaSetDevice(1)): switch to the device of `p` for the duration of the entry point.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes at;
+    if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+      if (cudaGetDevice(&prev) == cudaSuccess && prev != at.device) switched = (cudaSetDevice(at.device) == cudaSuccess);
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define HGB_DEVICE_GUARD(ptr) hgb::DeviceGuard _hgb_device_guard(ptr)
+
 #define HGB_CHECK_ARG(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \

@@ -367,6 +367,7 @@ int launch(const MsgArgs& a, cudaStream_t st) {
 extern "C" int hgb_msgpack_forward(const hgb_msgpack_plan* plan, const float* const* src,
                                    const int64_t* const* src_rows, const float* sh, const float* rbf,
                                    int64_t n_edges, float* out, const int64_t* out_index, void* stream) {
+  HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && src && sh && rbf && out, "hgb_msgpack_forward: NULL argument");
   HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4, "hgb_msgpack_forward: n_sources=%d", plan->n_sources);
   HGB_CHECK_ARG(plan->n_branches >= 1 && plan->n_branches <= 2, "hgb_msgpack_forward: n_branches=%d", plan->n_branches);

@@ -516,6 +516,7 @@ int launch_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int
 // The radial gate alone (for tests and for callers that keep g): g_ws[b][e][c], c < nch[b], row stride gstride.
 extern "C" int hgb_radial_gate(const hgb_msgpack_plan* plan, const float* rbf, const int32_t* w3_off, const int32_t* nch,
                                const int32_t* w3img_off, int32_t gstride, float* g_ws, int64_t n_edges, void* stream) {
+  HGB_DEVICE_GUARD(g_ws);
   HGB_CHECK_ARG(plan && rbf && g_ws && w3_off && nch, "hgb_radial_gate: NULL argument");
   HGB_CHECK_ARG(plan->n_branches >= 1 && plan->n_branches <= 2, "hgb_radial_gate: bad branch count");
   HGB_CHECK_ARG(plan->h2 <= 64 && plan->h1 <= 64 && plan->rbf_dim <= 64,
@@ -541,6 +542,7 @@ extern "C" int hgb_msgpack_tcg_forward_v2(const hgb_msgpack_plan* plan, const fl
                                           const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off,
                                           int32_t gstride, float* g_ws, int64_t n_edges, float* out,
                                           const int64_t* out_index, void* stream) {
+  HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && src && sh && rbf && out && g_ws && w3_off && nch, "hgb_msgpack_tcg_forward: NULL argument");
   HGB_CHECK_ARG(plan->types_host && plan->paths_host, "hgb_msgpack_tcg_forward: host copies of the type/path tables are required");
   HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
@@ -658,6 +660,7 @@ extern "C" int hgb_msgpack_tcg_forward_v2(const hgb_msgpack_plan* plan, const fl
 // ---------------------------------------------------------------------------------------------------------
 // Rotated-frame path (msgpack_rot_kernel.cuh)
 extern "C" int hgb_wigner(const hgb_rot_plan* rp, const float* edge_vec, int64_t n_edges, float* dw, void* stream) {
+  HGB_DEVICE_GUARD(dw);
   HGB_CHECK_ARG(rp && edge_vec && dw && rp->wigner_j, "hgb_wigner: NULL argument");
   HGB_CHECK_ARG(rp->lmax >= 0 && rp->lmax <= rot::LMAX, "hgb_wigner: lmax %d unsupported (<= %d)", rp->lmax, rot::LMAX);
   HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_wigner: bad edge count");
@@ -691,6 +694,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
                                        const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off, int32_t gstride,
                                        float* g_ws, float* xp_ws, int64_t chunk_edges, int64_t n_edges, float* out,
                                        const int64_t* out_index, void* stream) {
+  HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && rp && src && dw && rbf && out && g_ws && xp_ws && w3_off && nch, "hgb_msgpack_rot_forward: NULL argument");
   HGB_CHECK_ARG(plan->types_host && plan->paths_host && rp->blocks_host && rp->steps_host && rp->blocks && rp->steps,
                 "hgb_msgpack_rot_forward: host and device copies of the tables are required");

@@ -184,6 +184,7 @@ extern "C" int hgb_linear_forward(const hgb_linear_plan* plan, const float* x, c
 
 extern "C" int hgb_linear_forward_ld(const hgb_linear_plan* plan, const float* x, const int64_t* rows, int64_t n_rows,
                                      float* y, int64_t ldy, int32_t accumulate, void* stream) {
+  HGB_DEVICE_GUARD(y);
   HGB_CHECK_ARG(plan && x && y, "hgb_linear_forward: NULL argument");
   HGB_CHECK_ARG(n_rows >= 0, "hgb_linear_forward: negative row count");
   HGB_CHECK_ARG(ldy >= plan->out_dim, "hgb_linear_forward: output row stride %lld < out_dim %d", (long long)ldy, plan->out_dim);
@@ -201,6 +202,7 @@ extern "C" int hgb_linear_forward_ld(const hgb_linear_plan* plan, const float* x
 extern "C" int hgb_resblock_forward(const hgb_linear_plan* lin1, const hgb_gate_desc* gate, const hgb_linear_plan* lin2,
                                     const hgb_linear_plan* post, const float* x, const float* extra, int64_t n_rows,
                                     float* y, void* stream) {
+  HGB_DEVICE_GUARD(y);
   HGB_CHECK_ARG(lin1 && gate && lin2 && x && y, "hgb_resblock_forward: NULL argument");
   HGB_CHECK_ARG(lin1->out_dim == gate->in_dim && lin2->in_dim == gate->out_dim && lin2->out_dim == lin1->in_dim,
                 "hgb_resblock_forward: inconsistent dims lin1 %d->%d gate %d->%d lin2 %d->%d", lin1->in_dim, lin1->out_dim,

@@ -132,6 +132,7 @@ int launch(const float* A, const float* B, float* C, int tiles, int K, int N, in
 // C[t] (128 x N) = A[t] (128 x K) . B (K x N) for t < tiles.  K % 8 == 0, N <= 64.
 extern "C" int hgb_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t tiles, int32_t K, int32_t N,
                                     int32_t a_from_tmem, void* stream) {
+  HGB_DEVICE_GUARD(C);
   HGB_CHECK_ARG(A && B && C, "hgb_tc_gemm_selftest: NULL argument");
   HGB_CHECK_ARG(K > 0 && K % 8 == 0, "hgb_tc_gemm_selftest: K=%d must be a positive multiple of 8", K);
   HGB_CHECK_ARG(N > 0 && N <= 64, "hgb_tc_gemm_selftest: N=%d out of range (1..64)", N);

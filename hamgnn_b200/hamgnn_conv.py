@@ -39,6 +39,34 @@ class AttrDict(dict):
         self[k] = v
 
 
+# e3nn 0.5.0 modules carry constant buffers / FX sub-modules in their state_dict; the kernels
+# rebuild those constants on the host, so a reference checkpoint may contain them and the product ignores them.
+_E3NN_CONSTANT_KEYS = (r"\.output_mask$", r"\._compiled_main", r"\._w3j_", r"\.bias$", r"\.cg_\d+_\d+_\d+$", r"\._profiling_str$",
+                       r"\.sph\.", r"\._lmax$", r"\.mask$")
+
+
+def load_reference_state_dict(module: nn.Module, state_dict: dict) -> None:
+    """Strict load of a reference checkpoint's (sub-)state_dict into `module`: every parameter / buffer of the product
+    must be present with the same shape, and every extra key must be one of e3nn's constant buffers -- anything else
+    (a renamed or missing weight) raises instead of being dropped silently as `strict=False` would."""
+    import re
+    own = module.state_dict()
+    missing = [k for k in own if k not in state_dict]
+    extra = [k for k in state_dict if k not in own]
+    unknown = [k for k in extra if not any(re.search(p, k) for p in _E3NN_CONSTANT_KEYS)]
+    bad_shape = [k for k in own if k in state_dict and tuple(state_dict[k].shape) != tuple(own[k].shape)]
+    bias = [k for k in extra if k.endswith(".bias") and state_dict[k].numel() != 0]
+    if missing or unknown or bad_shape or bias:
+        raise RuntimeError(f"reference state_dict does not match: missing {missing[:5]} unexpected {unknown[:5]} "
+                           f"shape mismatch {bad_shape[:5]} non-empty bias {bias[:5]}")
+    module.load_state_dict({k: state_dict[k] for k in own}, strict=True)
+
+
+def _invalidate_hook(module, incompatible_keys):
+    from .plan import invalidate_weight_caches
+    invalidate_weight_caches()
+
+
 def _get(cfg, key, default=None):
     if isinstance(cfg, dict):
         return cfg.get(key, default)
@@ -308,6 +336,7 @@ class HamGNNConvE3(nn.Module):
             self.pair_interactions.append(PairInteractionBlock(D, self.irreps_edge_sh, self.num_radial, self.radial_MLP,
                                                                use_skip_connections=skip,
                                                                legacy_edge_update=self.legacy_edge_update))
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     @property
     def num_params(self):
@@ -343,8 +372,12 @@ class HamGNNConvE3(nn.Module):
             raise NotImplementedError("the B200 path computes in fp32 (reference default precision: 32)")
         z = data["z"]
         L.require_cuda(z)
-        if int(z.max()) >= self.num_types or int(z.min()) < 0:
-            raise IndexError("atomic number outside [0, num_types)")
+        zkey = (z.data_ptr(), z._version, z.numel())
+        if getattr(self, "_z_checked", None) != zkey:      # one host sync per distinct z tensor, not per forward
+            lo, hi = torch.aminmax(z)
+            if int(hi) >= self.num_types or int(lo) < 0:
+                raise IndexError("atomic number outside [0, num_types)")
+            self._z_checked = zkey
         onehot = torch.nn.functional.one_hot(z, num_classes=self.num_types).to(torch.float32)
         data["node_attrs"] = onehot
         data["node_features"] = onehot

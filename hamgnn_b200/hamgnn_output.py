@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from . import lib as L
-from .hamgnn_conv import ResidualBlock, _W
+from .hamgnn_conv import ResidualBlock, _W, _invalidate_hook
 from .irreps import Irreps
 from .plan import HamAssembly, LinearOp, SocSU2Assembly, SortedHeadOp
 
@@ -124,6 +124,7 @@ class HamGNNPlusPlusOut(nn.Module):
         self.soc_switch, self.spin_constrained, self.collinear_spin = soc_switch, spin_constrained, collinear_spin
         self.zero_point_shift, self.calculate_sparsity = zero_point_shift, calculate_sparsity
         self.calculate_band_energy = calculate_band_energy
+        self.get_nonzero_mask_tensor = get_nonzero_mask_tensor
         if self.ham_type != "openmx":
             if self.ham_type in ("siesta", "abacus", "pasp"):
                 raise NotImplementedError(f"ham_type '{ham_type}' basis tables are not part of this round's hot path")
@@ -132,7 +133,6 @@ class HamGNNPlusPlusOut(nn.Module):
         for flag, name in ((spin_constrained, "spin_constrained"), (collinear_spin, "collinear_spin"),
                            (calculate_band_energy, "calculate_band_energy"), (return_forces, "return_forces"),
                            (nonlinearity_type != "gate", "nonlinearity_type!='gate'"),
-                           (get_nonzero_mask_tensor, "get_nonzero_mask_tensor"),
                            (export_reciprocal_values, "export_reciprocal_values")):
             if flag:
                 raise NotImplementedError(f"HamGNN_out option {name} is outside the B200 hot path of this round "
@@ -171,6 +171,7 @@ class HamGNNPlusPlusOut(nn.Module):
             self.onsite_overlap_network = HamLayer(Irreps(irreps_in_node), self.hamiltonian_irreps)
             self.offsite_overlap_network = HamLayer(Irreps(irreps_in_edge), self.hamiltonian_irreps)
         self._tables: Dict[str, tuple] = {}
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     # ---------------------------------------------------------------------------------------------
     def _lookup(self, device):
@@ -185,10 +186,15 @@ class HamGNNPlusPlusOut(nn.Module):
         return self._tables[key]
 
     def validate_elements_in_basis_def(self, data):
-        zs = data["z"].unique().cpu().tolist()
+        z = data["z"]
+        zkey = (z.data_ptr(), z._version, z.numel())
+        if getattr(self, "_z_checked", None) == zkey:       # one host sync per distinct z tensor, not per forward
+            return True
+        zs = z.unique().cpu().tolist()
         missing = [z for z in zs if z not in self.basis_def]
         if missing:
             raise ValueError("The following elements are missing from basis_def: " + ", ".join(f"Z={m}" for m in missing))
+        self._z_checked = zkey
         return True
 
     def calculate_sparsity_ratio(self, data):
@@ -212,6 +218,47 @@ class HamGNNPlusPlusOut(nn.Module):
             eff = eff + torch.where(both, n_orb[z[src]] * n_orb[z[dst]], torch.full_like(src, nn2)).sum()
         t, e = total.double(), eff.double()
         return torch.where(e > 0, t / e, torch.full_like(t, float("inf"))).float()
+
+    # ---- get_nonzero_mask_tensor (hamgnn_output.py:2588-2782): element-wise table look-ups, no arithmetic
+    def create_orbital_validity_mask(self, atomic_numbers):
+        """[99, nao_max] 0/1 table in the dtype of `atomic_numbers` (hamgnn_output.py:2588-2613), cached per device."""
+        key = ("orbmask", str(atomic_numbers.device))
+        if key not in self._tables:
+            m = torch.zeros(99, self.nao_max, dtype=torch.long)
+            for Z, orbs in self.basis_def.items():
+                m[Z, list(orbs)] = 1
+            self._tables[key] = m.to(atomic_numbers.device)
+        return self._tables[key].type_as(atomic_numbers)
+
+    def _pair_masks(self, data):
+        src, dst = data["edge_index"][0], data["edge_index"][1]
+        z = data["z"]
+        m = self.create_orbital_validity_mask(z)
+        on = m[z][:, :, None] * m[z][:, None, :]
+        off = m[z[src]][:, :, None] * m[z[dst]][:, None, :]
+        return on, off
+
+    def build_interaction_masks(self, data):
+        """[N + E, nao^2] bool, on-site rows first (plain cat, NOT the per-crystal interleave: hamgnn_output.py:2615-2665)."""
+        on, off = self._pair_masks(data)
+        nn2 = self.nao_max ** 2
+        return torch.cat((on.bool().reshape(-1, nn2), off.bool().reshape(-1, nn2)), dim=0)
+
+    def build_column_wise_interaction_masks(self, data):
+        """[N + E, 2, nao^2] bool (hamgnn_output.py:2667-2719)."""
+        m = self.build_interaction_masks(data)
+        return torch.stack([m, m], dim=1)
+
+    def build_spin_orbit_interaction_masks(self, data):
+        """([N + E, (2 nao)^2], [2 (N + E), (2 nao)^2]) bool, per-crystal interleaved rows (hamgnn_output.py:2721-2782)."""
+        on, off = self._pair_masks(data)
+        M = 2 * self.nao_max
+
+        def spin(x):   # blockwise_2x2_concat(x, x, x, x)
+            return x.repeat(1, 2, 2).reshape(-1, M * M).bool()
+
+        real_imag = self.concatenate_hamiltonians_by_crystal(data, spin(on), spin(off))
+        return real_imag, torch.cat((real_imag, real_imag), dim=0)
 
     def _row_maps(self, data):
         """Row of every on-site / off-site block in the per-crystal interleaved output
@@ -288,6 +335,8 @@ class HamGNNPlusPlusOut(nn.Module):
                 shift = ((H - data["hamiltonian"]) * sel).sum() / (S * sel).sum()
                 H = H - shift * S
             result = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+            if self.get_nonzero_mask_tensor:
+                result["mask"] = self.build_interaction_masks(data)
         if overlap is not None:
             result["overlap"] = overlap
         if self.calculate_sparsity:
@@ -354,5 +403,8 @@ class HamGNNPlusPlusOut(nn.Module):
             shift = (diff * sel).sum() / (2.0 * (S * sel).sum())
             Hr[:, 0, :, 0, :] -= shift * S
             Hr[:, 1, :, 1, :] -= shift * S
-        return {"hamiltonian": H, "hamiltonian_real": H_re, "hamiltonian_imag": H_im, "band_energy": None,
-                "wavefunction": None}
+        result = {"hamiltonian": H, "hamiltonian_real": H_re, "hamiltonian_imag": H_im, "band_energy": None,
+                  "wavefunction": None}
+        if self.get_nonzero_mask_tensor:
+            result["mask_real_imag"] = self.build_spin_orbit_interaction_masks(data)[0]
+        return result

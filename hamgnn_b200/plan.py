@@ -90,6 +90,22 @@ def linear_blocks(irreps_in: Irreps, irreps_out: Irreps) -> Tuple[List[LinBlock]
     return blocks, w
 
 
+# Packed / folded / TF32-split copies of the parameters are cached per (parameter version, storage pointer, CACHE_EPOCH).
+# In-place edits through `.data` (EMA / SWA swaps, manual surgery) do not bump `Parameter._version`: call
+# `invalidate_weight_caches()` after such edits.  `load_state_dict` does it through a post-hook on the two top modules.
+CACHE_EPOCH = 0
+
+
+def invalidate_weight_caches() -> None:
+    """Force every LinearOp / MessagePackOp / SortedHeadOp to re-pack its weights on the next call."""
+    global CACHE_EPOCH
+    CACHE_EPOCH += 1
+
+
+def _wkey(*params) -> tuple:
+    return (CACHE_EPOCH,) + tuple((p._version, p.data_ptr()) for p in params)
+
+
 class DeviceTables:
     """Keeps ctypes structs, their host arrays and the device tensors they point to alive together."""
 
@@ -126,17 +142,22 @@ class LinearOp:
             raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
             d_blocks = torch.from_numpy(raw).to(dev)
             scale = torch.from_numpy(self._scale_np).to(dev)
-            ent = {"blocks": d_blocks, "scale": scale, "ver": None, "w": None, "plan": None}
+            ent = {"blocks": d_blocks, "scale": scale, "per_weight": {}}
             self._dev[key] = ent
-        ver = (weight._version, weight.data_ptr())
-        if ent["ver"] != ver:
-            ent["w"] = (weight.detach() * ent["scale"]).contiguous()
-            ent["ver"] = ver
+        # one entry per parameter storage: an op shared by several weights (linear_up_src / linear_up_tar) must not thrash
+        pw = ent["per_weight"]
+        slot = pw.get(weight.data_ptr())
+        ver = _wkey(weight)
+        if slot is None or slot["ver"] != ver:
+            if slot is None and len(pw) >= 8:
+                pw.clear()
+            w = (weight.detach() * ent["scale"]).contiguous()
             outs = [b.i_out for b in self.blocks]
             disjoint = 1 if len(set(outs)) == len(outs) else 0   # bit 0 of `pad`: every block owns its output slot
-            ent["plan"] = L.LinearPlan(len(self.blocks), self.irreps_in.dim, self.irreps_out.dim, disjoint,
-                                       ent["blocks"].data_ptr(), ent["w"].data_ptr())
-        return ent["plan"]
+            slot = {"ver": ver, "w": w, "plan": L.LinearPlan(len(self.blocks), self.irreps_in.dim, self.irreps_out.dim, disjoint,
+                                                            ent["blocks"].data_ptr(), w.data_ptr())}
+            pw[weight.data_ptr()] = slot
+        return slot["plan"]
 
 
 def linear_forward(op: LinearOp, weight: torch.Tensor, x: torch.Tensor, rows: Optional[torch.Tensor] = None,
@@ -500,7 +521,7 @@ class MessagePackOp:
                 *[w for w in weights["lin_out"] if w is not None]]
         if weights.get("direct") is not None:
             allp.append(weights["direct"])
-        ver = tuple((p._version, p.data_ptr()) for p in allp)
+        ver = _wkey(*allp)
         if st["ver"] != ver:
             with torch.no_grad():
                 parts = []
@@ -809,7 +830,7 @@ class MessagePackOp:
                 *[w for w in weights["lin_out"] if w is not None]]
         if weights.get("direct") is not None:
             allp.append(weights["direct"])
-        ver = tuple((p._version, p.data_ptr()) for p in allp)
+        ver = _wkey(*allp)
         if st.get("tc_ver") != ver:
             if "tc_dst" not in st:
                 st["tc_types"] = torch.from_numpy(np.frombuffer(bytes(self.tc_types_c), dtype=np.uint8).copy()).to(dev)
@@ -1066,7 +1087,7 @@ class SortedHeadOp:
         x = L.f32c(x)
         key = str(weight.device)
         ent = self._dev.setdefault(key, {"ver": None})
-        ver = (weight._version, weight.data_ptr())
+        ver = _wkey(weight)
         if ent["ver"] != ver:
             if "gather" not in ent:
                 ent["gather"] = [torch.from_numpy(g).to(weight.device) for _, _, g in self.chunks]
