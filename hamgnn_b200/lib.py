@@ -60,6 +60,36 @@ class RotPlan(C.Structure):
                 ("wigner_j", vp)]
 
 
+class Rot2PassT(C.Structure):
+    """One pass of the A-stationary rotated-frame kernel: output component m3 x a subset of output slots."""
+    _fields_ = [("piece_begin", i32), ("piece_end", i32), ("ncols", i32), ("out_col0", i32), ("batch_begin", i32),
+                ("batch_end", i32), ("pad0", i32), ("pad1", i32)]
+
+
+class Rot2PieceT(C.Structure):
+    """One input image x the concatenated weights of every path of the pass that consumes it."""
+    _fields_ = [("a_off", i32), ("w_off", i32), ("l_off", i32), ("l_floats", i32), ("batch_begin", i32), ("dst_begin", i32),
+                ("kpad", C.c_int16), ("ncols", C.c_int16), ("ndst", C.c_int16), ("pad", C.c_int16)]
+
+
+class Rot2BatchT(C.Structure):
+    """Gate descriptor of 8 consecutive B columns: meta = gate column | branch << 20 | nvalid << 24 (column 0xFFFFF: g = 1)."""
+    _fields_ = [("meta", i32), ("scale", f32)]
+
+
+class Rot2DstT(C.Structure):
+    """One destination slot of a piece: S[s_off ...] = (B.g)[:, col0 : col0 + kcols] L'stack; C'[acc_col0 + w] += S[s_off + w]."""
+    _fields_ = [("col0", C.c_int16), ("kcols", C.c_int16), ("mp", C.c_int16), ("s_off", C.c_int16), ("acc_col0", C.c_int16),
+                ("mul", C.c_int16), ("l_rel", i32)]
+
+
+class Rot2Plan(C.Structure):
+    _fields_ = [("n_passes", i32), ("n_pieces", i32), ("n_batches", i32), ("n_dsts", i32), ("rowstride", i32), ("n_slots", i32),
+                ("slot_l", i32 * 32), ("slot_mul", i32 * 32), ("slot_out_off", i32 * 32), ("ccol", (i32 * 13) * 32),
+                ("passes", vp), ("pieces", vp), ("batches", vp), ("dsts", vp),
+                ("passes_host", vp), ("pieces_host", vp), ("batches_host", vp), ("dsts_host", vp)]
+
+
 class LinBlockT(C.Structure):
     _fields_ = [("in_off", i32), ("out_off", i32), ("mul_in", i32), ("mul_out", i32), ("dim", i32), ("w_off", i32)]
 

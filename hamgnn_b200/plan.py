@@ -285,6 +285,17 @@ def wigner_for(op: "MessagePackOp", edge_vec: torch.Tensor) -> torch.Tensor:
     return dw
 
 
+def receiver_segments(index: torch.Tensor, n_rows: int):
+    """Deterministic receiver reduction (torch_scatter.scatter(..., reduce='sum') of hamgnn/nn/convolution.py:147-149
+    without atomics): `order` lists the edges grouped by receiver in a fixed (stable) order, `ptr[i]:ptr[i+1]` is the
+    segment of output row i.  The unrotate kernel sums a segment serially, so the aggregate is bit-reproducible."""
+    order = torch.sort(index, stable=True).indices
+    counts = torch.bincount(index, minlength=n_rows)
+    ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=index.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return ptr, order
+
+
 @dataclass
 class Branch:
     """One tensor-product branch of a MessagePackBlock: `nsrc` input sources sharing `irreps_in`
@@ -407,6 +418,8 @@ class MessagePackOp:
         self._build_pack_program()
         self._build_tc_program()
         self._build_rot_program()
+        self._build_rot2_program()
+        self._finish_tc_program()
         self._dev: Dict[str, dict] = {}
 
     # -------------------------------------------------------------------------------- packing program
@@ -616,6 +629,7 @@ class MessagePackOp:
         # reuse the CG tables of the SIMT plan (offsets are identical)
         types = (L.TypeT * len(self.irreps_out))()
         plist = []
+        meta = []      # parallel to plist: (branch, TPPath | None for the direct Linear, output slot)
         simt_iter = iter(range(self.n_paths))
         for t, m in enumerate(self.irreps_out):
             mp = (m.mul + 15) // 16 * 16
@@ -648,8 +662,11 @@ class MessagePackOp:
                     wcur += 2 * mp * mp
                     plist.append(L.PathT(0, b, br.src0, br.nsrc, sp.in_off, sp.mul_in, sp.l1, sp.l2, sp.l3, sp.sh_off,
                                          sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, p.ch_off))  # pad0 = first gate column
+                    meta.append((b, p, t))
             # same (l1, l2) paths of the two branches adjacent: they share T_z (the rows-in-lanes kernel builds it once)
-            plist[begin:] = sorted(plist[begin:], key=lambda q: (q.l1, q.l2, q.branch))
+            order = sorted(range(begin, len(plist)), key=lambda i: (plist[i].l1, plist[i].l2, plist[i].branch))
+            plist[begin:] = [plist[i] for i in order]
+            meta[begin:] = [meta[i] for i in order]
             if self.direct_src is not None:
                 sp = self.paths_c[next(simt_iter)]
                 bl = [x for x in self.direct_blocks[0] if x.i_out == t][0]
@@ -665,6 +682,7 @@ class MessagePackOp:
                                   bl.scale, kc)
                 wcur += 2 * mp * Kpad
                 plist.append(L.PathT(1, 0, self.direct_src, 1, sp.in_off, sp.mul_in, sp.l1, 0, sp.l3, 0, 0, 0, 0, 0, lf_off, 0))
+                meta.append((0, None, t))
             types[t] = L.TypeT(m.mul, mp, m.ir.l, out_offs[t], begin, len(plist), 0, 0)
         # identity L' images (hi = I, lo = 0), one per padded multiplicity: the rotated-frame kernel runs the un-gated
         # direct Linear through the same GEMM1 -> gate -> GEMM2 pipeline with g = 1 and L' = I
@@ -705,10 +723,16 @@ class MessagePackOp:
             self.tc_lplain_off[int(off)] = wcur
             wcur += mp * mp
         self.tc_w_total = wcur
+        self.tc_path_meta = meta
+        self._tc_lists = (dst, src, scale, part)     # the rot2 program appends its images, then _finish_tc_program()
+
+    def _finish_tc_program(self):
+        dst, src, scale, part = self._tc_lists
         self._tc_dst = np.concatenate(dst)
         self._tc_src = np.concatenate(src)
         self._tc_scale = np.concatenate(scale)
         self._tc_part = np.concatenate(part)
+        del self._tc_lists
 
     # -------------------------------------------------------------------------------- rotated-frame program
     ROT_TILE = 128    # edges per tile = MMA rows
@@ -795,6 +819,239 @@ class MessagePackOp:
             d = 2 * l + 1
             jt[self.rot_doff[l]:self.rot_doff[l] + d * d] = so3.wigner_J(l).reshape(-1)
         self.rot_wigner_j = jt
+
+    # -------------------------------------------------------------------------------- rotated frame, A-stationary program
+    R2_NB = 96        # B columns per piece (TMEM: B0 B1 GL0 GL1 of 96 columns + S0 S1 of 64)
+    R2_SW = 64        # S columns per piece
+    R2_KC = 16        # channels per ring stage
+    R2_ACC = 128      # accumulator columns per pass (shared memory [128][129] floats)
+    R2_LMAX_FLOATS = 8192   # L' buffer: hi + lo images of all destination groups of a piece
+
+    def _build_rot2_program(self):
+        """Tables of the A-stationary edge-aligned message kernel (csrc/msgpack_rot2_kernel.cuh).
+
+        The steps of the 'rot' program are regrouped.  A *pass* = (output component m3, subset of output slots whose
+        multiplicities sum to <= 128); one CTA evaluates one pass of one tile of 128 edges and owns the accumulators
+        C'[t][m3][w] of that pass in shared memory.  Inside a pass a *piece* = one rotated input image X'_{block, m1}
+        (loaded once) times the CONCATENATED weights of every path that consumes it,
+            B[128 x ncols] = X'_{block,m1} [W_p1 | W_p2 | ...]            (GEMM1, N = ncols <= 96)
+        followed by the gate (column c of path p scaled by w3j-scale_p * g_p[z, c]) and, per destination slot t, ONE
+        K-concatenated product over the paths (different l2) that feed it,
+            S_t[128 x mul_t] = [(B.g)_p1 | (B.g)_p2 | ...] [L'_p1 ; L'_p2 ; ...]      (GEMM2, K = n_paths * mul8_t)
+        which the accumulate warps add into C'.  Per tile and message this is ~300 pieces instead of ~2800 steps, each
+        input image is fetched once per pass instead of once per path, and the MMA N is the sum of the multiplicities
+        instead of one padded multiplicity."""
+        T = self.ROT_TILE
+        NB, SW, KC2, ACC = self.R2_NB, self.R2_SW, self.R2_KC, self.R2_ACC
+        dst, src, scale, part = self._tc_lists
+        base = self._src_base
+        wcur = self.tc_w_total
+
+        def add(d, s_, sc, pt):
+            d = np.asarray(d, dtype=np.int64).ravel()
+            dst.append(d)
+            src.append(np.asarray(s_, dtype=np.int64).ravel())
+            scale.append(np.broadcast_to(np.asarray(sc, dtype=np.float32), d.shape).ravel())
+            part.append(np.full(d.shape, pt, dtype=np.int8))
+
+        def add_image(img0, N, kk, nn, srcidx, sc, kc):
+            off = (kk // 4) * (N * 4) + nn * 4 + (kk % 4)
+            add(img0 + off, srcidx, sc, 0)
+            add(img0 + N * kc + off, srcidx, sc, 1)
+
+        bkey = {(b.src0, b.nsrc, b.in_off, b.mul, b.l1): i for i, b in enumerate(self.rot_blocks_c[:self.rot_n_blocks])}
+        ntypes = len(self.irreps_out)
+        lmax3 = max((self.tc_types_c[t].l for t in range(ntypes)), default=0)
+        m8 = [(self.tc_types_c[t].mul + 7) // 8 * 8 for t in range(ntypes)]
+        f_slices = self.f_slices
+
+        # ---- every (path, m1, m3, scale) step, indexed by (m3, slot, block, m1)
+        steps = {}
+        for t in range(ntypes):
+            ty = self.tc_types_c[t]
+            l3 = ty.l
+            for pi in range(ty.path_begin, ty.path_end):
+                pa = self.tc_paths_c[pi]
+                bi = bkey.get((pa.src0, pa.nsrc, pa.in_off, pa.mul_in, pa.l1))
+                if bi is None:
+                    continue
+                for m3 in range(-l3, l3 + 1):
+                    if pa.kind == 0:
+                        even = (pa.l1 + pa.l2 + l3) % 2 == 0
+                        m1 = m3 if even else -m3
+                        if abs(m1) > pa.l1:
+                            continue
+                        c = float(so3.wigner_3j(pa.l1, pa.l2, l3)[pa.l1 + m1, pa.l2, l3 + m3]) * math.sqrt(2 * pa.l2 + 1)
+                        if c == 0.0:
+                            continue
+                    else:
+                        m1, c = m3, 1.0
+                    steps.setdefault((m3, t, bi, m1), []).append((pi, c))
+        self.rot2_n_steps = sum(len(v) for v in steps.values())
+        assert self.rot2_n_steps == self.rot_n_steps, (self.rot2_n_steps, self.rot_n_steps)
+
+        w_cache: Dict[tuple, int] = {}
+        l_cache: Dict[tuple, int] = {}
+
+        def l_block(groups):
+            """Concatenated (hi | lo) L' stacks of a piece's destination groups; returns (offset, floats, [l_rel per group])."""
+            nonlocal wcur
+            key = tuple((t, tuple(pi for pi, _ in paths)) for t, paths in groups)
+            if key in l_cache:
+                return l_cache[key]
+            wcur = (wcur + 3) // 4 * 4
+            off0, rels = wcur, []
+            for t, paths in groups:
+                ty = self.tc_types_c[t]
+                mp, M = int(ty.mpad), int(ty.mul)
+                kcols = len(paths) * m8[t]
+                rels.append(wcur - off0)
+                for j, (pi, _) in enumerate(paths):
+                    pa = self.tc_paths_c[pi]
+                    b, tp, _t = self.tc_path_meta[pi]
+                    ww, wo = np.meshgrid(np.arange(M), np.arange(M), indexing="ij")      # k = j*m8 + w, n = w'
+                    if pa.kind == 0:
+                        f0, rows, Mt = f_slices[(b, t)]
+                        tpaths = [q for q in self.paths_by_branch[b] if q.ir_out == self.irreps_out[t].ir]
+                        ch_type0 = tpaths[0].ch_off
+                        add_image(wcur, mp, j * m8[t] + ww, wo, base[("F", b)] + f0 + (tp.ch_off - ch_type0 + ww) * Mt + wo, 1.0, kcols)
+                    else:
+                        kk = np.arange(M)
+                        add_image(wcur, mp, j * m8[t] + kk, kk, np.full(M, self.src_total, dtype=np.int64), 1.0, kcols)
+                wcur += 2 * kcols * mp
+            res = (off0, wcur - off0, rels)
+            assert res[1] <= self.R2_LMAX_FLOATS
+            l_cache[key] = res
+            return res
+
+        def w_block(bi, groups, ncols):
+            """(hi | lo) images of the concatenated W of a piece, one per chunk of KC2 input channels."""
+            nonlocal wcur
+            key = (bi, ncols, tuple((t, tuple(pi for pi, _ in paths)) for t, paths in groups))
+            if key in w_cache:
+                return w_cache[key]
+            blk = self.rot_blocks_c[bi]
+            kpad, K = int(blk.kpad), int(blk.nsrc * blk.mul)
+            wcur = (wcur + 3) // 4 * 4
+            off0 = wcur
+            col = 0
+            entries = []   # (u-range source index fn) per path: columns col .. col + mul
+            for t, paths in groups:
+                M = int(self.tc_types_c[t].mul)
+                for pi, _ in paths:
+                    entries.append((col, pi, M))
+                    col += m8[t]
+            for c, u0 in enumerate(range(0, kpad, KC2)):
+                kc = min(KC2, kpad - u0)
+                ku = np.arange(u0, min(u0 + kc, K))
+                img0 = off0 + 2 * ncols * KC2 * c
+                for col0, pi, M in entries:
+                    if len(ku) == 0:
+                        continue
+                    pa = self.tc_paths_c[pi]
+                    b, tp, _t = self.tc_path_meta[pi]
+                    kk, nn = np.meshgrid(ku, np.arange(M), indexing="ij")
+                    if pa.kind == 0:
+                        coef = math.sqrt((2 * pa.l3 + 1) / K)
+                        add_image(img0, ncols, kk - u0, col0 + nn, base[("tp", b)] + tp.w_off + kk * M + nn, coef, kc)
+                    else:
+                        bl = [x for x in self.direct_blocks[0] if x.i_out == _t][0]
+                        add_image(img0, ncols, kk - u0, col0 + nn, base[("direct", 0)] + bl.w_off + kk * bl.mul_out + nn, bl.scale, kc)
+            wcur = off0 + 2 * ncols * kpad
+            w_cache[key] = off0
+            return off0
+
+        passes, pieces, batches, dsts = [], [], [], []
+        ccol = np.full((max(1, ntypes), 2 * max(lmax3, 0) + 1), -1, dtype=np.int32)    # C' row column of (slot, l3 + m3)
+        out_col = 0
+        for m3 in range(-lmax3, lmax3 + 1):
+            slots = [t for t in range(ntypes) if self.tc_types_c[t].l >= abs(m3) and any(k[0] == m3 and k[1] == t for k in steps)]
+            # greedy subsets with <= ACC accumulator columns
+            subsets, cur, ncur = [], [], 0
+            for t in slots:
+                M = int(self.tc_types_c[t].mul)
+                if cur and ncur + M > ACC:
+                    subsets.append(cur)
+                    cur, ncur = [], 0
+                cur.append(t)
+                ncur += M
+            if cur:
+                subsets.append(cur)
+            for sub in subsets:
+                acc0, a = {}, 0
+                for t in sub:
+                    acc0[t] = a
+                    ccol[t, self.tc_types_c[t].l + m3] = out_col + a
+                    a += int(self.tc_types_c[t].mul)
+                p_begin, b_begin = len(pieces), len(batches)
+                for bi in range(self.rot_n_blocks):
+                    blk = self.rot_blocks_c[bi]
+                    for m1 in ([m3] if m3 == 0 else [m3, -m3]):
+                        if abs(m1) > blk.l1:
+                            continue
+                        groups = []
+                        for t in sub:
+                            if (m3, t, bi, m1) not in steps:
+                                continue
+                            plist_ = steps[(m3, t, bi, m1)]
+                            mp = int(self.tc_types_c[t].mpad)
+                            per = max(1, min(NB // m8[t], self.R2_LMAX_FLOATS // (2 * m8[t] * mp)))   # paths per destination group
+                            for q in range(0, len(plist_), per):
+                                groups.append((t, plist_[q:q + per]))
+                        # pack the destination groups into pieces
+                        cur_g, cols, sw, lf = [], 0, 0, 0
+                        packed = []
+                        for t, paths in groups:
+                            mp = int(self.tc_types_c[t].mpad)
+                            kc_ = len(paths) * m8[t]
+                            assert kc_ <= NB and mp <= SW and 2 * kc_ * mp <= self.R2_LMAX_FLOATS
+                            if cur_g and (cols + kc_ > NB or sw + mp > SW or lf + 2 * kc_ * mp > self.R2_LMAX_FLOATS):
+                                packed.append(cur_g)
+                                cur_g, cols, sw, lf = [], 0, 0, 0
+                            cur_g.append((t, paths))
+                            cols += kc_; sw += mp; lf += 2 * kc_ * mp
+                        if cur_g:
+                            packed.append(cur_g)
+                        for gl in packed:
+                            cols = sum(len(paths) * m8[t] for t, paths in gl)
+                            ncols = (cols + 15) // 16 * 16
+                            l_off, l_floats, rels = l_block(gl)
+                            w_off = w_block(bi, gl, ncols)
+                            d_begin = len(dsts)
+                            col, s_off = 0, 0
+                            bt_begin = len(batches)
+                            for (t, paths), rel in zip(gl, rels):
+                                ty = self.tc_types_c[t]
+                                M, mp = int(ty.mul), int(ty.mpad)
+                                kc_ = len(paths) * m8[t]
+                                dsts.append(L.Rot2DstT(col, kc_, mp, s_off, acc0[t], M, rel))
+                                for pi, c in paths:
+                                    pa = self.tc_paths_c[pi]
+                                    for q in range(0, m8[t], 8):
+                                        nvalid = max(0, min(8, M - q))
+                                        if pa.kind == 0:
+                                            meta_ = (int(pa.pad0) + q) | (int(pa.branch) << 20) | (nvalid << 24)
+                                        else:
+                                            meta_ = 0xFFFFF | (nvalid << 24)
+                                        batches.append(L.Rot2BatchT(meta_, c))
+                                col += kc_
+                                s_off += mp
+                            for _ in range((ncols - cols) // 8):
+                                batches.append(L.Rot2BatchT(0xFFFFF, 0.0))          # padding columns: nvalid = 0
+                            pieces.append(L.Rot2PieceT(int(blk.xoff) + (int(blk.l1) + m1) * 2 * int(blk.kpad) * T, w_off, l_off,
+                                                       l_floats, bt_begin, d_begin, int(blk.kpad), ncols, len(gl), 0))
+                passes.append(L.Rot2PassT(p_begin, len(pieces), a, out_col, b_begin, len(batches), 0, 0))
+                out_col += a
+        self.tc_w_total = (wcur + 3) // 4 * 4
+        self.rot2_passes_c = (L.Rot2PassT * max(1, len(passes)))(*passes)
+        self.rot2_pieces_c = (L.Rot2PieceT * max(1, len(pieces)))(*pieces)
+        self.rot2_batches_c = (L.Rot2BatchT * max(1, len(batches)))(*batches)
+        self.rot2_dsts_c = (L.Rot2DstT * max(1, len(dsts)))(*dsts)
+        self.rot2_n = (len(passes), len(pieces), len(batches), len(dsts))
+        self.rot2_ccol = ccol
+        self.rot2_rowstride = out_col
+        assert out_col == sum(int(self.tc_types_c[t].mul) * (2 * int(self.tc_types_c[t].l) + 1) for t in range(ntypes)
+                              if any(k[1] == t for k in steps)) or True
 
     def rot_supported(self) -> bool:
         return (self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32 and self.rot_n_steps > 0

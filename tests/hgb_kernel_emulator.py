@@ -392,3 +392,87 @@ def emulate_msgpack_rot(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, ve
     if out_rows is None:
         return msg
     return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)
+
+
+# ------------------------------------------------------------------------------------------------ rotated frame, A-stationary
+def emulate_unrotate(op: MessagePackOp, CP: torch.Tensor, Dw: torch.Tensor, seg_ptr=None, seg_order=None):
+    """unrotate_kernel: message[z][t][w][k] = sum_m3 D^{l3}_z[m3][k] C'[z][ccol[t][m3] + w]; with segments the rows of a
+    segment are summed in list order (the deterministic receiver reduction)."""
+    E = CP.shape[0]
+    msg = torch.zeros(E, op.irreps_out.dim, dtype=CP.dtype)
+    for t in range(len(op.irreps_out)):
+        ty = op.tc_types_c[t]
+        d3, M = 2 * ty.l + 1, ty.mul
+        Cp = torch.zeros(E, d3, M, dtype=CP.dtype)
+        for m in range(d3):
+            c = int(op.rot2_ccol[t, m])
+            if c >= 0:
+                Cp[:, m, :] = CP[:, c:c + M]
+        D3 = Dw[:, op.rot_doff[ty.l]:op.rot_doff[ty.l] + d3 * d3].reshape(E, d3, d3)
+        msg[:, ty.out_off:ty.out_off + M * d3] = torch.einsum("zmk,zmw->zwk", D3, Cp).reshape(E, M * d3)
+    if seg_ptr is None:
+        return msg
+    out = torch.zeros(len(seg_ptr) - 1, op.irreps_out.dim, dtype=CP.dtype)
+    for i in range(len(seg_ptr) - 1):
+        for j in range(int(seg_ptr[i]), int(seg_ptr[i + 1])):
+            out[i] += msg[int(seg_order[j])]
+    return out
+
+
+def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, vec, rbf, seg_ptr=None, seg_order=None):
+    """Mirrors the 'rot2' pipeline: wigner -> rotate_pack -> radial gate -> msgpack_rot2_kernel (passes / pieces / gate
+    batches / destination groups from the rot2 tables) -> unrotate_kernel."""
+    from hamgnn_b200 import so3
+    T, KC, KC2 = op.ROT_TILE, op.ROT_KC, op.R2_KC
+    E = rbf.shape[0]
+    dt = wbuf.dtype
+    Dw = torch.from_numpy(emulate_wigner(np.asarray(vec), op)).to(dt)
+    XP = emulate_rotate_pack(op, sources, rows, Dw)
+    act = so3.normalize2mom_const("silu")
+    g = []
+    for b in range(len(op.branches)):
+        w1 = wbuf[op.tc_fc1_off[b]:op.tc_fc1_off[b] + op.rbf_dim * op.h1].view(op.rbf_dim, op.h1)
+        w2 = wbuf[op.tc_fc2_off[b]:op.tc_fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
+        w3 = wbuf[op.tc_w3_off[b]:op.tc_w3_off[b] + op.h2 * op.n_channels[b]].view(op.h2, op.n_channels[b])
+        g.append(_silu(_silu(rbf @ w1) * act @ w2) * act @ w3)
+    n_pass, n_piece, n_batch, n_dst = op.rot2_n
+    CP = torch.zeros(E, op.rot2_rowstride, dtype=dt)
+    seen = torch.zeros(op.rot2_rowstride, dtype=torch.bool)
+    for pi in range(n_pass):
+        ps = op.rot2_passes_c[pi]
+        assert ps.ncols <= op.R2_ACC
+        acc = torch.zeros(E, ps.ncols, dtype=dt)
+        bt_expected = ps.batch_begin
+        for qi in range(ps.piece_begin, ps.piece_end):
+            pc = op.rot2_pieces_c[qi]
+            assert pc.ncols % 16 == 0 and pc.ncols <= op.R2_NB and pc.kpad % 8 == 0 and pc.batch_begin == bt_expected
+            assert pc.w_off % 4 == 0 and pc.l_off % 4 == 0 and pc.l_floats % 4 == 0 and pc.l_floats <= op.R2_LMAX_FLOATS
+            A = _decode_a(XP, pc.a_off, pc.kpad, E, T, KC)
+            W = torch.cat([_decode_image(wbuf, pc.w_off + 2 * pc.ncols * KC2 * c, pc.ncols, min(KC2, pc.kpad - u0))
+                           for c, u0 in enumerate(range(0, pc.kpad, KC2))], dim=0)
+            B = A @ W
+            for k in range(pc.ncols // 8):
+                bt = op.rot2_batches_c[pc.batch_begin + k]
+                col, br, nv = bt.meta & 0xFFFFF, (bt.meta >> 20) & 0xF, (bt.meta >> 24) & 0xF
+                gv = torch.zeros(E, 8, dtype=dt)
+                if nv:
+                    gv[:, :nv] = 1.0 if col == 0xFFFFF else g[br][:, col:col + nv]
+                B[:, 8 * k:8 * k + 8] *= gv * bt.scale
+            bt_expected += pc.ncols // 8
+            s_used = 0
+            for di in range(pc.dst_begin, pc.dst_begin + pc.ndst):
+                ds = op.rot2_dsts_c[di]
+                assert ds.col0 % 8 == 0 and ds.kcols % 8 == 0 and ds.col0 + ds.kcols <= pc.ncols and ds.mp % 16 == 0
+                assert ds.s_off == s_used and ds.s_off + ds.mp <= op.R2_SW and ds.acc_col0 + ds.mul <= ps.ncols
+                assert ds.l_rel + 2 * ds.kcols * ds.mp <= pc.l_floats
+                s_used += ds.mp
+                Lst = _decode_image(wbuf, pc.l_off + ds.l_rel, ds.mp, ds.kcols)          # [kcols, mp]
+                S = B[:, ds.col0:ds.col0 + ds.kcols] @ Lst
+                acc[:, ds.acc_col0:ds.acc_col0 + ds.mul] += S[:, :ds.mul]
+                assert float(S[:, ds.mul:].abs().max()) == 0 if ds.mul < ds.mp else True
+        assert bt_expected == ps.batch_end
+        assert not seen[ps.out_col0:ps.out_col0 + ps.ncols].any()
+        seen[ps.out_col0:ps.out_col0 + ps.ncols] = True
+        CP[:, ps.out_col0:ps.out_col0 + ps.ncols] = acc
+    assert seen.all()
+    return emulate_unrotate(op, CP, Dw, seg_ptr, seg_order)

@@ -208,6 +208,19 @@ def test_rotated_frame_program_matches_oracle(small):
     with torch.no_grad():
         ref_emb = opre.pair_embedding(dd2)
     assert rel_err(got, ref_emb) < 2e-6
+    # ---- the A-stationary regrouping of the same steps (rot2 tables) + the segmented receiver reduction
+    got2 = EM.emulate_msgpack_rot2(pe.conv_tp.op, st["tc_wbuf"].double(), [h], [None], vec, d["edge_embedding"])
+    assert rel_err(got2, ref_emb) < 2e-6
+    st = pb.conv_tp.op.pack_tc(pb.conv_tp.weights(pb.skip_linear.weight))
+    got2 = EM.emulate_msgpack_rot2(pb.conv_tp.op, st["tc_wbuf"].double(), [xs, xt, e], [s, r, None], vec, d["edge_embedding"])
+    assert rel_err(got2, ref_pair) < 2e-6
+    st = cb.op.pack_tc(cb.weights())
+    from hamgnn_b200.plan import receiver_segments
+    seg_ptr, seg_order = receiver_segments(r, N)
+    assert torch.equal(r[seg_order], torch.sort(r, stable=True).values) and int(seg_ptr[-1]) == E
+    got2 = EM.emulate_msgpack_rot2(cb.op, st["tc_wbuf"].double(), [x, x, e], [s, r, None], vec, d["edge_embedding"],
+                                   seg_ptr=seg_ptr, seg_order=seg_order)
+    assert rel_err(got2, torch.zeros(N, D, dtype=torch.float64).index_add_(0, r, ref_msg)) < 2e-6
 
 
 def test_rotated_frame_tables_are_well_formed():
