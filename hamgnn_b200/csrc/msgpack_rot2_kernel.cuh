@@ -1,0 +1,422 @@
+// A-stationary edge-aligned fused MessagePackBlock ("rot2").  Included by msgpack_tcg.cu after msgpack_rot_kernel.cuh
+// (same Wigner / rotate-pack / radial-gate pre-passes, same packed X' images).
+//
+// msgpack_rot_kernel evaluates one (path, m1) step at a time: 2 800 steps per tile of 128 edges and message, every
+// step a GEMM1 with N = one padded multiplicity (16 on the slots that hold half of the time), its own copy of the
+// input image from L2 (53 MB of A traffic per tile and message) and a gate -> GEMM2 -> accumulate hand-off
+// (profiles/r01v_rot_msgpack_ncu_summary.md: tensor pipe 7 %, 3 000 cycles per step, bound by the hand-offs).
+// Here the steps are regrouped on the host (plan.MessagePackOp._build_rot2_program):
+//
+//   CTA   = (tile of 128 edges, pass); pass = (output component m3, output slots with <= 128 accumulator columns)
+//   piece = one image X'_{block, m1} x the CONCATENATED weights of every path of the pass that reads it
+//             GEMM1  B[n&1][128 x ncols] = X' [W_p1 | W_p2 | ...]          warp 9, A / W chunks of 16 channels from the TMA ring
+//             gate   B <- hi(B * s_p g_p), GL[n&1] <- lo                    warps 0-3, thread = edge = TMEM lane, 8 columns a batch
+//             GEMM2  S[n&1][s_off ..] = (B.g)[:, col0 : col0 + kcols] L'stack   warp 10, one K-concatenated chain per destination slot
+//             acc    C'[acc_col0 + w] += S[s_off + w]                        warps 4-7, fp32 round-to-nearest in shared memory
+//   end   : the pass's columns of the aligned-frame row cp[e][.] are stored (coalesced), unrotate_kernel finishes.
+//
+// ~700 pieces instead of ~2 800 steps, mean N 62 instead of 16-32, every image fetched once per pass: 15 MB of A per tile and
+// message instead of 53 MB.  The tensor core's truncating accumulation still only spans one piece (<= 16 + 36 MMAs); the
+// sum over pieces is fp32 round-to-nearest (see msgpack_rot_kernel.cuh on why).
+// TMEM (512 columns, 1 CTA / SM): B0 B1 | GL0 GL1 (96 each) | S0 S1 (64 each) -- everything double buffered, so a gate
+// warp only ever waits for GEMM1 and the GEMM2 issuer only for the gate.
+#pragma once
+
+namespace rot2 {
+using namespace tcmsg;
+using rot::arrive_a;
+using rot::bulk_g2s_a;
+using rot::bulk_prefetch_l2;
+using rot::commit_a;
+using rot::elect_one;
+using rot::expect_tx_a;
+using rot::tmem_alloc_dyn;
+using rot::tmem_dealloc_dyn;
+using rot::wait_a;
+using rot::warp_wait_a;
+
+constexpr int TILE = 128;
+constexpr int KC32 = 32;   // channel chunk of the packed X' images (rot::KC)
+constexpr int KC2 = 16;    // channels per ring stage (host: MessagePackOp.R2_KC)
+constexpr int NB = 96;     // B columns per piece (R2_NB)
+constexpr int SW = 64;     // S columns per piece (R2_SW)
+constexpr int NST = 3;
+constexpr int ACC_COLS = 128, ACC_LD = 129;
+constexpr int A_LO = KC2 * TILE;                       // float offset of the A lo image inside a stage
+constexpr int W_AT = 2 * KC2 * TILE;                   // float offset of the W chunk inside a stage
+constexpr int STG = 2 * KC2 * TILE + 2 * KC2 * NB;     // floats per ring stage (28 KB)
+constexpr int LBUF = 8192;                             // floats per L' buffer (R2_LMAX_FLOATS)
+constexpr int NTHR = 352;                              // warps 0-3 gate, 4-7 accumulate, 8 TMA, 9 GEMM1, 10 GEMM2
+constexpr uint32_t TB = 0, TGL = 2 * NB, TS = 4 * NB;  // TMEM columns
+constexpr size_t SMEM_BYTES = (size_t)(NST * STG + 2 * LBUF + ACC_COLS * ACC_LD) * sizeof(float);
+
+struct Args {
+  const float* wbuf;
+  const hgb_rot2_pass_t* passes;
+  const hgb_rot2_piece_t* pieces;
+  const hgb_rot2_batch_t* batches;
+  const hgb_rot2_dst_t* dsts;
+  int n_passes;
+  const float* xp;      // packed rotated inputs of the chunk [tile][tile_stride]
+  int tile_stride;
+  const float* g;       // radial gate of the chunk [branch][tile][gstride][128]
+  int gstride;
+  int64_t e_lo, n_chunk;
+  float* cp;            // aligned-frame messages of ALL edges [E][rowstride]
+  int rowstride;
+};
+
+struct PieceRec {   // hgb_rot2_piece_t as two 16-byte words
+  int a_off, w_off, l_off, l_floats, batch_begin, dst_begin, kpad, ncols, ndst;
+};
+__device__ __forceinline__ PieceRec load_piece(const hgb_rot2_piece_t* p) {
+  const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p)), w1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  PieceRec r;
+  r.a_off = (int)w0.x; r.w_off = (int)w0.y; r.l_off = (int)w0.z; r.l_floats = (int)w0.w;
+  r.batch_begin = (int)w1.x; r.dst_begin = (int)w1.y;
+  r.kpad = (int)(w1.z & 0xffffu); r.ncols = (int)(w1.z >> 16); r.ndst = (int)(w1.w & 0xffffu);
+  return r;
+}
+
+__global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(128) float smem[];
+  // barriers: full[3] | empty[3] | lfull[2] | bfull[2] | gfull[2] | s2done[2] | sfree[2]
+  __shared__ uint64_t bars[16];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar0 = tc::smem_u32(bars);
+  const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_BFULL = B_LFULL + 16, B_GFULL = B_LFULL + 32,
+                 B_S2 = B_LFULL + 48, B_SFREE = B_LFULL + 64;
+  const uint32_t stage0 = tc::smem_u32(smem);
+  const uint32_t lbuf0 = stage0 + (uint32_t)(NST * STG) * 4u;
+  float* accs = smem + NST * STG + 2 * LBUF;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x / a.n_passes;
+  const int pass = blockIdx.x - tile * a.n_passes;
+  const hgb_rot2_pass_t ps = a.passes[pass];
+
+  if (tid == 0) {
+    for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], ((i >= 10 && i < 12) || i >= 14) ? 4 : 1);   // gfull / sfree: one arrival per warp
+    tc::mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc_dyn(&tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const float* __restrict__ wbuf = a.wbuf;
+  const uint32_t dhi = tc::smem_desc_hi(128);
+  const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
+
+  if (warp == 8) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const float* xt = a.xp + (size_t)tile * a.tile_stride;
+      const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+      // gate blocks of a piece: nvalid columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 one
+      // piece ahead of the gate warps (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident)
+      auto prefetch_gate = [&](int qi) {
+        if (qi >= ps.piece_end) return;
+        const int b0 = a.pieces[qi].batch_begin, nb = a.pieces[qi].ncols >> 3;
+        for (int k = 0; k < nb; ++k) {
+          const uint32_t meta = (uint32_t)__ldg(&a.batches[b0 + k].meta);
+          const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu, nv = (meta >> 24) & 0xFu;
+          if (nv != 0 && col != 0xFFFFFu) bulk_prefetch_l2(gt + (size_t)br * g_bstride + (size_t)col * TILE, nv * TILE * 4u);
+        }
+      };
+      prefetch_gate(ps.piece_begin);
+      int n = 0, c_all = 0;
+      for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+        const PieceRec pc = load_piece(a.pieces + qi);
+        prefetch_gate(qi + 1);
+        {
+          const int lb = n & 1;
+          if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read this L' buffer
+          const uint32_t lbytes = (uint32_t)pc.l_floats * 4u;
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(lbuf0 + (uint32_t)(lb * LBUF) * 4u, wbuf + pc.l_off, lbytes, B_LFULL + 8 * lb);
+        }
+        for (int u0 = 0, c = 0; u0 < pc.kpad; u0 += KC2, ++c, ++c_all) {
+          const int kc = min(KC2, pc.kpad - u0), s = c_all % NST;
+          if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
+          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
+          const uint32_t ab = (uint32_t)(kc * TILE) * 4u, wb = (uint32_t)(2 * kc * pc.ncols) * 4u;
+          // the packed image is chunked by 32 channels, (hi | lo) per chunk: this stage is half of such a chunk
+          const int c32 = c >> 1, kc32 = min(KC32, pc.kpad - c32 * KC32);
+          const float* ahi = xt + pc.a_off + (size_t)c32 * (2 * KC32 * TILE) + (size_t)(c & 1) * (KC2 * TILE);
+          expect_tx_a(B_FULL + 8 * s, 2 * ab + wb);
+          bulk_g2s_a(sa, ahi, ab, B_FULL + 8 * s);
+          bulk_g2s_a(sa + A_LO * 4, ahi + (size_t)kc32 * TILE, ab, B_FULL + 8 * s);
+          bulk_g2s_a(sa + W_AT * 4, wbuf + pc.w_off + (size_t)c * (2 * KC2 * pc.ncols), wb, B_FULL + 8 * s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // =============================== GEMM1 issuer ===============================
+    const uint32_t lbo_a = TILE * 16, astep = (2 * lbo_a) >> 4;
+    int n = 0, c_all = 0;
+    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+      const PieceRec pc = load_piece(a.pieces + qi);
+      if (n >= 2) warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read B / GL [n&1]
+      const uint32_t dcol = tmem + TB + (uint32_t)((n & 1) * NB);
+      const uint32_t idesc = tc::idesc_tf32_m128(pc.ncols);
+      const uint32_t lbo_n = (uint32_t)pc.ncols * 16, bstep = (2 * lbo_n) >> 4;
+      for (int u0 = 0, c = 0; u0 < pc.kpad; u0 += KC2, ++c, ++c_all) {
+        const int kc = min(KC2, pc.kpad - u0), s = c_all % NST;
+        warp_wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
+        tc::fence_after_sync();
+        if (elect_one()) {
+          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
+          const uint32_t ah = tc::smem_desc_lo(sa, lbo_a), al = tc::smem_desc_lo(sa + A_LO * 4, lbo_a);
+          const uint32_t wh = tc::smem_desc_lo(sa + W_AT * 4, lbo_n), wl = wh + (((uint32_t)pc.ncols * kc * 4) >> 4);
+          for (int k8 = 0; k8 < (kc >> 3); ++k8) {
+            const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
+            const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl_ = tc::desc64(wl + k8 * bstep, dhi);
+            tc::mma_tf32(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+            tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
+            tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+          }
+          commit_a(B_EMPTY + 8 * s);
+          if (u0 + KC2 >= pc.kpad) commit_a(B_BFULL + 8 * (n & 1));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== GEMM2 issuer ===============================
+    int n = 0;
+    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+      const PieceRec pc = load_piece(a.pieces + qi);
+      const int nb = n & 1;
+      const uint32_t par = (uint32_t)((n >> 1) & 1);
+      if (n >= 2) warp_wait_a(B_SFREE + 8 * nb, par ^ 1u);   // the accumulate warps have drained S[n&1] of piece n-2
+      warp_wait_a(B_LFULL + 8 * nb, par);
+      warp_wait_a(B_GFULL + 8 * nb, par);
+      tc::fence_after_sync();
+      if (elect_one()) {
+        const uint32_t bq = tmem + TB + (uint32_t)(nb * NB), gl = tmem + TGL + (uint32_t)(nb * NB), sc0 = tmem + TS + (uint32_t)(nb * SW);
+        const uint32_t lb = lbuf0 + (uint32_t)(nb * LBUF) * 4u;
+        for (int di = 0; di < pc.ndst; ++di) {
+          const uint4 dw = __ldg(reinterpret_cast<const uint4*>(a.dsts + pc.dst_begin + di));
+          const uint32_t col0 = dw.x & 0xffffu, kcols = dw.x >> 16, mp = dw.y & 0xffffu, s_off = dw.y >> 16, l_rel = dw.w;
+          const uint32_t idesc = tc::idesc_tf32_m128((int)mp);
+          const uint32_t lbo_l = mp * 16, lstep = (2 * lbo_l) >> 4;
+          const uint32_t lh = tc::smem_desc_lo(lb + l_rel * 4u, lbo_l), ll = lh + ((kcols * mp * 4u) >> 4);
+          const uint32_t sc = sc0 + s_off;
+          for (uint32_t k8 = 0; k8 < (kcols >> 3); ++k8) {
+            const uint64_t bh = tc::desc64(lh + k8 * lstep, dhi), bl = tc::desc64(ll + k8 * lstep, dhi);
+            tc::mma_tf32_ts(sc, gl + col0 + k8 * 8, bh, idesc, (uint32_t)(k8 > 0));
+            tc::mma_tf32_ts(sc, bq + col0 + k8 * 8, bl, idesc, 1);
+            tc::mma_tf32_ts(sc, bq + col0 + k8 * 8, bh, idesc, 1);
+          }
+        }
+        commit_a(B_S2 + 8 * nb);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // =============================== gate: B <- hi(B * s g), GL <- lo  (thread = edge = TMEM lane) ===============================
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int64_t el = (int64_t)tile * TILE + tid;
+    const bool live = el < a.n_chunk;
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);   // column c of this edge: grow[c * TILE]
+    constexpr int DEPTH = 4;          // gate batches in flight (register ring): L2 latency / ~60 cycles per batch
+    float gv[DEPTH][8], gs[DEPTH];
+    const int b_end = ps.batch_end;
+    // gate values of batch bb -> ring slot u (compile-time after unrolling); un-gated batches get 1, padding columns 0
+    auto issue = [&](float (&gq)[8], float& sq, int bb) {
+      if (bb >= b_end) return;
+      const int2 bt = __ldg(reinterpret_cast<const int2*>(a.batches + bb));
+      const uint32_t meta = (uint32_t)bt.x;
+      const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu;
+      const int nv = (int)((meta >> 24) & 0xFu);
+      sq = __int_as_float(bt.y);
+      if (col == 0xFFFFFu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? 1.f : 0.f;
+      } else {
+        const float* gp = grow + (size_t)br * g_bstride + (size_t)col * TILE;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? __ldg(gp + j * TILE) : 0.f;   // warp-uniform predicate; 128 contiguous bytes per warp
+      }
+    };
+    int n = 0, qi = ps.piece_begin;
+    PieceRec pc = load_piece(a.pieces + qi);
+    int pb0 = pc.batch_begin, pb1 = pb0 + (pc.ncols >> 3);
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) issue(gv[u], gs[u], ps.batch_begin + u);
+    warp_wait_a(B_BFULL, 0);
+    tc::fence_after_sync();
+    for (int b = ps.batch_begin; b < b_end; b += DEPTH) {
+#pragma unroll
+      for (int u = 0; u < DEPTH; ++u) {
+        const int bb = b + u;
+        if (bb < b_end) {
+          if (bb == pb1) {   // piece n is gated: hand it to GEMM2, move to the next piece
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
+            ++n; ++qi;
+            pc = load_piece(a.pieces + qi);
+            pb0 = bb; pb1 = bb + (pc.ncols >> 3);
+            warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
+            tc::fence_after_sync();
+          }
+          const uint32_t col = (uint32_t)((bb - pb0) * 8);
+          const uint32_t bq = tmem + lane_base + TB + (uint32_t)((n & 1) * NB) + col;
+          const uint32_t gl = tmem + lane_base + TGL + (uint32_t)((n & 1) * NB) + col;
+          uint32_t rb[8], hi[8], lo[8];
+          tc::tmem_ld8(bq, rb);
+          tc::tmem_ld_wait8(rb);
+          const float sc = gs[u];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float h, l;
+            tc::split_tf32(__uint_as_float(rb[j]) * (gv[u][j] * sc), h, l);
+            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
+          }
+          tc::tmem_st8(bq, hi);
+          tc::tmem_st8(gl, lo);
+          issue(gv[u], gs[u], bb + DEPTH);
+        }
+      }
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
+  } else {
+    // =============================== accumulate: C' += S, finally store the pass's columns of cp ===============================
+    const int q = warp - 4, zl = tid - 128;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* acc = accs + zl;
+    for (int c = 0; c < ps.ncols; ++c) acc[c * ACC_LD] = 0.f;
+    int n = 0;
+    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
+      const int dst_begin = (int)w1.y, ndst = (int)(w1.w & 0xffffu);
+      warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
+      tc::fence_after_sync();
+      const uint32_t sc0 = tmem + lane_base + TS + (uint32_t)((n & 1) * SW);
+      for (int di = 0; di < ndst; ++di) {
+        const uint4 dw = __ldg(reinterpret_cast<const uint4*>(a.dsts + dst_begin + di));
+        const int s_off = (int)(dw.y >> 16), acc_col0 = (int)(dw.z & 0xffffu), mul = (int)(dw.z >> 16);
+        float* ap = acc + acc_col0 * ACC_LD;
+        for (int c0 = 0; c0 < mul; c0 += 8) {
+          uint32_t rs[8];
+          tc::tmem_ld8(sc0 + (uint32_t)(s_off + c0), rs);
+          tc::tmem_ld_wait8(rs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < mul) ap[(c0 + j) * ACC_LD] += __uint_as_float(rs[j]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive_a(B_SFREE + 8 * (n & 1));
+    }
+    __syncwarp();
+    // warp q owns edges [32 q, 32 q + 32) of the tile: rows of cp, the pass's columns are contiguous
+    for (int zz = 0; zz < 32; ++zz) {
+      const int64_t el = (int64_t)tile * TILE + q * 32 + zz;
+      if (el >= a.n_chunk) break;
+      float* row = a.cp + (size_t)(a.e_lo + el) * a.rowstride + ps.out_col0;
+      const float* as = accs + q * 32 + zz;
+      for (int c = lane; c < ps.ncols; c += 32) row[c] = as[c * ACC_LD];
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc_dyn(tmem, 512);
+}
+
+// ===================================================================================================== unrotate (+ segment sum)
+struct UnrotArgs {
+  const float* cp;
+  int rowstride;
+  const float* dw;
+  int dstride;
+  int doff[12];
+  int n_warps;                     // warps per sweep = blockDim.x / 32
+  int n_items;                     // (slot, 32-channel group) items; item i is handled by warp i % n_warps in sweep i / n_warps
+  int item_slot[64], item_w0[64];
+  int slot_l[32], slot_mul[32], slot_out_off[32];
+  int ccol[32][13];
+  const int64_t* seg_ptr;          // NULL: row r = edge r
+  const int64_t* seg_order;
+  int64_t n_rows;
+  float* out;
+  int out_dim;
+};
+
+__device__ __forceinline__ void unrot_bar() { asm volatile("bar.sync 1;" ::: "memory"); }   // same barrier from every instantiation
+
+// warp = (slot t, 32 channels); thread: o[k] = sum over the segment's edges of sum_m3 D^{l3}_e[m3][k] C'_e[t][m3][w], summed in
+// list order (deterministic).  Every warp of the CTA walks the same segment and meets the others at unrot_bar() twice per
+// edge (D^l of the edge staged once in shared memory); warps differ in L3, lanes of a warp do not.
+template <int L3>
+__device__ __forceinline__ void unrot_run(const UnrotArgs& a, float (*sD)[480], int t, int w, bool active, int64_t j0, int64_t j1,
+                                          int64_t row) {
+  constexpr int d3 = 2 * L3 + 1;
+  float o[d3];
+#pragma unroll
+  for (int k = 0; k < d3; ++k) o[k] = 0.f;
+  int cc[d3];
+#pragma unroll
+  for (int m = 0; m < d3; ++m) cc[m] = active ? a.ccol[t][m] : -1;
+  const int dof = a.doff[L3];
+  int buf = 0;
+  for (int64_t j = j0; j < j1; ++j, buf ^= 1) {
+    const int64_t e = a.seg_order ? a.seg_order[j] : j;
+    const float* drow = a.dw + (size_t)e * a.dstride;
+    for (int i = threadIdx.x; i < a.dstride; i += blockDim.x) sD[buf][i] = __ldg(drow + i);
+    float c[d3];
+    const float* crow = a.cp + (size_t)e * a.rowstride + w;
+#pragma unroll
+    for (int m = 0; m < d3; ++m) c[m] = (cc[m] >= 0) ? __ldg(crow + cc[m]) : 0.f;
+    unrot_bar();   // sD[buf] complete; sD[buf ^ 1] was last read before the previous barrier
+    if (L3 == 0) {
+      o[0] += c[0];
+    } else {
+      const float* D = sD[buf] + dof;
+#pragma unroll
+      for (int m = 0; m < d3; ++m)
+#pragma unroll
+        for (int k = 0; k < d3; ++k) o[k] = fmaf(D[m * d3 + k], c[m], o[k]);
+    }
+  }
+  if (active) {
+    float* op = a.out + (size_t)row * a.out_dim + a.slot_out_off[t] + w * d3;
+#pragma unroll
+    for (int k = 0; k < d3; ++k) op[k] = o[k];
+  }
+}
+
+__global__ void __launch_bounds__(1024) unrotate_kernel(const __grid_constant__ UnrotArgs a) {
+  __shared__ float sD[2][480];
+  const int64_t row = blockIdx.x;
+  const int64_t j0 = a.seg_ptr ? a.seg_ptr[row] : row, j1 = a.seg_ptr ? a.seg_ptr[row + 1] : row + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < a.n_items; i0 += a.n_warps) {
+    const int it = i0 + warp;
+    const bool have = it < a.n_items;
+    const int t = have ? a.item_slot[it] : 0;
+    const int w = have ? a.item_w0[it] + lane : 0;
+    const bool active = have && w < a.slot_mul[t];
+    const int l3 = have ? a.slot_l[t] : 0;
+    switch (l3) {   // warp-uniform
+      case 0: unrot_run<0>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      case 1: unrot_run<1>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      case 2: unrot_run<2>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      case 3: unrot_run<3>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      case 4: unrot_run<4>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      case 5: unrot_run<5>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+      default: unrot_run<6>(a, sD, t, active ? w : 0, active, j0, j1, row); break;
+    }
+    unrot_bar();
+  }
+}
+
+}  // namespace rot2

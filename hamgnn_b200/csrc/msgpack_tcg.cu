@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
 #include "msgpack_rot_s2_kernel.cuh"
+#include "msgpack_rot2_kernel.cuh"
 
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
 // MLP widths fit its tiling, the fp32-FMA kernel otherwise.
@@ -832,6 +833,154 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }
+  }
+  return 0;
+}
+
+// ============================================================================================== rot2 (A-stationary) host side
+extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_rot_plan* rp, const hgb_rot2_plan* r2,
+                                        const float* const* src, const int64_t* const* src_rows, const float* dw,
+                                        const float* rbf, const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off,
+                                        int32_t gstride, float* g_ws, float* xp_ws, float* cp_ws, int64_t chunk_edges,
+                                        int64_t n_edges, float* out, const int64_t* seg_ptr, const int64_t* seg_order,
+                                        int64_t n_out_rows, void* stream) {
+  HGB_DEVICE_GUARD(out);
+  HGB_CHECK_ARG(plan && rp && r2 && src && dw && rbf && out && g_ws && xp_ws && cp_ws && w3_off && nch, "hgb_msgpack_rot2_forward: NULL argument");
+  HGB_CHECK_ARG(rp->blocks_host && rp->blocks && r2->passes && r2->pieces && r2->batches && r2->dsts && r2->passes_host && r2->pieces_host &&
+                    r2->batches_host && r2->dsts_host,
+                "hgb_msgpack_rot2_forward: host and device copies of the tables are required");
+  HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
+                "hgb_msgpack_rot2_forward: bad source/branch count");
+  HGB_CHECK_ARG(plan->h2 <= 64 && plan->h1 <= 64 && plan->rbf_dim <= 64,
+                "hgb_msgpack_rot2_forward: radial MLP [%d,%d,%d] unsupported (all widths <= 64)", plan->rbf_dim, plan->h1, plan->h2);
+  HGB_CHECK_ARG(rp->lmax >= 0 && rp->lmax <= rot::LMAX && r2->n_slots >= 1 && r2->n_slots <= 32, "hgb_msgpack_rot2_forward: too many output slots or l > %d", rot::LMAX);
+  HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_msgpack_rot2_forward: bad edge count");
+  HGB_CHECK_ARG(chunk_edges >= rot::TILE && chunk_edges % rot::TILE == 0, "hgb_msgpack_rot2_forward: chunk_edges must be a positive multiple of %d", rot::TILE);
+  HGB_CHECK_ARG(rp->tile_stride > 0 && rp->tile_stride % 4 == 0 && rp->n_blocks >= 1, "hgb_msgpack_rot2_forward: bad packed-input layout");
+  HGB_CHECK_ARG((seg_ptr == nullptr) == (seg_order == nullptr), "hgb_msgpack_rot2_forward: seg_ptr and seg_order go together");
+  HGB_CHECK_ARG(seg_ptr ? n_out_rows >= 0 : n_out_rows == n_edges, "hgb_msgpack_rot2_forward: bad output row count");
+  HGB_CHECK_ARG(r2->n_passes >= 1 && r2->rowstride >= 1 && r2->rowstride <= plan->out_dim, "hgb_msgpack_rot2_forward: bad pass table");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b = 0; b < plan->n_branches; ++b)
+    HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "hgb_msgpack_rot2_forward: gate width %d exceeds stride %d", nch[b], gstride);
+  for (int s = 0; s < plan->n_sources; ++s) HGB_CHECK_ARG(src[s] != nullptr, "hgb_msgpack_rot2_forward: source %d is NULL", s);
+
+  // ---- validate the tables (host copies): every offset the kernel dereferences
+  for (int i = 0; i < rp->n_blocks; ++i) {
+    const hgb_rot_block_t& b = rp->blocks_host[i];
+    HGB_CHECK_ARG(b.l1 >= 0 && b.l1 <= rp->lmax && b.nsrc >= 1 && b.nsrc <= 2 && b.src0 >= 0 && b.src0 + b.nsrc <= plan->n_sources,
+                  "hgb_msgpack_rot2_forward: bad block %d", i);
+    HGB_CHECK_ARG(b.kpad % 8 == 0 && b.kpad >= b.nsrc * b.mul && b.mul >= 1 && b.in_off >= 0 &&
+                      b.in_off + b.mul * (2 * b.l1 + 1) <= plan->src_dim[b.src0],
+                  "hgb_msgpack_rot2_forward: block %d outside its source row", i);
+    HGB_CHECK_ARG(b.xoff >= 0 && b.xoff % 4 == 0 && (int64_t)b.xoff + (int64_t)(2 * b.l1 + 1) * 2 * b.kpad * rot::TILE <= rp->tile_stride,
+                  "hgb_msgpack_rot2_forward: block %d outside the packed tile", i);
+  }
+  int col_cover = 0;
+  for (int p = 0; p < r2->n_passes; ++p) {
+    const hgb_rot2_pass_t& ps = r2->passes_host[p];
+    HGB_CHECK_ARG(ps.piece_begin >= 0 && ps.piece_begin < ps.piece_end && ps.piece_end <= r2->n_pieces && ps.ncols >= 1 &&
+                      ps.ncols <= rot2::ACC_COLS && ps.out_col0 == col_cover && ps.batch_begin >= 0 && ps.batch_end <= r2->n_batches,
+                  "hgb_msgpack_rot2_forward: bad pass %d", p);
+    col_cover += ps.ncols;
+    int bt = ps.batch_begin;
+    for (int q = ps.piece_begin; q < ps.piece_end; ++q) {
+      const hgb_rot2_piece_t& pc = r2->pieces_host[q];
+      HGB_CHECK_ARG(pc.kpad >= 8 && pc.kpad % 8 == 0 && pc.ncols >= 16 && pc.ncols % 16 == 0 && pc.ncols <= rot2::NB && pc.a_off >= 0 &&
+                        pc.a_off % 4 == 0 && (int64_t)pc.a_off + (int64_t)2 * pc.kpad * rot::TILE <= rp->tile_stride && pc.w_off >= 0 &&
+                        pc.w_off % 4 == 0 && pc.l_off >= 0 && pc.l_off % 4 == 0 && pc.l_floats > 0 && pc.l_floats % 4 == 0 &&
+                        pc.l_floats <= rot2::LBUF && pc.batch_begin == bt && pc.ndst >= 1 && pc.dst_begin >= 0 &&
+                        pc.dst_begin + pc.ndst <= r2->n_dsts,
+                    "hgb_msgpack_rot2_forward: bad piece %d", q);
+      for (int k = 0; k < pc.ncols / 8; ++k) {
+        const uint32_t meta = (uint32_t)r2->batches_host[bt + k].meta;
+        const int col = (int)(meta & 0xFFFFFu), br = (int)((meta >> 20) & 0xFu), nv = (int)((meta >> 24) & 0xFu);
+        HGB_CHECK_ARG(nv <= 8 && (col == 0xFFFFF || (br < plan->n_branches && col + nv <= nch[br])),
+                      "hgb_msgpack_rot2_forward: gate batch %d out of range", bt + k);
+      }
+      bt += pc.ncols / 8;
+      int s_used = 0;
+      for (int d = pc.dst_begin; d < pc.dst_begin + pc.ndst; ++d) {
+        const hgb_rot2_dst_t& ds = r2->dsts_host[d];
+        HGB_CHECK_ARG(ds.col0 >= 0 && ds.col0 % 8 == 0 && ds.kcols >= 8 && ds.kcols % 8 == 0 && ds.col0 + ds.kcols <= pc.ncols &&
+                          ds.mp >= 16 && ds.mp % 16 == 0 && ds.s_off == s_used && ds.s_off + ds.mp <= rot2::SW && ds.mul >= 1 &&
+                          ds.mul <= ds.mp && ds.acc_col0 >= 0 && ds.acc_col0 + ds.mul <= ps.ncols && ds.l_rel >= 0 && ds.l_rel % 4 == 0 &&
+                          ds.l_rel + 2 * ds.kcols * ds.mp <= pc.l_floats,
+                      "hgb_msgpack_rot2_forward: bad destination group %d", d);
+        s_used += ds.mp;
+      }
+    }
+    HGB_CHECK_ARG(bt == ps.batch_end, "hgb_msgpack_rot2_forward: gate batches of pass %d are not contiguous", p);
+  }
+  HGB_CHECK_ARG(col_cover == r2->rowstride, "hgb_msgpack_rot2_forward: passes cover %d of %d columns", col_cover, r2->rowstride);
+
+  rot2::UnrotArgs ua;
+  memset(&ua, 0, sizeof(ua));
+  ua.cp = cp_ws; ua.rowstride = r2->rowstride; ua.dw = dw; ua.dstride = rp->dstride;
+  HGB_CHECK_ARG(rp->dstride <= 480, "hgb_msgpack_rot2_forward: Wigner row of %d floats exceeds the staging buffer", rp->dstride);
+  for (int l = 0; l <= rp->lmax; ++l) ua.doff[l] = rp->doff[l];
+  int n_items = 0;
+  for (int t = 0; t < r2->n_slots; ++t) {
+    HGB_CHECK_ARG(r2->slot_l[t] >= 0 && r2->slot_l[t] <= rp->lmax && r2->slot_mul[t] >= 1 && r2->slot_out_off[t] >= 0 &&
+                      r2->slot_out_off[t] + r2->slot_mul[t] * (2 * r2->slot_l[t] + 1) <= plan->out_dim,
+                  "hgb_msgpack_rot2_forward: bad slot %d", t);
+    ua.slot_l[t] = r2->slot_l[t]; ua.slot_mul[t] = r2->slot_mul[t]; ua.slot_out_off[t] = r2->slot_out_off[t];
+    for (int m = 0; m < 13; ++m) {
+      ua.ccol[t][m] = r2->ccol[t][m];
+      HGB_CHECK_ARG(m < 2 * r2->slot_l[t] + 1 ? (r2->ccol[t][m] >= -1 && r2->ccol[t][m] + r2->slot_mul[t] <= r2->rowstride) : true,
+                    "hgb_msgpack_rot2_forward: bad cp column of slot %d", t);
+    }
+    for (int w0 = 0; w0 < r2->slot_mul[t]; w0 += 32) {
+      HGB_CHECK_ARG(n_items < 64, "hgb_msgpack_rot2_forward: more than 64 (slot, 32-channel) groups");
+      ua.item_slot[n_items] = t; ua.item_w0[n_items] = w0; ++n_items;
+    }
+  }
+  ua.n_items = n_items;
+  ua.n_warps = n_items < 32 ? n_items : 32;
+  ua.seg_ptr = seg_ptr; ua.seg_order = seg_order; ua.n_rows = n_out_rows; ua.out = out; ua.out_dim = plan->out_dim;
+  if (n_edges == 0) {
+    if (n_out_rows > 0) HGB_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)n_out_rows * plan->out_dim * sizeof(float), st));
+    return 0;
+  }
+
+  rot::RpArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.blocks = rp->blocks; pa.n_blocks = rp->n_blocks; pa.tile_stride = rp->tile_stride; pa.dstride = rp->dstride;
+  for (int l = 0; l <= rp->lmax; ++l) pa.doff[l] = rp->doff[l];
+  for (int s = 0; s < plan->n_sources; ++s) {
+    pa.src[s] = src[s];
+    pa.src_rows[s] = src_rows ? src_rows[s] : nullptr;
+    pa.src_dim[s] = plan->src_dim[s];
+  }
+  pa.dw = dw; pa.xp = xp_ws;
+  pa.blocks_per_cta = (rp->n_blocks + 3) / 4;
+  const unsigned rp_gy = (unsigned)((rp->n_blocks + pa.blocks_per_cta - 1) / pa.blocks_per_cta);
+
+  rot2::Args ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.wbuf = plan->wbuf; ka.passes = r2->passes; ka.pieces = r2->pieces; ka.batches = r2->batches; ka.dsts = r2->dsts;
+  ka.n_passes = r2->n_passes; ka.xp = xp_ws; ka.tile_stride = rp->tile_stride; ka.g = g_ws; ka.gstride = gstride;
+  ka.cp = cp_ws; ka.rowstride = r2->rowstride;
+  static_assert(rot2::SMEM_BYTES <= 227 * 1024, "msgpack_rot2_kernel: shared memory budget");
+  HGB_CUDA_OK(cudaFuncSetAttribute(rot2::msgpack_rot2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot2::SMEM_BYTES));
+
+  for (int64_t e_lo = 0; e_lo < n_edges; e_lo += chunk_edges) {
+    const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
+    const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
+    {
+      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 1);
+      if (rc != 0) return rc;
+    }
+    pa.e_lo = e_lo; pa.n_chunk = n;
+    rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
+    HGB_LAUNCH_OK("rotate_pack_kernel");
+    ka.e_lo = e_lo; ka.n_chunk = n;
+    rot2::msgpack_rot2_kernel<<<(unsigned)(n_tiles * r2->n_passes), rot2::NTHR, rot2::SMEM_BYTES, st>>>(ka);
+    HGB_LAUNCH_OK("msgpack_rot2_kernel");
+  }
+  if (n_out_rows > 0) {
+    rot2::unrotate_kernel<<<(unsigned)n_out_rows, (unsigned)(32 * ua.n_warps), 0, st>>>(ua);
+    HGB_LAUNCH_OK("unrotate_kernel");
   }
   return 0;
 }

@@ -258,14 +258,53 @@ class KernelProfiler:
 PROFILER: Optional[KernelProfiler] = None
 # which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
-BACKEND = os.environ.get("HGB_MSGPACK", "rot")
+BACKEND = os.environ.get("HGB_MSGPACK", "rot2")
 # radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
-GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND == "rot" else "simt")
+GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND in ("rot", "rot2") else "simt")
 
 
 # edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)
-ROT_CHUNK_EDGES = int(os.environ.get("HGB_ROT_CHUNK", str(512 * 1024)))
+def _rot_chunk_edges() -> int:
+    """Edges per chunk of the rotated-frame paths: a multiple of the 128-edge tile (HGB_ROT_CHUNK is rounded up)."""
+    v = int(os.environ.get("HGB_ROT_CHUNK", str(128 * 1024)))
+    return max(128, (v + 127) // 128 * 128)
+
+
+ROT_CHUNK_EDGES = _rot_chunk_edges()
 _WIGNER_CACHE: Dict[Tuple, torch.Tensor] = {}
+_WORKSPACES: Dict[Tuple[str, str], torch.Tensor] = {}
+_SEGMENT_CACHE: Dict[str, tuple] = {}
+
+
+def workspace(name: str, numel: int, device) -> torch.Tensor:
+    """Grow-only fp32 scratch buffer shared by all message ops of a device (the seven message calls of a forward run
+    back to back on one stream, so they can share it); avoids a multi-GB torch.empty per call."""
+    key = (name, str(device))
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < numel:
+        _WORKSPACES.pop(key, None)
+        buf = torch.empty(int(numel), device=device, dtype=torch.float32)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    """Drop the cached scratch buffers, the Wigner matrices and the receiver segments (they pin GBs for large graphs)."""
+    _WORKSPACES.clear()
+    _WIGNER_CACHE.clear()
+    _SEGMENT_CACHE.clear()
+
+
+def segments_for(index: torch.Tensor, n_rows: int):
+    """receiver_segments(index) cached on the identity of the index tensor (one entry: the three ConvBlockE3 of a forward
+    share it)."""
+    key = (index.data_ptr(), index._version, int(index.numel()), int(n_rows), str(index.device))
+    hit = _SEGMENT_CACHE.get("k")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    ptr, order = receiver_segments(index, n_rows)
+    _SEGMENT_CACHE["k"] = (key, ptr, order, index)
+    return ptr, order
 
 
 def wigner_for(op: "MessagePackOp", edge_vec: torch.Tensor) -> torch.Tensor:
@@ -1076,6 +1115,31 @@ class MessagePackOp:
             st["rot_plan"] = rp
         return st["rot_plan"]
 
+    def rot2_supported(self) -> bool:
+        n_items = sum((int(ty.mul) + 31) // 32 for ty in self.tc_types_c)
+        return (self.rot_supported() and self.rot2_n[1] > 0 and n_items <= 64 and self.rot_dstride <= 480
+                and max(self.n_channels) < 0xFFFFF and self.rot2_rowstride <= self.irreps_out.dim)
+
+    def rot2_plan(self, device) -> "L.Rot2Plan":
+        st = self._device_state(device)
+        if "rot2_plan" not in st:
+            for name in ("passes", "pieces", "batches", "dsts"):
+                arr = getattr(self, f"rot2_{name}_c")
+                st[f"rot2_{name}"] = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+            p = L.Rot2Plan()
+            p.n_passes, p.n_pieces, p.n_batches, p.n_dsts = self.rot2_n
+            p.rowstride, p.n_slots = self.rot2_rowstride, len(self.irreps_out)
+            for t in range(len(self.irreps_out)):
+                ty = self.tc_types_c[t]
+                p.slot_l[t], p.slot_mul[t], p.slot_out_off[t] = ty.l, ty.mul, ty.out_off
+                for m in range(13):
+                    p.ccol[t][m] = int(self.rot2_ccol[t, m]) if m < self.rot2_ccol.shape[1] else -1
+            for name in ("passes", "pieces", "batches", "dsts"):
+                setattr(p, name, st[f"rot2_{name}"].data_ptr())
+                setattr(p, f"{name}_host", C.cast(getattr(self, f"rot2_{name}_c"), C.c_void_p).value)
+            st["rot2_plan"] = p
+        return st["rot2_plan"]
+
     def tc_supported(self) -> bool:
         return (max((m.mul for m in self.irreps_out), default=0) <= 64 and self.h2 % 16 == 0 and self.h2 <= 64
                 and self.h1 <= 64 and len(self.irreps_out) <= 32)
@@ -1137,26 +1201,67 @@ class MessagePackOp:
                 sh: torch.Tensor, rbf: torch.Tensor, n_edges: int, out: torch.Tensor,
                 out_index: Optional[torch.Tensor] = None, edge_vec: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
-        use_tc = (BACKEND in ("tc", "tcg", "rot")) and self.tc_supported()   # configs outside the tensor-core kernels' limits run on the fp32-FMA kernel
-        use_rot = use_tc and BACKEND == "rot" and edge_vec is not None and self.rot_supported()
+        backend = BACKEND
+        if backend in ("rot", "rot2") and (edge_vec is None or not (self.rot2_supported() if backend == "rot2" else self.rot_supported())):
+            # Outside the rotated-frame kernels' limits (multiplicity > 64, l > 6, ...) the fp32-FMA kernel is the only other
+            # backend inside the 1e-5 budget; the older tensor-core backends (tc / tcg, 9e-6 .. 1.1e-5)
+            # run only when asked for by name.
+            if not getattr(self, "_warned_fallback", False):
+                import warnings
+                warnings.warn("hamgnn_b200: this MessagePackBlock is outside the rotated-frame kernels' limits "
+                              "(multiplicity <= 64, l <= 6, radial MLP widths <= 64): running the fp32-FMA kernel "
+                              "(~8x slower, same accuracy)", RuntimeWarning, stacklevel=2)
+                self._warned_fallback = True
+            backend = "simt"
+        use_tc = (backend in ("tc", "tcg", "rot", "rot2")) and self.tc_supported()
+        use_rot = use_tc and backend == "rot"
+        use_rot2 = use_tc and backend == "rot2"
         st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
-        assert len(sources) == ns and len(rows) == ns
-        srcs = (C.c_void_p * 4)(*[L.f32c(s).data_ptr() for s in sources] + [None] * (4 - ns))
-        rws = (C.c_void_p * 4)(*[L.ptr(r) for r in rows] + [None] * (4 - ns))
+        if len(sources) != ns or len(rows) != ns:
+            raise L.HgbError(f"MessagePackOp.forward: expected {ns} sources, got {len(sources)}")
+        sources = [L.f32c(s) for s in sources]     # contiguous fp32 copies are kept alive until the launch is enqueued
         for s, d in zip(sources, self.src_dims):
-            assert s.shape[-1] == d and s.is_contiguous(), (s.shape, d)
+            if s.shape[-1] != d:
+                raise L.HgbError(f"MessagePackOp.forward: source row width {s.shape[-1]} != {d}")
+        srcs = (C.c_void_p * 4)(*[s.data_ptr() for s in sources] + [None] * (4 - ns))
+        rws = (C.c_void_p * 4)(*[L.ptr(r) for r in rows] + [None] * (4 - ns))
         prof = PROFILER
         if prof is not None:
             prof.begin(self, int(n_edges), out.device)
-        if use_rot:
+        if use_rot2:
+            nb = len(self.branches)
+            E = int(n_edges)
+            dev = out.device
+            dw = wigner_for(self, edge_vec)
+            chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
+            gstride = (max(self.n_channels) + 3) // 4 * 4
+            g_ws = workspace("gate", nb * chunk * gstride, dev)                                  # [nb][tile][gstride][128]
+            xp_ws = workspace("xp", (chunk // self.ROT_TILE) * self.rot_tile_stride, dev)
+            cp_ws = workspace("cp", max(1, E) * self.rot2_rowstride, dev)                        # aligned-frame messages of all edges
+            w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
+            nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
+            w3i = None
+            if GATE_BACKEND == "tc" and self.tc_w3img_off is not None:
+                w3i = (C.c_int32 * 2)(*(list(self.tc_w3img_off) + [0] * (2 - nb)))
+            if out_index is not None:
+                seg_ptr, seg_order = segments_for(out_index, out.shape[0])
+                n_rows = out.shape[0]
+            else:
+                seg_ptr = seg_order = None
+                n_rows = E
+            rc = L.load().hgb_msgpack_rot2_forward(C.byref(st["tc_plan"]), C.byref(self.rot_plan(dev)), C.byref(self.rot2_plan(dev)),
+                                                   srcs, rws, dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride,
+                                                   g_ws.data_ptr(), xp_ws.data_ptr(), cp_ws.data_ptr(), chunk, E, out.data_ptr(),
+                                                   L.ptr(seg_ptr), L.ptr(seg_order), n_rows, L.stream_ptr(dev))
+        elif use_rot:
             nb = len(self.branches)
             E = int(n_edges)
             dw = wigner_for(self, edge_vec)
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
-            g_ws = torch.empty(nb * chunk * gstride, device=out.device, dtype=torch.float32)   # [nb][tile][gstride][128]
-            xp_ws = torch.empty((chunk // self.ROT_TILE) * self.rot_tile_stride, device=out.device, dtype=torch.float32)
+            g_ws = workspace("gate", nb * chunk * gstride, out.device)   # [nb][tile][gstride][128]
+            xp_ws = workspace("xp", (chunk // self.ROT_TILE) * self.rot_tile_stride, out.device)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
             nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
             w3i = None
@@ -1166,7 +1271,7 @@ class MessagePackOp:
                                                   dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride, g_ws.data_ptr(),
                                                   xp_ws.data_ptr(), chunk, E, out.data_ptr(), L.ptr(out_index),
                                                   L.stream_ptr(out.device))
-        elif use_tc and BACKEND in ("tcg", "rot"):
+        elif use_tc and backend == "tcg":
             nb = len(self.branches)
             gstride = (max(self.n_channels) + 3) // 4 * 4
             g_ws = torch.empty(nb * int(n_edges) * gstride, device=out.device, dtype=torch.float32)
@@ -1188,7 +1293,8 @@ class MessagePackOp:
                                               int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
         if prof is not None:
             prof.end(out.device)
-        L.check(rc, "hgb_msgpack_rot_forward" if use_rot else ("hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward"))
+        L.check(rc, "hgb_msgpack_rot2_forward" if use_rot2 else "hgb_msgpack_rot_forward" if use_rot else
+                ("hgb_msgpack_tc_forward" if use_tc else "hgb_msgpack_forward"))
         return out
 
     def radial_gate(self, weights: dict, rbf: torch.Tensor, backend: str = "tc") -> torch.Tensor:

@@ -207,6 +207,81 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
                             float* out, const int64_t* out_index, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a5-a9, A-stationary form of the rotated frame ("rot2", the default message path).  Same mathematics and same call
+ * sites as hgb_msgpack_rot_forward (MessagePackBlock.forward hamgnn/nn/message_passing.py:191-231, ConvBlockE3's
+ * scatter-sum hamgnn/nn/convolution.py:147-149, PairInteractionBlock hamgnn/nn/interaction_blocks.py:133-164); the
+ * (path, m1) steps are regrouped so that every rotated input image is multiplied ONCE by the concatenated weights of all
+ * paths that consume it:
+ *   pass   = (output component m3, subset of output slots with sum of multiplicities <= 128): one CTA per (tile, pass),
+ *            accumulators C'[slot][m3][w] of the pass in shared memory, written as columns [out_col0, out_col0 + ncols)
+ *            of the per-edge aligned-frame row cp[e][rowstride];
+ *   piece  = image X'_{block, m1} x [W_p1 | W_p2 | ...] -> B[128 x ncols] (GEMM1), gate per 8-column batch,
+ *            per destination slot S = (B.g)[:, col0 : col0 + kcols] [L'_p1; L'_p2; ...] (GEMM2, K-concatenated);
+ *   unrotate: out[row][slot][w][k] = sum over the row's edge segment, sum_m3 D^{l3}_e[m3][k] cp[e][ccol[slot][m3] + w]
+ *            -- the receiver reduction is a serial sum over a receiver-sorted segment (deterministic, no atomics).
+ */
+typedef struct {
+  int32_t piece_begin, piece_end; /* pieces of the pass                                                    */
+  int32_t ncols;                  /* accumulator columns (<= 128)                                         */
+  int32_t out_col0;               /* first column of the pass in a cp row                                 */
+  int32_t batch_begin, batch_end; /* gate batches of the pass (contiguous over its pieces)                */
+  int32_t pad0, pad1;
+} hgb_rot2_pass_t;
+
+typedef struct {
+  int32_t a_off;       /* float offset of the image X'_{block, m1} inside a packed tile (hgb_rot_block_t layout)   */
+  int32_t w_off;       /* wbuf offset of the concatenated W: per chunk of 16 channels (hi | lo) [kc/4][ncols][4]   */
+  int32_t l_off;       /* wbuf offset of the piece's L' stacks (all destination groups, contiguous)                */
+  int32_t l_floats;    /* their size (<= 8192 floats)                                                              */
+  int32_t batch_begin; /* ncols / 8 gate batches                                                                   */
+  int32_t dst_begin;
+  int16_t kpad;        /* K of GEMM1 (multiple of 8)                                                               */
+  int16_t ncols;       /* N of GEMM1 (multiple of 16, <= 96)                                                       */
+  int16_t ndst;
+  int16_t pad;
+} hgb_rot2_piece_t;
+
+typedef struct {
+  int32_t meta;        /* gate column | branch << 20 | nvalid << 24; column 0xFFFFF: un-gated (g = 1)              */
+  float scale;         /* w3j(l1,l2,l3)[m1, 0, m3] * sqrt(2 l2 + 1) of the path                                    */
+} hgb_rot2_batch_t;
+
+typedef struct {
+  int16_t col0, kcols; /* B columns of the group = K of GEMM2 (multiples of 8)                                     */
+  int16_t mp;          /* N of GEMM2 (padded multiplicity of the slot, multiple of 16, <= 64)                      */
+  int16_t s_off;       /* column of the result inside the S buffer (64 columns)                                   */
+  int16_t acc_col0;    /* accumulator column of the slot inside the pass                                           */
+  int16_t mul;
+  int32_t l_rel;       /* offset of the group's (hi | lo) L' stack [kcols/4][mp][4] inside the piece's L' block    */
+} hgb_rot2_dst_t;
+
+typedef struct {
+  int32_t n_passes, n_pieces, n_batches, n_dsts;
+  int32_t rowstride;                  /* floats per cp row = sum over slots of mul * (2l+1)                        */
+  int32_t n_slots;
+  int32_t slot_l[32], slot_mul[32], slot_out_off[32];
+  int32_t ccol[32][13];               /* cp column of (slot, l3 + m3), -1: no contribution                        */
+  const hgb_rot2_pass_t* passes;      /* device */
+  const hgb_rot2_piece_t* pieces;     /* device */
+  const hgb_rot2_batch_t* batches;    /* device */
+  const hgb_rot2_dst_t* dsts;         /* device */
+  const hgb_rot2_pass_t* passes_host;
+  const hgb_rot2_piece_t* pieces_host;
+  const hgb_rot2_batch_t* batches_host;
+  const hgb_rot2_dst_t* dsts_host;
+} hgb_rot2_plan;
+
+/* g_ws / xp_ws: per-chunk workspaces as in hgb_msgpack_rot_forward; cp_ws: n_edges * rowstride floats (all edges).
+ * seg_ptr == NULL: out has n_edges rows, row e = message of edge e.  Otherwise out has n_out_rows rows and row i is
+ * the sum of the messages of edges seg_order[seg_ptr[i] .. seg_ptr[i+1]) in that order (see receiver_segments). */
+int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_plan* rot_host, const hgb_rot2_plan* rot2_host,
+                             const float* const* src_host, const int64_t* const* src_rows_host, const float* dw,
+                             const float* rbf, const int32_t* w3_off_host, const int32_t* nch_host,
+                             const int32_t* w3img_off_host, int32_t gstride, float* g_ws, float* xp_ws, float* cp_ws,
+                             int64_t chunk_edges, int64_t n_edges, float* out, const int64_t* seg_ptr,
+                             const int64_t* seg_order, int64_t n_out_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a10/a13 and the o3.Linear's: row-wise equivariant Linear -> Gate -> Linear (+residual) [-> Linear].
  * Replaces o3.Linear call sites (hamgnn/nn/convolution.py:112, interaction_blocks.py:126,306-309,
  * embeddings.py:286, toolbox/nequip/nn/_atomwise.py:51, hamgnn_output.py:49), ResidualBlock.forward

@@ -1,0 +1,116 @@
+"""GPU parity tests of the A-stationary rotated-frame message path ('rot2', the default backend) through the C ABI
+(hgb_msgpack_rot2_forward): the three fused-message forms on random inputs vs the oracle modules (message rows,
+receiver-reduced aggregate, edge update with the direct skip path, embedding TP), edge chunking with ragged last tiles,
+bit-reproducibility of the segmented receiver reduction (north_star: no atomics in the scatter), and the full forward.
+Tolerance 1e-5 relative (max|a-b| / max|b| per tensor), oracle evaluated in fp64 on the same fp32 weights."""
+import pytest
+import torch
+
+from hamgnn_b200 import graph_data as gd
+from hamgnn_b200 import plan as P
+from hgb_testlib import DEFAULT_CFG, SMALL_CFG, build_pair, oracle_forward, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _graphs(which):
+    if which == "si":
+        return [gd.bulk_silicon()]
+    return [gd.bulk_silicon(), gd.graphene(rep=(2, 2, 1), seed=1), gd.mos2_monolayer(seed=2)]
+
+
+@pytest.fixture(scope="module", params=[("small", "mixed"), ("default", "si")])
+def setup(request):
+    cfg_name, gname = request.param
+    cfg = SMALL_CFG if cfg_name == "small" else DEFAULT_CFG
+    pre, out, opre, oout = build_pair(cfg, nao_max=19, add_H0=False)
+    batch = gd.Batch.from_data_list(_graphs(gname))
+    d, rep, res = oracle_forward(opre, oout, batch)
+    dev = torch.device("cuda:0")
+    pre.to(dev)
+    out.to(dev)
+    return cfg_name, pre, out, opre, oout, batch, d, rep, res, dev
+
+
+@pytest.mark.parametrize("chunk", [None, 128, 384])
+def test_single_message_calls(setup, chunk):
+    cfg_name, pre, out, opre, oout, batch, d, rep, res, dev = setup
+    if chunk is not None and cfg_name == "default":
+        pytest.skip("chunking is exercised on the small model")
+    assert P.BACKEND == "rot2"
+    torch.manual_seed(11)
+    E, N, D = batch.edge_index.shape[1], batch.num_nodes, pre.irreps_node_features.dim
+    x, e = torch.randn(N, D), torch.randn(E, D)
+    s, r = batch.edge_index
+    dd = {"edge_index": batch.edge_index, "node_features": x.double(), "edge_features": e.double(),
+          "edge_attrs": d["edge_attrs"], "edge_embedding": d["edge_embedding"]}
+    with torch.no_grad():
+        ref_pair = opre.pair_interactions[1](dict(dd))
+        ref_msg = opre.convolutions[0].conv_tp(x.double()[s], x.double()[r], e.double(), d["edge_attrs"], d["edge_embedding"])
+        ref_agg = torch.zeros(N, D, dtype=torch.float64).index_add_(0, r, ref_msg)
+        onehot = torch.nn.functional.one_hot(batch.z, opre.num_types).double()
+        dd2 = dict(dd); dd2["node_features"] = onehot
+        ref_emb = opre.pair_embedding(dd2)
+    sh, rbf, vec = d["edge_attrs"].float().to(dev), d["edge_embedding"].float().to(dev), d["edge_vectors"].float().to(dev)
+    xd, ed, sd, rd = x.to(dev), e.to(dev), s.to(dev), r.to(dev)
+    old = P.ROT_CHUNK_EDGES
+    try:
+        if chunk is not None:
+            P.ROT_CHUNK_EDGES = chunk
+        cb = pre.convolutions[0].conv_tp
+        assert cb.op.rot2_supported()
+        msg = torch.full((E, D), float("nan"), device=dev)
+        cb.op.forward(cb.weights(), [xd, xd, ed], [sd, rd, None], sh, rbf, E, msg, edge_vec=vec)
+        aggs = []
+        for _ in range(2):
+            agg = torch.full((N, D), float("nan"), device=dev)       # the segmented reduction overwrites every row
+            cb.op.forward(cb.weights(), [xd, xd, ed], [sd, rd, None], sh, rbf, E, agg, out_index=rd, edge_vec=vec)
+            aggs.append(agg)
+        b = gd.Batch(**batch.to_dict()).to(dev)
+        b["node_features"], b["edge_features"], b["edge_attrs"], b["edge_embedding"], b["edge_vectors"] = xd, ed, sh, rbf, vec
+        pair = pre.pair_interactions[1](b)
+        b2 = gd.Batch(**batch.to_dict()).to(dev)
+        b2["node_features"], b2["edge_attrs"], b2["edge_embedding"], b2["edge_vectors"] = onehot.float().to(dev), sh, rbf, vec
+        emb = pre.pair_embedding(b2)
+        torch.cuda.synchronize()
+    finally:
+        P.ROT_CHUNK_EDGES = old
+    em, ea, ep, ee = (rel_err(msg.cpu(), ref_msg), rel_err(aggs[0].cpu(), ref_agg), rel_err(pair.cpu(), ref_pair),
+                      rel_err(emb.cpu(), ref_emb))
+    print(f"[{cfg_name} rot2 chunk={chunk}] rel err message {em:.2e} aggregate {ea:.2e} edge update {ep:.2e} embedding {ee:.2e}")
+    assert em < TOL and ea < TOL and ep < TOL and ee < TOL
+    assert torch.equal(aggs[0], aggs[1]), "the receiver reduction must be bit-reproducible"
+    # ... and equals the sum of the message rows per receiver (different association: tolerance, not bits)
+    want = torch.zeros(N, D, device=dev).index_add_(0, rd, msg)
+    assert rel_err(aggs[0].cpu(), want.cpu()) < 2e-6
+
+
+@pytest.mark.parametrize("cfg_name,gname", [("small", "mixed"), ("default", "si")])
+def test_full_forward_rot2_vs_oracle_and_rot(cfg_name, gname):
+    cfg = SMALL_CFG if cfg_name == "small" else DEFAULT_CFG
+    pre, out, opre, oout = build_pair(cfg, nao_max=19, add_H0=False)
+    batch = gd.Batch.from_data_list(_graphs(gname))
+    d, rep, res = oracle_forward(opre, oout, batch)
+    dev = torch.device("cuda:0")
+    pre.to(dev)
+    out.to(dev)
+    errs, H = {}, {}
+    old = P.BACKEND
+    try:
+        for backend in ("rot", "rot2", "rot2"):
+            P.BACKEND = backend
+            b = gd.Batch(**batch.to_dict()).to(dev)
+            with torch.no_grad():
+                r = pre(b)
+                o = out(b, r)
+            torch.cuda.synchronize()
+            if backend in H:
+                assert torch.equal(H[backend], o["hamiltonian"]), "rot2 forward must be bit-reproducible run to run"
+            H[backend] = o["hamiltonian"]
+            errs[backend] = (rel_err(r["node_attr"].cpu(), rep["node_attr"]), rel_err(r["edge_attr"].cpu(), rep["edge_attr"]),
+                             rel_err(o["hamiltonian"].cpu(), res["hamiltonian"]))
+            print(f"[{cfg_name} {gname} {backend}] rel err node {errs[backend][0]:.2e} edge {errs[backend][1]:.2e} H {errs[backend][2]:.2e}")
+    finally:
+        P.BACKEND = old
+    assert max(errs["rot2"]) < TOL, errs
