@@ -1,0 +1,69 @@
+// Micro-probe of tcgen05.mma.kind::tf32 issue / completion cost on sm_100a (diagnosis tool, not on the product path):
+// one CTA issues `count` MMAs (M = 128, N = n, K = 8) from one thread, round-robin over `ndest` accumulators,
+// A from shared memory (ts = 0) or from TMEM (ts = 1), and reports the cycles until the commit barrier fires.
+#include "hgb_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+struct ProbeArgs {
+  int n, count, ndest, ts, same_ab;
+  long long* out;   // [0] issue cycles, [1] total cycles until completion
+};
+
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeArgs a) {
+  extern __shared__ __align__(128) float smem[];   // A: 2 x [2 slabs][128][4], B: [2 slabs][256][4] x 2
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384; i += 128) smem[i] = 0.f;
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32_m128(a.n);
+    const uint32_t dhi = tc::smem_desc_hi(128);
+    const uint32_t sa = tc::smem_u32(smem), sb = sa + 16384;
+    const uint32_t ah = tc::smem_desc_lo(sa, 128 * 16), bh = tc::smem_desc_lo(sb, (uint32_t)a.n * 16);
+    const long long t0 = clock64();
+    const uint32_t dmask = (uint32_t)(a.ndest - 1);   // ndest is a power of two
+    const uint64_t da0 = tc::desc64(ah, dhi), db0 = tc::desc64(bh, dhi);
+    const uint64_t da1 = tc::desc64(ah + (a.same_ab ? 0u : 512u), dhi), db1 = tc::desc64(bh + (a.same_ab ? 0u : 512u), dhi);
+    if (a.ts) {
+#pragma unroll 4
+      for (int i = 0; i < a.count; i += 2) {
+        tc::mma_tf32_ts(tmem + ((uint32_t)i & dmask) * (uint32_t)a.n, tmem + 384, db0, idesc, (uint32_t)(i >= a.ndest));
+        tc::mma_tf32_ts(tmem + ((uint32_t)(i + 1) & dmask) * (uint32_t)a.n, tmem + 392, db1, idesc, (uint32_t)(i + 1 >= a.ndest));
+      }
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < a.count; i += 2) {
+        tc::mma_tf32(tmem + ((uint32_t)i & dmask) * (uint32_t)a.n, da0, db0, idesc, (uint32_t)(i >= a.ndest));
+        tc::mma_tf32(tmem + ((uint32_t)(i + 1) & dmask) * (uint32_t)a.n, da1, db1, idesc, (uint32_t)(i + 1 >= a.ndest));
+      }
+    }
+    const long long t1 = clock64();
+    tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    a.out[0] = t1 - t0;
+    a.out[1] = t2 - t0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+}  // namespace
+
+extern "C" int hgb_mma_probe(int32_t n, int32_t count, int32_t ndest, int32_t ts, int32_t same_ab, long long* out_dev, void* stream) {
+  HGB_DEVICE_GUARD(out_dev);
+  HGB_CHECK_ARG(out_dev && n >= 16 && n % 16 == 0 && n <= 256 && ndest >= 1 && ndest * n <= 384 && count >= 1, "hgb_mma_probe: bad arguments");
+  ProbeArgs a{n, count, ndest, ts, same_ab, out_dev};
+  HGB_CUDA_OK(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  mma_probe_kernel<<<1, 128, 65536, (cudaStream_t)stream>>>(a);
+  HGB_LAUNCH_OK("mma_probe_kernel");
+  return 0;
+}

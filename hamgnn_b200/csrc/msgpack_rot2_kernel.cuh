@@ -9,10 +9,11 @@
 //
 //   CTA   = (tile of 128 edges, pass); pass = (output component m3, output slots with <= 128 accumulator columns)
 //   piece = one image X'_{block, m1} x the CONCATENATED weights of every path of the pass that reads it
-//             GEMM1  B[n&1][128 x ncols] = X' [W_p1 | W_p2 | ...]          warp 9, A / W chunks of 16 channels from the TMA ring
-//             gate   B <- hi(B * s_p g_p), GL[n&1] <- lo                    warps 0-3, thread = edge = TMEM lane, 8 columns a batch
-//             GEMM2  S[n&1][s_off ..] = (B.g)[:, col0 : col0 + kcols] L'stack   warp 10, one K-concatenated chain per destination slot
-//             acc    C'[acc_col0 + w] += S[s_off + w]                        warps 4-7, fp32 round-to-nearest in shared memory
+//             GEMM1  B[n&1][128 x ncols] = X' [W_p1 | W_p2 | ...]          warp 13, A / W chunks of 16 channels from the TMA ring (warp 12)
+//             gate   B <- hi(B * g_p), GL[n&1] <- lo                        warps 0-7 (two per TMEM lane quadrant, alternate 8-column batches);
+//                                                                           the w3j scale of the step is folded into the piece's W image
+//             GEMM2  S[n&1][s_off ..] = (B.g)[:, col0 : col0 + kcols] L'stack   warp 14, one K-concatenated chain per destination slot
+//             acc    C'[acc_col0 + w] += S[s_off + w]                        warps 8-11, fp32 round-to-nearest in shared memory
 //   end   : the pass's columns of the aligned-frame row cp[e][.] are stored (coalesced), unrotate_kernel finishes.
 //
 // ~700 pieces instead of ~2 800 steps, mean N 62 instead of 16-32, every image fetched once per pass: 15 MB of A per tile and
@@ -46,7 +47,9 @@ constexpr int A_LO = KC2 * TILE;                       // float offset of the A 
 constexpr int W_AT = 2 * KC2 * TILE;                   // float offset of the W chunk inside a stage
 constexpr int STG = 2 * KC2 * TILE + 2 * KC2 * NB;     // floats per ring stage (28 KB)
 constexpr int LBUF = 8192;                             // floats per L' buffer (R2_LMAX_FLOATS)
-constexpr int NTHR = 352;                              // warps 0-3 gate, 4-7 accumulate, 8 TMA, 9 GEMM1, 10 GEMM2
+constexpr int NTHR = 480;                              // warps 0-7 gate, 8-11 accumulate, 12 TMA, 13 GEMM1, 14 GEMM2
+constexpr int W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
+constexpr int HB = NB / 16;                            // gate batches per gate warp and piece (batches 2k + h)
 constexpr uint32_t TB = 0, TGL = 2 * NB, TS = 4 * NB;  // TMEM columns
 constexpr size_t SMEM_BYTES = (size_t)(NST * STG + 2 * LBUF + ACC_COLS * ACC_LD) * sizeof(float);
 
@@ -64,7 +67,16 @@ struct Args {
   int64_t e_lo, n_chunk;
   float* cp;            // aligned-frame messages of ALL edges [E][rowstride]
   int rowstride;
+  long long* trace;     // optional (HGB_ROT2_TRACE): clock64 stamps of CTA trace_cta, [role][piece][2]
+  int trace_cta, trace_pieces;
 };
+
+// role: 0 TMA, 1 GEMM1, 2 gate (warp 0), 3 GEMM2, 4 accumulate (warp 8)
+#define R2_TRACE(role, n, k)                                                                                         \
+  do {                                                                                                               \
+    if (a.trace != nullptr && (int)blockIdx.x == a.trace_cta && (threadIdx.x & 31) == 0 && (n) < a.trace_pieces)     \
+      a.trace[((role) * a.trace_pieces + (n)) * 2 + (k)] = clock64();                                                \
+  } while (0)
 
 struct PieceRec {   // hgb_rot2_piece_t as two 16-byte words
   int a_off, w_off, l_off, l_floats, batch_begin, dst_begin, kpad, ncols, ndst;
@@ -96,10 +108,10 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   const hgb_rot2_pass_t ps = a.passes[pass];
 
   if (tid == 0) {
-    for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], ((i >= 10 && i < 12) || i >= 14) ? 4 : 1);   // gfull / sfree: one arrival per warp
+    for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], (i >= 10 && i < 12) ? 8 : (i >= 14 ? 4 : 1));   // gfull / sfree: one arrival per warp
     tc::mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc_dyn(&tmem_slot, 512);
+  if (warp == W_MMA1) tmem_alloc_dyn(&tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -108,34 +120,30 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   const uint32_t dhi = tc::smem_desc_hi(128);
   const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      const float* xt = a.xp + (size_t)tile * a.tile_stride;
-      const float* gt = a.g + (size_t)tile * a.gstride * TILE;
-      // gate blocks of a piece: nvalid columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 one
-      // piece ahead of the gate warps (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident)
-      auto prefetch_gate = [&](int qi) {
-        if (qi >= ps.piece_end) return;
-        const int b0 = a.pieces[qi].batch_begin, nb = a.pieces[qi].ncols >> 3;
-        for (int k = 0; k < nb; ++k) {
-          const uint32_t meta = (uint32_t)__ldg(&a.batches[b0 + k].meta);
-          const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu, nv = (meta >> 24) & 0xFu;
-          if (nv != 0 && col != 0xFFFFFu) bulk_prefetch_l2(gt + (size_t)br * g_bstride + (size_t)col * TILE, nv * TILE * 4u);
-        }
-      };
-      prefetch_gate(ps.piece_begin);
-      int n = 0, c_all = 0;
-      for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
-        const PieceRec pc = load_piece(a.pieces + qi);
-        prefetch_gate(qi + 1);
-        {
-          const int lb = n & 1;
-          if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read this L' buffer
-          const uint32_t lbytes = (uint32_t)pc.l_floats * 4u;
-          expect_tx_a(B_LFULL + 8 * lb, lbytes);
-          bulk_g2s_a(lbuf0 + (uint32_t)(lb * LBUF) * 4u, wbuf + pc.l_off, lbytes, B_LFULL + 8 * lb);
-        }
+    const float* xt = a.xp + (size_t)tile * a.tile_stride;
+    const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+    // gate blocks of a piece: nvalid columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 one
+    // piece ahead of the gate warps (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident).
+    // Lane k takes batch k, so the table reads of a piece cost one load latency, not twelve.
+    auto prefetch_gate = [&](int qi) {
+      if (qi >= ps.piece_end) return;
+      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
+      const int b0 = (int)w1.x, nb = (int)(w1.z >> 16) >> 3;
+      if (lane < nb) {
+        const uint32_t meta = (uint32_t)__ldg(&a.batches[b0 + lane].meta);
+        const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu, nv = (meta >> 24) & 0xFu;
+        if (nv != 0 && col != 0xFFFFFu) bulk_prefetch_l2(gt + (size_t)br * g_bstride + (size_t)col * TILE, nv * TILE * 4u);
+      }
+    };
+    prefetch_gate(ps.piece_begin);
+    int n = 0, c_all = 0;
+    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+      const PieceRec pc = load_piece(a.pieces + qi);
+      prefetch_gate(qi + 1);
+      if (lane == 0) {
+        R2_TRACE(0, n, 0);
         for (int u0 = 0, c = 0; u0 < pc.kpad; u0 += KC2, ++c, ++c_all) {
           const int kc = min(KC2, pc.kpad - u0), s = c_all % NST;
           if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
@@ -149,16 +157,26 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
           bulk_g2s_a(sa + A_LO * 4, ahi + (size_t)kc32 * TILE, ab, B_FULL + 8 * s);
           bulk_g2s_a(sa + W_AT * 4, wbuf + pc.w_off + (size_t)c * (2 * KC2 * pc.ncols), wb, B_FULL + 8 * s);
         }
+        // the L' stacks are needed last (GEMM2 of this piece): issued after the operands of GEMM1
+        const int lb = n & 1;
+        if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read this L' buffer
+        const uint32_t lbytes = (uint32_t)pc.l_floats * 4u;
+        expect_tx_a(B_LFULL + 8 * lb, lbytes);
+        bulk_g2s_a(lbuf0 + (uint32_t)(lb * LBUF) * 4u, wbuf + pc.l_off, lbytes, B_LFULL + 8 * lb);
+        R2_TRACE(0, n, 1);
+      } else {
+        for (int u0 = 0; u0 < pc.kpad; u0 += KC2) ++c_all;
       }
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == W_MMA1) {
     // =============================== GEMM1 issuer ===============================
     const uint32_t lbo_a = TILE * 16, astep = (2 * lbo_a) >> 4;
     int n = 0, c_all = 0;
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
       const PieceRec pc = load_piece(a.pieces + qi);
       if (n >= 2) warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read B / GL [n&1]
+      R2_TRACE(1, n, 0);
       const uint32_t dcol = tmem + TB + (uint32_t)((n & 1) * NB);
       const uint32_t idesc = tc::idesc_tf32_m128(pc.ncols);
       const uint32_t lbo_n = (uint32_t)pc.ncols * 16, bstep = (2 * lbo_n) >> 4;
@@ -182,24 +200,30 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
         }
         __syncwarp();
       }
+      R2_TRACE(1, n, 1);
     }
-  } else if (warp == 10) {
+  } else if (warp == W_MMA2) {
     // =============================== GEMM2 issuer ===============================
     int n = 0;
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
-      const PieceRec pc = load_piece(a.pieces + qi);
+      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
+      const int dst_begin = (int)w1.y, ndst = (int)(w1.w & 0xffffu);
+      uint4 drec = make_uint4(0, 0, 0, 0);   // lane d holds destination group d of the piece
+      if (lane < ndst) drec = __ldg(reinterpret_cast<const uint4*>(a.dsts + dst_begin + lane));
       const int nb = n & 1;
       const uint32_t par = (uint32_t)((n >> 1) & 1);
       if (n >= 2) warp_wait_a(B_SFREE + 8 * nb, par ^ 1u);   // the accumulate warps have drained S[n&1] of piece n-2
       warp_wait_a(B_LFULL + 8 * nb, par);
       warp_wait_a(B_GFULL + 8 * nb, par);
       tc::fence_after_sync();
-      if (elect_one()) {
-        const uint32_t bq = tmem + TB + (uint32_t)(nb * NB), gl = tmem + TGL + (uint32_t)(nb * NB), sc0 = tmem + TS + (uint32_t)(nb * SW);
-        const uint32_t lb = lbuf0 + (uint32_t)(nb * LBUF) * 4u;
-        for (int di = 0; di < pc.ndst; ++di) {
-          const uint4 dw = __ldg(reinterpret_cast<const uint4*>(a.dsts + pc.dst_begin + di));
-          const uint32_t col0 = dw.x & 0xffffu, kcols = dw.x >> 16, mp = dw.y & 0xffffu, s_off = dw.y >> 16, l_rel = dw.w;
+      R2_TRACE(3, n, 0);
+      const uint32_t bq = tmem + TB + (uint32_t)(nb * NB), gl = tmem + TGL + (uint32_t)(nb * NB), sc0 = tmem + TS + (uint32_t)(nb * SW);
+      const uint32_t lb = lbuf0 + (uint32_t)(nb * LBUF) * 4u;
+      for (int di = 0; di < ndst; ++di) {
+        const uint32_t dx = __shfl_sync(0xffffffffu, drec.x, di), dy = __shfl_sync(0xffffffffu, drec.y, di),
+                       dwv = __shfl_sync(0xffffffffu, drec.w, di);
+        if (elect_one()) {
+          const uint32_t col0 = dx & 0xffffu, kcols = dx >> 16, mp = dy & 0xffffu, s_off = dy >> 16, l_rel = dwv;
           const uint32_t idesc = tc::idesc_tf32_m128((int)mp);
           const uint32_t lbo_l = mp * 16, lstep = (2 * lbo_l) >> 4;
           const uint32_t lh = tc::smem_desc_lo(lb + l_rel * 4u, lbo_l), ll = lh + ((kcols * mp * 4u) >> 4);
@@ -210,29 +234,36 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
             tc::mma_tf32_ts(sc, bq + col0 + k8 * 8, bl, idesc, 1);
             tc::mma_tf32_ts(sc, bq + col0 + k8 * 8, bh, idesc, 1);
           }
+          if (di == ndst - 1) commit_a(B_S2 + 8 * nb);
         }
-        commit_a(B_S2 + 8 * nb);
+        __syncwarp();
       }
-      __syncwarp();
+      R2_TRACE(3, n, 1);
     }
-  } else if (warp < 4) {
-    // =============================== gate: B <- hi(B * s g), GL <- lo  (thread = edge = TMEM lane) ===============================
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int64_t el = (int64_t)tile * TILE + tid;
-    const bool live = el < a.n_chunk;
-    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);   // column c of this edge: grow[c * TILE]
-    constexpr int DEPTH = 4;          // gate batches in flight (register ring): L2 latency / ~60 cycles per batch
-    float gv[DEPTH][8], gs[DEPTH];
-    const int b_end = ps.batch_end;
-    // gate values of batch bb -> ring slot u (compile-time after unrolling); un-gated batches get 1, padding columns 0
-    auto issue = [&](float (&gq)[8], float& sq, int bb) {
-      if (bb >= b_end) return;
-      const int2 bt = __ldg(reinterpret_cast<const int2*>(a.batches + bb));
-      const uint32_t meta = (uint32_t)bt.x;
+  } else if (warp < 8) {
+    // =============================== gate: B <- hi(B * g), GL <- lo  (thread = edge = TMEM lane) ===============================
+    // Two warps per lane quadrant; warp half h takes the 8-column batches 2k + h of every piece.  The gate values of piece
+    // n + 1 are loaded into the registers of batch k as soon as batch k of piece n is done, so the global-load latency is
+    // hidden behind a whole piece; the three TMEM loads of a group are issued together.
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int zt = q * 32 + lane;
+    const bool live = (int64_t)tile * TILE + zt < a.n_chunk;
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? zt : 0);   // column c of this edge: grow[c * TILE]
+    float gv[HB][8];
+    // lane k <- descriptor of this warp's k-th batch of piece qi; nbw = number of such batches
+    auto fetch_meta = [&](int qi, int& nbw) -> uint32_t {
+      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
+      const int nb = (int)(w1.z >> 16) >> 3;
+      nbw = (nb - h + 1) >> 1;
+      uint32_t m = 0xFFFFFu;   // nvalid = 0
+      if (lane < nbw) m = (uint32_t)__ldg(&a.batches[(int)w1.x + 2 * lane + h].meta);
+      return m;
+    };
+    auto issue = [&](float (&gq)[8], uint32_t meta) {
       const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu;
       const int nv = (int)((meta >> 24) & 0xFu);
-      sq = __int_as_float(bt.y);
-      if (col == 0xFFFFFu) {
+      if (col == 0xFFFFFu) {   // un-gated (direct Linear) or padding columns
 #pragma unroll
         for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? 1.f : 0.f;
       } else {
@@ -241,55 +272,60 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
         for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? __ldg(gp + j * TILE) : 0.f;   // warp-uniform predicate; 128 contiguous bytes per warp
       }
     };
-    int n = 0, qi = ps.piece_begin;
-    PieceRec pc = load_piece(a.pieces + qi);
-    int pb0 = pc.batch_begin, pb1 = pb0 + (pc.ncols >> 3);
+    int nbw = 0;
+    uint32_t mt = fetch_meta(ps.piece_begin, nbw);
 #pragma unroll
-    for (int u = 0; u < DEPTH; ++u) issue(gv[u], gs[u], ps.batch_begin + u);
-    warp_wait_a(B_BFULL, 0);
-    tc::fence_after_sync();
-    for (int b = ps.batch_begin; b < b_end; b += DEPTH) {
+    for (int k = 0; k < HB; ++k) {
+      const uint32_t m = __shfl_sync(0xffffffffu, mt, k);
+      if (k < nbw) issue(gv[k], m);
+    }
+    int n = 0;
+    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+      int nbw_next = 0;
+      uint32_t mt_next = 0xFFFFFu;
+      if (qi + 1 < ps.piece_end) mt_next = fetch_meta(qi + 1, nbw_next);
+      warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
+      tc::fence_after_sync();
+      if (warp == 0) R2_TRACE(2, n, 0);
+      const uint32_t bq0 = tmem + lane_base + TB + (uint32_t)((n & 1) * NB) + (uint32_t)(h * 8);
+      const uint32_t gl0 = tmem + lane_base + TGL + (uint32_t)((n & 1) * NB) + (uint32_t)(h * 8);
 #pragma unroll
-      for (int u = 0; u < DEPTH; ++u) {
-        const int bb = b + u;
-        if (bb < b_end) {
-          if (bb == pb1) {   // piece n is gated: hand it to GEMM2, move to the next piece
-            tc::tmem_st_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
-            ++n; ++qi;
-            pc = load_piece(a.pieces + qi);
-            pb0 = bb; pb1 = bb + (pc.ncols >> 3);
-            warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
-            tc::fence_after_sync();
+      for (int k0 = 0; k0 < HB; k0 += 3) {
+        uint32_t rb[3][8];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (k0 + i < nbw) tc::tmem_ld8(bq0 + (uint32_t)((k0 + i) * 16), rb[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (k0 + i < nbw) {
+            tc::tmem_ld_wait8(rb[i]);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float hh, ll;
+              tc::split_tf32(__uint_as_float(rb[i][j]) * gv[k0 + i][j], hh, ll);
+              hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(ll);
+            }
+            tc::tmem_st8(bq0 + (uint32_t)((k0 + i) * 16), hi);
+            tc::tmem_st8(gl0 + (uint32_t)((k0 + i) * 16), lo);
           }
-          const uint32_t col = (uint32_t)((bb - pb0) * 8);
-          const uint32_t bq = tmem + lane_base + TB + (uint32_t)((n & 1) * NB) + col;
-          const uint32_t gl = tmem + lane_base + TGL + (uint32_t)((n & 1) * NB) + col;
-          uint32_t rb[8], hi[8], lo[8];
-          tc::tmem_ld8(bq, rb);
-          tc::tmem_ld_wait8(rb);
-          const float sc = gs[u];
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float h, l;
-            tc::split_tf32(__uint_as_float(rb[j]) * (gv[u][j] * sc), h, l);
-            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
-          }
-          tc::tmem_st8(bq, hi);
-          tc::tmem_st8(gl, lo);
-          issue(gv[u], gs[u], bb + DEPTH);
+        for (int i = 0; i < 3; ++i) {
+          const uint32_t m = __shfl_sync(0xffffffffu, mt_next, k0 + i);
+          if (k0 + i < nbw_next) issue(gv[k0 + i], m);
         }
       }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
+      if (warp == 0) R2_TRACE(2, n, 1);
+      nbw = nbw_next;
     }
-    tc::tmem_st_wait();
-    tc::fence_before_sync();
-    __syncwarp();
-    if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
   } else {
     // =============================== accumulate: C' += S, finally store the pass's columns of cp ===============================
-    const int q = warp - 4, zl = tid - 128;
+    const int q = warp - 8, zl = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float* acc = accs + zl;
     for (int c = 0; c < ps.ncols; ++c) acc[c * ACC_LD] = 0.f;
@@ -297,25 +333,36 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
       const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
       const int dst_begin = (int)w1.y, ndst = (int)(w1.w & 0xffffu);
+      uint4 drec = make_uint4(0, 0, 0, 0);   // lane d holds destination group d of the piece
+      if (lane < ndst) drec = __ldg(reinterpret_cast<const uint4*>(a.dsts + dst_begin + lane));
       warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
+      if (q == 0) R2_TRACE(4, n, 0);
       const uint32_t sc0 = tmem + lane_base + TS + (uint32_t)((n & 1) * SW);
       for (int di = 0; di < ndst; ++di) {
-        const uint4 dw = __ldg(reinterpret_cast<const uint4*>(a.dsts + dst_begin + di));
-        const int s_off = (int)(dw.y >> 16), acc_col0 = (int)(dw.z & 0xffffu), mul = (int)(dw.z >> 16);
+        const uint32_t dy = __shfl_sync(0xffffffffu, drec.y, di), dz = __shfl_sync(0xffffffffu, drec.z, di);
+        const int s_off = (int)(dy >> 16), acc_col0 = (int)(dz & 0xffffu), mul = (int)(dz >> 16);
         float* ap = acc + acc_col0 * ACC_LD;
-        for (int c0 = 0; c0 < mul; c0 += 8) {
-          uint32_t rs[8];
-          tc::tmem_ld8(sc0 + (uint32_t)(s_off + c0), rs);
-          tc::tmem_ld_wait8(rs);
+        for (int c0 = 0; c0 < mul; c0 += 32) {   // <= 32 columns in flight per wait
+          uint32_t rs[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (c0 + j < mul) ap[(c0 + j) * ACC_LD] += __uint_as_float(rs[j]);
+          for (int i = 0; i < 4; ++i)
+            if (c0 + 8 * i < mul) tc::tmem_ld8(sc0 + (uint32_t)(s_off + c0 + 8 * i), rs[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 8 * i < mul) {
+              tc::tmem_ld_wait8(rs[i]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (c0 + 8 * i + j < mul) ap[(c0 + 8 * i + j) * ACC_LD] += __uint_as_float(rs[i][j]);
+            }
+          }
         }
       }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) arrive_a(B_SFREE + 8 * (n & 1));
+      if (q == 0) R2_TRACE(4, n, 1);
     }
     __syncwarp();
     // warp q owns edges [32 q, 32 q + 32) of the tile: rows of cp, the pass's columns are contiguous
@@ -329,7 +376,7 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc_dyn(tmem, 512);
+  if (warp == W_MMA1) tmem_dealloc_dyn(tmem, 512);
 }
 
 // ===================================================================================================== unrotate (+ segment sum)

@@ -7,6 +7,7 @@
 //
 // Everything else (tables, packing, A-operand generation, 3xTF32 split, GEMM1 / GEMM2 structure) is identical to
 // msgpack_tc.cu.  Price: 2 x 4 B x n_channels (28.7 KB) of extra HBM write + read per message.
+#include <stdlib.h>
 #include "hgb_common.cuh"
 #include "tc_common.cuh"
 #include "msgpack_tc_helpers.cuh"
@@ -975,8 +976,45 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
     rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
     HGB_LAUNCH_OK("rotate_pack_kernel");
     ka.e_lo = e_lo; ka.n_chunk = n;
+    // HGB_ROT2_TRACE=<file>: per-role clock64 stamps of one CTA (pass HGB_ROT2_TRACE_PASS of tile 0) appended to <file>;
+    // a diagnosis aid (one extra sync per launch), off unless the variable is set
+    const char* trace_path = getenv("HGB_ROT2_TRACE");
+    long long* d_trace = nullptr;
+    const int trace_pieces = 128;
+    if (trace_path && trace_path[0]) {
+      const char* tp = getenv("HGB_ROT2_TRACE_PASS");
+      ka.trace_cta = tp ? atoi(tp) : 5;
+      if (ka.trace_cta >= r2->n_passes) ka.trace_cta = r2->n_passes - 1;
+      ka.trace_pieces = trace_pieces;
+      HGB_CUDA_OK(cudaMalloc(&d_trace, sizeof(long long) * 5 * trace_pieces * 2));
+      HGB_CUDA_OK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 5 * trace_pieces * 2, st));
+      ka.trace = d_trace;
+    }
     rot2::msgpack_rot2_kernel<<<(unsigned)(n_tiles * r2->n_passes), rot2::NTHR, rot2::SMEM_BYTES, st>>>(ka);
     HGB_LAUNCH_OK("msgpack_rot2_kernel");
+    if (d_trace) {
+      static long long h_trace[5 * 128 * 2];
+      HGB_CUDA_OK(cudaStreamSynchronize(st));
+      HGB_CUDA_OK(cudaMemcpy(h_trace, d_trace, sizeof(h_trace), cudaMemcpyDeviceToHost));
+      cudaFree(d_trace);
+      ka.trace = nullptr;
+      FILE* f = fopen(trace_path, "a");
+      if (f) {
+        const hgb_rot2_pass_t& tps = r2->passes_host[ka.trace_cta];
+        fprintf(f, "# launch n_tiles %d pass %d pieces %d\n", n_tiles, ka.trace_cta, tps.piece_end - tps.piece_begin);
+        long long t0 = 0;
+        for (int i = 0; i < 5 * trace_pieces * 2; ++i)
+          if (h_trace[i] && (!t0 || h_trace[i] < t0)) t0 = h_trace[i];
+        for (int n2 = 0; n2 < trace_pieces && n2 < tps.piece_end - tps.piece_begin; ++n2) {
+          const hgb_rot2_piece_t& pc = r2->pieces_host[tps.piece_begin + n2];
+          fprintf(f, "%d kpad %d ncols %d ndst %d |", n2, pc.kpad, pc.ncols, pc.ndst);
+          for (int role = 0; role < 5; ++role)
+            fprintf(f, " %lld %lld |", h_trace[(role * trace_pieces + n2) * 2] - t0, h_trace[(role * trace_pieces + n2) * 2 + 1] - t0);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
   }
   if (n_out_rows > 0) {
     rot2::unrotate_kernel<<<(unsigned)n_out_rows, (unsigned)(32 * ua.n_warps), 0, st>>>(ua);

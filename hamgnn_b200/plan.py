@@ -966,7 +966,7 @@ class MessagePackOp:
         def w_block(bi, groups, ncols):
             """(hi | lo) images of the concatenated W of a piece, one per chunk of KC2 input channels."""
             nonlocal wcur
-            key = (bi, ncols, tuple((t, tuple(pi for pi, _ in paths)) for t, paths in groups))
+            key = (bi, ncols, tuple((t, tuple((pi, c) for pi, c in paths)) for t, paths in groups))
             if key in w_cache:
                 return w_cache[key]
             blk = self.rot_blocks_c[bi]
@@ -977,14 +977,14 @@ class MessagePackOp:
             entries = []   # (u-range source index fn) per path: columns col .. col + mul
             for t, paths in groups:
                 M = int(self.tc_types_c[t].mul)
-                for pi, _ in paths:
-                    entries.append((col, pi, M))
+                for pi, c_ in paths:
+                    entries.append((col, pi, M, c_))
                     col += m8[t]
             for c, u0 in enumerate(range(0, kpad, KC2)):
                 kc = min(KC2, kpad - u0)
                 ku = np.arange(u0, min(u0 + kc, K))
                 img0 = off0 + 2 * ncols * KC2 * c
-                for col0, pi, M in entries:
+                for col0, pi, M, c_ in entries:
                     if len(ku) == 0:
                         continue
                     pa = self.tc_paths_c[pi]
@@ -992,10 +992,11 @@ class MessagePackOp:
                     kk, nn = np.meshgrid(ku, np.arange(M), indexing="ij")
                     if pa.kind == 0:
                         coef = math.sqrt((2 * pa.l3 + 1) / K)
-                        add_image(img0, ncols, kk - u0, col0 + nn, base[("tp", b)] + tp.w_off + kk * M + nn, coef, kc)
+                        # c_ = w3j(l1,l2,l3)[m1,0,m3] sqrt(2 l2 + 1): the step's scale rides on its W columns, the gate is a plain product
+                        add_image(img0, ncols, kk - u0, col0 + nn, base[("tp", b)] + tp.w_off + kk * M + nn, coef * c_, kc)
                     else:
                         bl = [x for x in self.direct_blocks[0] if x.i_out == _t][0]
-                        add_image(img0, ncols, kk - u0, col0 + nn, base[("direct", 0)] + bl.w_off + kk * bl.mul_out + nn, bl.scale, kc)
+                        add_image(img0, ncols, kk - u0, col0 + nn, base[("direct", 0)] + bl.w_off + kk * bl.mul_out + nn, bl.scale * c_, kc)
             wcur = off0 + 2 * ncols * kpad
             w_cache[key] = off0
             return off0
@@ -1072,7 +1073,7 @@ class MessagePackOp:
                                             meta_ = (int(pa.pad0) + q) | (int(pa.branch) << 20) | (nvalid << 24)
                                         else:
                                             meta_ = 0xFFFFF | (nvalid << 24)
-                                        batches.append(L.Rot2BatchT(meta_, c))
+                                        batches.append(L.Rot2BatchT(meta_, 1.0))   # scale folded into W (field kept for the ABI)
                                 col += kc_
                                 s_off += mp
                             for _ in range((ncols - cols) // 8):
