@@ -14,9 +14,10 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeArgs a) {
   extern __shared__ __align__(128) float smem[];   // A: 2 x [2 slabs][128][4], B: [2 slabs][256][4] x 2
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int flag;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 16384; i += 128) smem[i] = 0.f;
-  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); flag = 0; }
   if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -46,11 +47,22 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeArgs a) {
       }
     }
     const long long t1 = clock64();
+    *reinterpret_cast<volatile int*>(&flag) = 1;   // the MMAs are queued: warp 1 now times a TMEM load
     tc::mma_commit(&bar);
     tc::mbar_wait(&bar, 0);
     const long long t2 = clock64();
     a.out[0] = t1 - t0;
     a.out[1] = t2 - t0;
+  }
+  if (warp == 1) {
+    // TMEM load round trip while `count` MMAs are queued on the tensor pipe (columns 448.. are not touched by the MMAs)
+    while (*reinterpret_cast<volatile int*>(&flag) == 0) {}
+    const long long t0 = clock64();
+    uint32_t r[8];
+    tc::tmem_ld8(tmem + (32u << 16) + 448, r);
+    tc::tmem_ld_wait8(r);
+    const long long t1 = clock64();
+    if (tid == 32) { a.out[2] = t1 - t0; a.out[3] = (long long)r[0]; }
   }
   tc::fence_before_sync();
   __syncthreads();

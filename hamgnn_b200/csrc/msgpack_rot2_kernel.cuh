@@ -10,8 +10,11 @@
 //   CTA   = (tile of 128 edges, pass); pass = (output component m3, output slots with <= 128 accumulator columns)
 //   piece = one image X'_{block, m1} x the CONCATENATED weights of every path of the pass that reads it
 //             GEMM1  B[n&1][128 x ncols] = X' [W_p1 | W_p2 | ...]          warp 13, A / W chunks of 16 channels from the TMA ring (warp 12)
-//             gate   B <- hi(B * g_p), GL[n&1] <- lo                        warps 0-7 (two per TMEM lane quadrant, alternate 8-column batches);
-//                                                                           the w3j scale of the step is folded into the piece's W image
+//             gate   b = B * g_p (8-column batches, thread = edge)          warps 0-7, two per TMEM lane quadrant, each walks its own
+//                                                                           host-built stream; the w3j scale is folded into W.
+//                      multiplicity > 16: B <- hi(b), GL[n&1] <- lo        -> GEMM2 on the tensor core
+//                      multiplicity <= 16: s += b L' on the fp32 FMA pipes, C' += s  (no GEMM2: a tcgen05.mma costs ~55 cycles
+//                                          whatever its N, profiles/r02g_mma_probe.txt -- 57 % of the GEMM2 instructions had N = 16)
 //             GEMM2  S[n&1][s_off ..] = (B.g)[:, col0 : col0 + kcols] L'stack   warp 14, one K-concatenated chain per destination slot
 //             acc    C'[acc_col0 + w] += S[s_off + w]                        warps 8-11, fp32 round-to-nearest in shared memory
 //   end   : the pass's columns of the aligned-frame row cp[e][.] are stored (coalesced), unrotate_kernel finishes.
@@ -33,8 +36,37 @@ using rot::elect_one;
 using rot::expect_tx_a;
 using rot::tmem_alloc_dyn;
 using rot::tmem_dealloc_dyn;
-using rot::wait_a;
-using rot::warp_wait_a;
+
+// Barrier wait that SLEEPS: try_wait with a suspend-time hint parks the thread in hardware until the phase completes (or
+// the hint expires), instead of re-issuing the poll every few cycles.  With 15 warps per CTA of which ~10 are waiting at any
+// time, the polling loops of msgpack_rot_kernel's wait_a took more than half of all issued instructions and starved the
+// gate warps of issue slots (profiles/r02p).  Bounded: ~4 s, then trap.
+__device__ __forceinline__ void wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "mov.u32 %0, 1;\n"
+      "HGB_R2_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\t"
+      "@p bra HGB_R2_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 0x400000;\n\t"
+      "@p bra HGB_R2_WAIT;\n\t"
+      "mov.u32 %0, 0;\n"
+      "HGB_R2_DONE:\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (!ok) __trap();   // a pipeline bug must surface as a kernel error, never as a hung GPU
+}
+__device__ __forceinline__ void warp_wait_a(uint32_t addr, uint32_t parity) {   // one lane waits, the warp re-converges
+  if ((threadIdx.x & 31) == 0) wait_a(addr, parity);
+  __syncwarp();
+}
 
 constexpr int TILE = 128;
 constexpr int KC32 = 32;   // channel chunk of the packed X' images (rot::KC)
@@ -49,7 +81,6 @@ constexpr int STG = 2 * KC2 * TILE + 2 * KC2 * NB;     // floats per ring stage 
 constexpr int LBUF = 8192;                             // floats per L' buffer (R2_LMAX_FLOATS)
 constexpr int NTHR = 480;                              // warps 0-7 gate, 8-11 accumulate, 12 TMA, 13 GEMM1, 14 GEMM2
 constexpr int W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
-constexpr int HB = NB / 16;                            // gate batches per gate warp and piece (batches 2k + h)
 constexpr uint32_t TB = 0, TGL = 2 * NB, TS = 4 * NB;  // TMEM columns
 constexpr size_t SMEM_BYTES = (size_t)(NST * STG + 2 * LBUF + ACC_COLS * ACC_LD) * sizeof(float);
 
@@ -59,16 +90,18 @@ struct Args {
   const hgb_rot2_piece_t* pieces;
   const hgb_rot2_batch_t* batches;
   const hgb_rot2_dst_t* dsts;
+  const hgb_rot2_gpf_t* gpf;
   int n_passes;
   const float* xp;      // packed rotated inputs of the chunk [tile][tile_stride]
   int tile_stride;
-  const float* g;       // radial gate of the chunk [branch][tile][gstride][128]
-  int gstride;
+  const float* g;       // radial gate of the chunk [tile][branch][gstride][128]
+  int gtile_floats;     // n_branches * gstride * 128
   int64_t e_lo, n_chunk;
   float* cp;            // aligned-frame messages of ALL edges [E][rowstride]
   int rowstride;
   long long* trace;     // optional (HGB_ROT2_TRACE): clock64 stamps of CTA trace_cta, [role][piece][2]
   int trace_cta, trace_pieces;
+  int flags;            // experiment switches (HGB_ROT2_FLAGS), unused at present
 };
 
 // role: 0 TMA, 1 GEMM1, 2 gate (warp 0), 3 GEMM2, 4 accumulate (warp 8)
@@ -79,25 +112,25 @@ struct Args {
   } while (0)
 
 struct PieceRec {   // hgb_rot2_piece_t as two 16-byte words
-  int a_off, w_off, l_off, l_floats, batch_begin, dst_begin, kpad, ncols, ndst;
+  int a_off, w_off, l_off, l_floats, gpf_begin, dst_begin, kpad, ncols, ndst, gpf_n;
 };
 __device__ __forceinline__ PieceRec load_piece(const hgb_rot2_piece_t* p) {
   const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p)), w1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
   PieceRec r;
   r.a_off = (int)w0.x; r.w_off = (int)w0.y; r.l_off = (int)w0.z; r.l_floats = (int)w0.w;
-  r.batch_begin = (int)w1.x; r.dst_begin = (int)w1.y;
-  r.kpad = (int)(w1.z & 0xffffu); r.ncols = (int)(w1.z >> 16); r.ndst = (int)(w1.w & 0xffffu);
+  r.gpf_begin = (int)w1.x; r.dst_begin = (int)w1.y;
+  r.kpad = (int)(w1.z & 0xffffu); r.ncols = (int)(w1.z >> 16); r.ndst = (int)(w1.w & 0xffffu); r.gpf_n = (int)(w1.w >> 16);
   return r;
 }
 
 __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) float smem[];
-  // barriers: full[3] | empty[3] | lfull[2] | bfull[2] | gfull[2] | s2done[2] | sfree[2]
-  __shared__ uint64_t bars[16];
+  // barriers: full[3] | empty[3] | lfull[2] | bfull[2] | gfull[2] | s2done[2] | sfree[2] | simtdone
+  __shared__ uint64_t bars[17];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar0 = tc::smem_u32(bars);
   const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_BFULL = B_LFULL + 16, B_GFULL = B_LFULL + 32,
-                 B_S2 = B_LFULL + 48, B_SFREE = B_LFULL + 64;
+                 B_S2 = B_LFULL + 48, B_SFREE = B_LFULL + 64, B_SIMT = B_LFULL + 80;
   const uint32_t stage0 = tc::smem_u32(smem);
   const uint32_t lbuf0 = stage0 + (uint32_t)(NST * STG) * 4u;
   float* accs = smem + NST * STG + 2 * LBUF;
@@ -108,40 +141,44 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   const hgb_rot2_pass_t ps = a.passes[pass];
 
   if (tid == 0) {
-    for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], (i >= 10 && i < 12) ? 8 : (i >= 14 ? 4 : 1));   // gfull / sfree: one arrival per warp
+    for (int i = 0; i < 17; ++i) tc::mbar_init(&bars[i], ((i >= 10 && i < 12) || i == 16) ? 8 : (i >= 14 ? 4 : 1));   // gfull / simtdone / sfree: one arrival per warp
     tc::mbar_fence_init();
   }
   if (warp == W_MMA1) tmem_alloc_dyn(&tmem_slot, 512);
+  for (int i = tid; i < ps.ncols * ACC_LD; i += NTHR) accs[i] = 0.f;   // C' of the pass
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const float* __restrict__ wbuf = a.wbuf;
   const uint32_t dhi = tc::smem_desc_hi(128);
-  const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;   // floats per branch
 
   if (warp == W_TMA) {
     // =============================== TMA producer ===============================
     const float* xt = a.xp + (size_t)tile * a.tile_stride;
-    const float* gt = a.g + (size_t)tile * a.gstride * TILE;
-    // gate blocks of a piece: nvalid columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 one
-    // piece ahead of the gate warps (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident).
-    // Lane k takes batch k, so the table reads of a piece cost one load latency, not twelve.
-    auto prefetch_gate = [&](int qi) {
+    // The ring holds about one piece, so the operands of the pieces after it are pulled into L2 ahead of time (the packed
+    // inputs of a chunk are GBs: the first CTA of a tile to touch an image reads it from DRAM, ~2 000 cycles)
+    const float* gtile = a.g + (size_t)tile * a.gtile_floats;
+    auto prefetch_piece = [&](int qi) {
       if (qi >= ps.piece_end) return;
-      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
-      const int b0 = (int)w1.x, nb = (int)(w1.z >> 16) >> 3;
-      if (lane < nb) {
-        const uint32_t meta = (uint32_t)__ldg(&a.batches[b0 + lane].meta);
-        const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu, nv = (meta >> 24) & 0xFu;
-        if (nv != 0 && col != 0xFFFFFu) bulk_prefetch_l2(gt + (size_t)br * g_bstride + (size_t)col * TILE, nv * TILE * 4u);
+      const PieceRec pp = load_piece(a.pieces + qi);
+      if (lane == 0) {
+        bulk_prefetch_l2(xt + pp.a_off, (uint32_t)(2 * pp.kpad * TILE) * 4u);
+        bulk_prefetch_l2(wbuf + pp.w_off, (uint32_t)(2 * pp.kpad * pp.ncols) * 4u);
+        bulk_prefetch_l2(wbuf + pp.l_off, (uint32_t)pp.l_floats * 4u);
+      }
+      // the gate blocks of the piece (the gate tensor of a chunk is GBs, written by the pre-pass): lane k takes run k
+      if (lane < pp.gpf_n) {
+        const uint2 gr = __ldg(reinterpret_cast<const uint2*>(a.gpf + pp.gpf_begin + lane));
+        bulk_prefetch_l2(gtile + gr.x, gr.y);
       }
     };
-    prefetch_gate(ps.piece_begin);
+    prefetch_piece(ps.piece_begin + 1);
+    prefetch_piece(ps.piece_begin + 2);
     int n = 0, c_all = 0;
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
       const PieceRec pc = load_piece(a.pieces + qi);
-      prefetch_gate(qi + 1);
+      prefetch_piece(qi + 3);
       if (lane == 0) {
         R2_TRACE(0, n, 0);
         for (int u0 = 0, c = 0; u0 < pc.kpad; u0 += KC2, ++c, ++c_all) {
@@ -238,97 +275,143 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
         }
         __syncwarp();
       }
+      if (ndst == 0) {   // every destination of the piece was applied on the FMA pipes: nothing to wait for, B / GL / L' are free
+        if (elect_one()) commit_a(B_S2 + 8 * nb);
+        __syncwarp();
+      }
       R2_TRACE(3, n, 1);
     }
   } else if (warp < 8) {
-    // =============================== gate: B <- hi(B * g), GL <- lo  (thread = edge = TMEM lane) ===============================
-    // Two warps per lane quadrant; warp half h takes the 8-column batches 2k + h of every piece.  The gate values of piece
-    // n + 1 are loaded into the registers of batch k as soon as batch k of piece n is done, so the global-load latency is
-    // hidden behind a whole piece; the three TMEM loads of a group are issued together.
+    // =============================== gate (thread = edge = TMEM lane) ===============================
+    // Two warps per lane quadrant; half h walks its own stream of 8-column batches (host: FMA-pipe slots belong to one
+    // half, tensor batches alternate).  Two-stage software pipeline: the gate values of batch k + 1 are in flight while
+    // batch k is processed (the body exists twice -- no register shuffling, ~10 KB of code).
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int zt = q * 32 + lane;
     const bool live = (int64_t)tile * TILE + zt < a.n_chunk;
-    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? zt : 0);   // column c of this edge: grow[c * TILE]
-    float gv[HB][8];
-    // lane k <- descriptor of this warp's k-th batch of piece qi; nbw = number of such batches
-    auto fetch_meta = [&](int qi, int& nbw) -> uint32_t {
-      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
-      const int nb = (int)(w1.z >> 16) >> 3;
-      nbw = (nb - h + 1) >> 1;
-      uint32_t m = 0xFFFFFu;   // nvalid = 0
-      if (lane < nbw) m = (uint32_t)__ldg(&a.batches[(int)w1.x + 2 * lane + h].meta);
-      return m;
-    };
-    auto issue = [&](float (&gq)[8], uint32_t meta) {
-      const uint32_t col = meta & 0xFFFFFu, br = (meta >> 20) & 0xFu;
-      const int nv = (int)((meta >> 24) & 0xFu);
-      if (col == 0xFFFFFu) {   // un-gated (direct Linear) or padding columns
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? 1.f : 0.f;
+    // gate tensor of the chunk: [tile][branch][gstride][128]; a batch record holds the float offset of its two 4-column blocks
+    const float* gz = a.g + (size_t)tile * a.gtile_floats + (live ? zt : 0);
+    float* acc = accs + zt;
+    const float* lbase = smem + NST * STG;
+    const int sb = h ? ps.stream1_begin : ps.stream0_begin, se = h ? ps.stream1_end : ps.stream0_end;
+    const uint4* recs = reinterpret_cast<const uint4*>(a.batches);
+    auto load_gates = [&](const uint4& r, float (&gq)[8]) {
+      if (r.y == 0xFFFFFFFFu) {
+        gq[0] = gq[1] = gq[2] = gq[3] = 1.f;
       } else {
-        const float* gp = grow + (size_t)br * g_bstride + (size_t)col * TILE;
+        const float* gp = gz + r.y;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gq[j] = (j < nv) ? __ldg(gp + j * TILE) : 0.f;   // warp-uniform predicate; 128 contiguous bytes per warp
+        for (int j = 0; j < 4; ++j) gq[j] = __ldg(gp + j * TILE);   // a warp reads 128 contiguous bytes per column
+      }
+      if (r.z == 0xFFFFFFFFu) {
+        gq[4] = gq[5] = gq[6] = gq[7] = 1.f;
+      } else {
+        const float* gp = gz + r.z;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gq[4 + j] = __ldg(gp + j * TILE);
       }
     };
-    int nbw = 0;
-    uint32_t mt = fetch_meta(ps.piece_begin, nbw);
+    float s[16];
 #pragma unroll
-    for (int k = 0; k < HB; ++k) {
-      const uint32_t m = __shfl_sync(0xffffffffu, mt, k);
-      if (k < nbw) issue(gv[k], m);
-    }
-    int n = 0;
-    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
-      int nbw_next = 0;
-      uint32_t mt_next = 0xFFFFFu;
-      if (qi + 1 < ps.piece_end) mt_next = fetch_meta(qi + 1, nbw_next);
-      warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
-      tc::fence_after_sync();
-      if (warp == 0) R2_TRACE(2, n, 0);
-      const uint32_t bq0 = tmem + lane_base + TB + (uint32_t)((n & 1) * NB) + (uint32_t)(h * 8);
-      const uint32_t gl0 = tmem + lane_base + TGL + (uint32_t)((n & 1) * NB) + (uint32_t)(h * 8);
+    for (int w = 0; w < 16; ++w) s[w] = 0.f;
+    int n = 0, tb = 0;
+    auto process = [&](const uint4& r, const float (&gq)[8]) {
+      const uint32_t meta = r.x;
+      const uint32_t kind = meta & 3u;
+      if (meta & 4u) {   // first batch of this half in piece n
+        warp_wait_a(B_BFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
+        warp_wait_a(B_LFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));   // FMA-pipe batches read the L' rows of the piece
+        tc::fence_after_sync();
+        if (warp == 0) R2_TRACE(2, n, 0);
+      }
+      const bool tr = a.trace != nullptr && (int)blockIdx.x == a.trace_cta && warp == 0 && lane == 0 && tb < 256;
+      if (tr) a.trace[10 * a.trace_pieces + tb * 4 + 0] = clock64();
+      if (kind != 2u) {
+        const uint32_t col = (meta >> 5) & 0x7F8u;   // (meta >> 8 & 0xFF) * 8
+        const uint32_t bq = tmem + lane_base + TB + (uint32_t)((n & 1) * NB) + col;
+        uint32_t rb[8];
+        tc::tmem_ld8(bq, rb);
+        tc::tmem_ld_wait8(rb);
+        if (tr) a.trace[10 * a.trace_pieces + tb * 4 + 1] = clock64();
+        float bg[8];
 #pragma unroll
-      for (int k0 = 0; k0 < HB; k0 += 3) {
-        uint32_t rb[3][8];
+        for (int j = 0; j < 8; ++j) bg[j] = __uint_as_float(rb[j]) * gq[j];
+        if (tr) { float sum = 0.f; for (int j = 0; j < 8; ++j) sum += bg[j]; if (sum == 123.456f) a.trace[0] = 0; a.trace[10 * a.trace_pieces + tb * 4 + 2] = clock64(); }
+        if (kind == 0u) {
+          uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (k0 + i < nbw) tc::tmem_ld8(bq0 + (uint32_t)((k0 + i) * 16), rb[i]);
+          for (int j = 0; j < 8; ++j) {
+            float hh, ll;
+            tc::split_tf32(bg[j], hh, ll);
+            hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(ll);
+          }
+          tc::tmem_st8(bq, hi);
+          tc::tmem_st8(tmem + lane_base + TGL + (uint32_t)((n & 1) * NB) + col, lo);
+        } else {
+          // s[w'] += sum_j b_j L'[j][w'] : L' rows broadcast from shared memory (padding rows are zero, b = 0 there)
+          const int mul = (int)((meta >> 16) & 0x1Fu), m4 = (mul + 3) & ~3;
+          if (meta & 16u) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (k0 + i < nbw) {
-            tc::tmem_ld_wait8(rb[i]);
-            uint32_t hi[8], lo[8];
+            for (int w = 0; w < 16; ++w) s[w] = 0.f;
+          }
+          const float* lr = lbase + (n & 1) * LBUF + r.w;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float hh, ll;
-              tc::split_tf32(__uint_as_float(rb[i][j]) * gv[k0 + i][j], hh, ll);
-              hi[j] = __float_as_uint(hh); lo[j] = __float_as_uint(ll);
+          for (int w4 = 0; w4 < 4; ++w4) {
+            if (4 * w4 < m4) {   // warp-uniform
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 lv = *reinterpret_cast<const float4*>(lr + j * m4 + 4 * w4);
+                s[4 * w4 + 0] = fmaf(bg[j], lv.x, s[4 * w4 + 0]);
+                s[4 * w4 + 1] = fmaf(bg[j], lv.y, s[4 * w4 + 1]);
+                s[4 * w4 + 2] = fmaf(bg[j], lv.z, s[4 * w4 + 2]);
+                s[4 * w4 + 3] = fmaf(bg[j], lv.w, s[4 * w4 + 3]);
+              }
             }
-            tc::tmem_st8(bq0 + (uint32_t)((k0 + i) * 16), hi);
-            tc::tmem_st8(gl0 + (uint32_t)((k0 + i) * 16), lo);
+          }
+          if (meta & 32u) {   // last batch of the destination group: C' += s (this warp owns these columns)
+            float* ap = acc + ((meta >> 21) & 0xFFu) * ACC_LD;
+#pragma unroll
+            for (int w = 0; w < 16; ++w)
+              if (w < mul) ap[w * ACC_LD] += s[w];
           }
         }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const uint32_t m = __shfl_sync(0xffffffffu, mt_next, k0 + i);
-          if (k0 + i < nbw_next) issue(gv[k0 + i], m);
-        }
       }
-      tc::tmem_st_wait();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
-      if (warp == 0) R2_TRACE(2, n, 1);
-      nbw = nbw_next;
+      if (tr) a.trace[10 * a.trace_pieces + tb * 4 + 3] = clock64() | ((long long)kind << 60);
+      ++tb;
+      if (meta & 8u) {   // last batch of this half in piece n: hand the piece to GEMM2
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) arrive_a(B_GFULL + 8 * (n & 1));
+        if (warp == 0) R2_TRACE(2, n, 1);
+        ++n;
+      }
+    };
+    uint4 r0 = make_uint4(2u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u), r1 = r0;
+    float g0[8], g1[8];
+    if (sb < se) { r0 = __ldg(recs + sb); load_gates(r0, g0); }
+    if (sb + 1 < se) r1 = __ldg(recs + sb + 1);
+#pragma unroll 1
+    for (int bb = sb; bb < se; bb += 2) {
+      uint4 r2 = r0, r3 = r0;
+      if (bb + 1 < se) load_gates(r1, g1);
+      if (bb + 2 < se) r2 = __ldg(recs + bb + 2);
+      process(r0, g0);
+      if (bb + 1 < se) {
+        if (bb + 2 < se) load_gates(r2, g0);
+        if (bb + 3 < se) r3 = __ldg(recs + bb + 3);
+        process(r1, g1);
+      }
+      r0 = r2; r1 = r3;
     }
+    __syncwarp();
+    if (lane == 0) arrive_a(B_SIMT);   // every FMA-pipe contribution of this warp is in C'
   } else {
     // =============================== accumulate: C' += S, finally store the pass's columns of cp ===============================
     const int q = warp - 8, zl = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float* acc = accs + zl;
-    for (int c = 0; c < ps.ncols; ++c) acc[c * ACC_LD] = 0.f;
     int n = 0;
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
       const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
@@ -364,6 +447,7 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
       if (lane == 0) arrive_a(B_SFREE + 8 * (n & 1));
       if (q == 0) R2_TRACE(4, n, 1);
     }
+    warp_wait_a(B_SIMT, 0);   // the gate warps have added the last FMA-pipe contributions
     __syncwarp();
     // warp q owns edges [32 q, 32 q + 32) of the tile: rows of cp, the pass's columns are contiguous
     for (int zz = 0; zz < 32; ++zz) {

@@ -353,7 +353,7 @@ struct GateArgs {
   int64_t n_edges;
   int n_branches, rbf_dim, h1, h2dim, gstride;
   float act_const;
-  int tmajor;           // 1: g is [n_branches][tile of 128 edges][gstride][128] (see gtc::Args)
+  int tmajor;           // 1: g is [n_branches][tile of 128 edges][gstride][128], 2: [tile][n_branches][gstride][128] (see gtc::Args)
 };
 constexpr int GE = 64;    // edges per CTA
 constexpr int GN = 128;   // W3 column tile
@@ -438,7 +438,8 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
       if (a.tmajor) {
         // rows ty*4 .. ty*4+3 of one column are 16 contiguous bytes of the tile-major layout (padding rows included)
         const int64_t n_tiles = (a.n_edges + 127) / 128;
-        float* gt = a.g + ((size_t)b * n_tiles + (size_t)(e0 >> 7)) * (size_t)a.gstride * 128 + (e0 & 127) + ty * 4;
+        const size_t blk = (a.tmajor == 2) ? (size_t)(e0 >> 7) * a.n_branches + b : (size_t)b * n_tiles + (size_t)(e0 >> 7);   // 2: [tile][branch]
+        float* gt = a.g + blk * (size_t)a.gstride * 128 + (e0 & 127) + ty * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = n0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
@@ -848,7 +849,7 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
   HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && rp && r2 && src && dw && rbf && out && g_ws && xp_ws && cp_ws && w3_off && nch, "hgb_msgpack_rot2_forward: NULL argument");
   HGB_CHECK_ARG(rp->blocks_host && rp->blocks && r2->passes && r2->pieces && r2->batches && r2->dsts && r2->passes_host && r2->pieces_host &&
-                    r2->batches_host && r2->dsts_host,
+                    r2->batches_host && r2->dsts_host && (r2->n_gpf == 0 || (r2->gpf && r2->gpf_host)),
                 "hgb_msgpack_rot2_forward: host and device copies of the tables are required");
   HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
                 "hgb_msgpack_rot2_forward: bad source/branch count");
@@ -863,7 +864,7 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
   HGB_CHECK_ARG(r2->n_passes >= 1 && r2->rowstride >= 1 && r2->rowstride <= plan->out_dim, "hgb_msgpack_rot2_forward: bad pass table");
   cudaStream_t st = (cudaStream_t)stream;
   for (int b = 0; b < plan->n_branches; ++b)
-    HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "hgb_msgpack_rot2_forward: gate width %d exceeds stride %d", nch[b], gstride);
+    HGB_CHECK_ARG(nch[b] > 0 && nch[b] + 3 <= gstride && gstride % 4 == 0, "hgb_msgpack_rot2_forward: gate width %d exceeds stride %d", nch[b], gstride);
   for (int s = 0; s < plan->n_sources; ++s) HGB_CHECK_ARG(src[s] != nullptr, "hgb_msgpack_rot2_forward: source %d is NULL", s);
 
   // ---- validate the tables (host copies): every offset the kernel dereferences
@@ -881,25 +882,25 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
   for (int p = 0; p < r2->n_passes; ++p) {
     const hgb_rot2_pass_t& ps = r2->passes_host[p];
     HGB_CHECK_ARG(ps.piece_begin >= 0 && ps.piece_begin < ps.piece_end && ps.piece_end <= r2->n_pieces && ps.ncols >= 1 &&
-                      ps.ncols <= rot2::ACC_COLS && ps.out_col0 == col_cover && ps.batch_begin >= 0 && ps.batch_end <= r2->n_batches,
+                      ps.ncols <= rot2::ACC_COLS && ps.out_col0 == col_cover && ps.stream0_begin >= 0 &&
+                      ps.stream0_begin <= ps.stream0_end && ps.stream0_end <= r2->n_batches && ps.stream1_begin >= 0 &&
+                      ps.stream1_begin <= ps.stream1_end && ps.stream1_end <= r2->n_batches,
                   "hgb_msgpack_rot2_forward: bad pass %d", p);
     col_cover += ps.ncols;
-    int bt = ps.batch_begin;
     for (int q = ps.piece_begin; q < ps.piece_end; ++q) {
       const hgb_rot2_piece_t& pc = r2->pieces_host[q];
       HGB_CHECK_ARG(pc.kpad >= 8 && pc.kpad % 8 == 0 && pc.ncols >= 16 && pc.ncols % 16 == 0 && pc.ncols <= rot2::NB && pc.a_off >= 0 &&
                         pc.a_off % 4 == 0 && (int64_t)pc.a_off + (int64_t)2 * pc.kpad * rot::TILE <= rp->tile_stride && pc.w_off >= 0 &&
                         pc.w_off % 4 == 0 && pc.l_off >= 0 && pc.l_off % 4 == 0 && pc.l_floats > 0 && pc.l_floats % 4 == 0 &&
-                        pc.l_floats <= rot2::LBUF && pc.batch_begin == bt && pc.ndst >= 1 && pc.dst_begin >= 0 &&
-                        pc.dst_begin + pc.ndst <= r2->n_dsts,
+                        pc.l_floats <= rot2::LBUF && pc.ndst >= 0 && pc.dst_begin >= 0 && pc.dst_begin + pc.ndst <= r2->n_dsts &&
+                        pc.gpf_n >= 0 && pc.gpf_n <= 32 && pc.gpf_begin >= 0 && (int64_t)pc.gpf_begin + pc.gpf_n <= r2->n_gpf,
                     "hgb_msgpack_rot2_forward: bad piece %d", q);
-      for (int k = 0; k < pc.ncols / 8; ++k) {
-        const uint32_t meta = (uint32_t)r2->batches_host[bt + k].meta;
-        const int col = (int)(meta & 0xFFFFFu), br = (int)((meta >> 20) & 0xFu), nv = (int)((meta >> 24) & 0xFu);
-        HGB_CHECK_ARG(nv <= 8 && (col == 0xFFFFF || (br < plan->n_branches && col + nv <= nch[br])),
-                      "hgb_msgpack_rot2_forward: gate batch %d out of range", bt + k);
+      for (int k = pc.gpf_begin; k < pc.gpf_begin + pc.gpf_n; ++k) {
+        const hgb_rot2_gpf_t& gr = r2->gpf_host[k];
+        HGB_CHECK_ARG(gr.off % 4 == 0 && gr.bytes % 16 == 0 && gr.bytes > 0 &&
+                          (uint64_t)gr.off * 4 + gr.bytes <= (uint64_t)plan->n_branches * gstride * 128 * 4,
+                      "hgb_msgpack_rot2_forward: gate prefetch run %d out of range", k);
       }
-      bt += pc.ncols / 8;
       int s_used = 0;
       for (int d = pc.dst_begin; d < pc.dst_begin + pc.ndst; ++d) {
         const hgb_rot2_dst_t& ds = r2->dsts_host[d];
@@ -911,7 +912,31 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
         s_used += ds.mp;
       }
     }
-    HGB_CHECK_ARG(bt == ps.batch_end, "hgb_msgpack_rot2_forward: gate batches of pass %d are not contiguous", p);
+    // the two gate streams: each visits every piece of the pass once (first ... last flags), in piece order
+    for (int h = 0; h < 2; ++h) {
+      const int sb = h ? ps.stream1_begin : ps.stream0_begin, se = h ? ps.stream1_end : ps.stream0_end;
+      int q = ps.piece_begin, open = 0;
+      for (int b = sb; b < se; ++b) {
+        const hgb_rot2_batch_t& bt = r2->batches_host[b];
+        const uint32_t meta = (uint32_t)bt.meta;
+        const int kind = (int)(meta & 3u);
+        HGB_CHECK_ARG(q < ps.piece_end && (((meta >> 2) & 1u) != 0) == (open == 0), "hgb_msgpack_rot2_forward: gate stream %d of pass %d is not piece-aligned at %d", h, p, b);
+        open = 1;
+        const hgb_rot2_piece_t& pc = r2->pieces_host[q];
+        const uint32_t gmax = (uint32_t)plan->n_branches * (uint32_t)gstride * 128u;
+        HGB_CHECK_ARG(kind <= 2 && (bt.goff_a == 0xFFFFFFFFu || (bt.goff_a % 128u == 0 && bt.goff_a + 4u * 128u <= gmax)) &&
+                          (bt.goff_b == 0xFFFFFFFFu || (bt.goff_b % 128u == 0 && bt.goff_b + 4u * 128u <= gmax)),
+                      "hgb_msgpack_rot2_forward: gate batch %d out of range", b);
+        if (kind != 2) HGB_CHECK_ARG((int)((meta >> 8) & 0xFFu) * 8 + 8 <= pc.ncols, "hgb_msgpack_rot2_forward: gate batch %d outside its piece", b);
+        if (kind == 1) {
+          const int mul = (int)((meta >> 16) & 0x1Fu), acc0 = (int)((meta >> 21) & 0xFFu), m4 = (mul + 3) & ~3;
+          HGB_CHECK_ARG(mul >= 1 && mul <= 16 && acc0 + mul <= ps.ncols && bt.l_off >= 0 && bt.l_off % 4 == 0 && bt.l_off + 8 * m4 <= pc.l_floats,
+                        "hgb_msgpack_rot2_forward: bad FMA-pipe batch %d", b);
+        }
+        if ((meta >> 3) & 1u) { open = 0; ++q; }
+      }
+      HGB_CHECK_ARG(open == 0 && q == ps.piece_end, "hgb_msgpack_rot2_forward: gate stream %d of pass %d does not cover its pieces", h, p);
+    }
   }
   HGB_CHECK_ARG(col_cover == r2->rowstride, "hgb_msgpack_rot2_forward: passes cover %d of %d columns", col_cover, r2->rowstride);
 
@@ -959,9 +984,10 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
 
   rot2::Args ka;
   memset(&ka, 0, sizeof(ka));
-  ka.wbuf = plan->wbuf; ka.passes = r2->passes; ka.pieces = r2->pieces; ka.batches = r2->batches; ka.dsts = r2->dsts;
-  ka.n_passes = r2->n_passes; ka.xp = xp_ws; ka.tile_stride = rp->tile_stride; ka.g = g_ws; ka.gstride = gstride;
+  ka.wbuf = plan->wbuf; ka.passes = r2->passes; ka.pieces = r2->pieces; ka.batches = r2->batches; ka.dsts = r2->dsts; ka.gpf = r2->gpf;
+  ka.n_passes = r2->n_passes; ka.xp = xp_ws; ka.tile_stride = rp->tile_stride; ka.g = g_ws; ka.gtile_floats = plan->n_branches * gstride * 128;
   ka.cp = cp_ws; ka.rowstride = r2->rowstride;
+  { const char* fl = getenv("HGB_ROT2_FLAGS"); ka.flags = fl ? atoi(fl) : 0; }
   static_assert(rot2::SMEM_BYTES <= 227 * 1024, "msgpack_rot2_kernel: shared memory budget");
   HGB_CUDA_OK(cudaFuncSetAttribute(rot2::msgpack_rot2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot2::SMEM_BYTES));
 
@@ -969,7 +995,7 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
     const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
     const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
     {
-      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 1);
+      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 2);
       if (rc != 0) return rc;
     }
     pa.e_lo = e_lo; pa.n_chunk = n;
@@ -986,14 +1012,14 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
       ka.trace_cta = tp ? atoi(tp) : 5;
       if (ka.trace_cta >= r2->n_passes) ka.trace_cta = r2->n_passes - 1;
       ka.trace_pieces = trace_pieces;
-      HGB_CUDA_OK(cudaMalloc(&d_trace, sizeof(long long) * 5 * trace_pieces * 2));
-      HGB_CUDA_OK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 5 * trace_pieces * 2, st));
+      HGB_CUDA_OK(cudaMalloc(&d_trace, sizeof(long long) * (10 * trace_pieces + 1024)));
+      HGB_CUDA_OK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * (10 * trace_pieces + 1024), st));
       ka.trace = d_trace;
     }
     rot2::msgpack_rot2_kernel<<<(unsigned)(n_tiles * r2->n_passes), rot2::NTHR, rot2::SMEM_BYTES, st>>>(ka);
     HGB_LAUNCH_OK("msgpack_rot2_kernel");
     if (d_trace) {
-      static long long h_trace[5 * 128 * 2];
+      static long long h_trace[10 * 128 + 1024];
       HGB_CUDA_OK(cudaStreamSynchronize(st));
       HGB_CUDA_OK(cudaMemcpy(h_trace, d_trace, sizeof(h_trace), cudaMemcpyDeviceToHost));
       cudaFree(d_trace);
@@ -1011,6 +1037,13 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
           for (int role = 0; role < 5; ++role)
             fprintf(f, " %lld %lld |", h_trace[(role * trace_pieces + n2) * 2] - t0, h_trace[(role * trace_pieces + n2) * 2 + 1] - t0);
           fprintf(f, "\n");
+        }
+        fprintf(f, "# gate warp 0 batches: start | after tmem ld | after gate values | end (kind)\n");
+        for (int b2 = 0; b2 < 256; ++b2) {
+          const long long* q4 = h_trace + 10 * trace_pieces + b2 * 4;
+          if (!q4[0]) break;
+          fprintf(f, "b%d %lld %lld %lld %lld k%lld\n", b2, q4[0] - t0, q4[1] ? q4[1] - t0 : 0, q4[2] ? q4[2] - t0 : 0,
+                  (q4[3] & 0x0fffffffffffffffll) - t0, (q4[3] >> 60) & 3);
         }
         fclose(f);
       }

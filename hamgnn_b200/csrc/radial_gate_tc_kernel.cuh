@@ -46,7 +46,8 @@ struct Args {
   int64_t n_edges;
   int rbf_dim, h1, h2dim, gstride;
   float act_const;
-  int tmajor;              // 1: g is [n_branches][tile of 128 edges][gstride][128] (edge-minor inside a tile: the layout the
+  int tmajor;              // 2: [tile][n_branches][gstride][128] (rot2: a gate block has ONE offset inside its tile);
+                           // 1: g is [n_branches][tile of 128 edges][gstride][128] (edge-minor inside a tile: the layout the
                            // rotated-frame message kernel reads, coalesced on both sides); 0: [n_branches][E][gstride]
 };
 
@@ -201,7 +202,8 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
         if (a.tmajor) {
           // every thread (padding rows of the last tile included: the workspace is padded) writes one float per column;
           // a warp covers 128 contiguous bytes
-          float* gt = a.g + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)a.gstride * ROWS + tid;
+          const size_t blk = (a.tmajor == 2) ? (size_t)blockIdx.x * gridDim.y + b : (size_t)b * gridDim.x + blockIdx.x;
+          float* gt = a.g + blk * (size_t)a.gstride * ROWS + tid;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
 #pragma unroll

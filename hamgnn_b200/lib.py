@@ -62,19 +62,27 @@ class RotPlan(C.Structure):
 
 class Rot2PassT(C.Structure):
     """One pass of the A-stationary rotated-frame kernel: output component m3 x a subset of output slots."""
-    _fields_ = [("piece_begin", i32), ("piece_end", i32), ("ncols", i32), ("out_col0", i32), ("batch_begin", i32),
-                ("batch_end", i32), ("pad0", i32), ("pad1", i32)]
+    _fields_ = [("piece_begin", i32), ("piece_end", i32), ("ncols", i32), ("out_col0", i32), ("stream0_begin", i32),
+                ("stream0_end", i32), ("stream1_begin", i32), ("stream1_end", i32)]
 
 
 class Rot2PieceT(C.Structure):
     """One input image x the concatenated weights of every path of the pass that consumes it."""
-    _fields_ = [("a_off", i32), ("w_off", i32), ("l_off", i32), ("l_floats", i32), ("batch_begin", i32), ("dst_begin", i32),
-                ("kpad", C.c_int16), ("ncols", C.c_int16), ("ndst", C.c_int16), ("pad", C.c_int16)]
+    _fields_ = [("a_off", i32), ("w_off", i32), ("l_off", i32), ("l_floats", i32), ("gpf_begin", i32), ("dst_begin", i32),
+                ("kpad", C.c_int16), ("ncols", C.c_int16), ("ndst", C.c_int16), ("gpf_n", C.c_int16)]
+
+
+class Rot2GpfT(C.Structure):
+    """One contiguous run of gate columns of a piece (L2 prefetch list)."""
+    _fields_ = [("off", C.c_uint32), ("bytes", C.c_uint32)]
 
 
 class Rot2BatchT(C.Structure):
-    """Gate descriptor of 8 consecutive B columns: meta = gate column | branch << 20 | nvalid << 24 (column 0xFFFFF: g = 1)."""
-    _fields_ = [("meta", i32), ("scale", f32)]
+    """Gate-stream entry = 8 consecutive B columns of a piece, in the stream of one gate-warp half.
+    meta = kind (0 tensor, 1 FMA pipes, 2 dummy) | first-of-piece << 2 | last-of-piece << 3 | group-first << 4 | group-last << 5 |
+    (B column / 8) << 8 | mul << 16 | acc_col0 << 21; goff_a / goff_b: float offset of the gate block (4 columns x 128 edges) of
+    columns 0-3 / 4-7 inside the tile's gate block [branch][gstride][128], 0xFFFFFFFF = un-gated; l_off: FMA-pipe L' rows."""
+    _fields_ = [("meta", i32), ("goff_a", C.c_uint32), ("goff_b", C.c_uint32), ("l_off", i32)]
 
 
 class Rot2DstT(C.Structure):
@@ -86,8 +94,8 @@ class Rot2DstT(C.Structure):
 class Rot2Plan(C.Structure):
     _fields_ = [("n_passes", i32), ("n_pieces", i32), ("n_batches", i32), ("n_dsts", i32), ("rowstride", i32), ("n_slots", i32),
                 ("slot_l", i32 * 32), ("slot_mul", i32 * 32), ("slot_out_off", i32 * 32), ("ccol", (i32 * 13) * 32),
-                ("passes", vp), ("pieces", vp), ("batches", vp), ("dsts", vp),
-                ("passes_host", vp), ("pieces_host", vp), ("batches_host", vp), ("dsts_host", vp)]
+                ("passes", vp), ("pieces", vp), ("batches", vp), ("dsts", vp), ("gpf", vp), ("n_gpf", i64),
+                ("passes_host", vp), ("pieces_host", vp), ("batches_host", vp), ("dsts_host", vp), ("gpf_host", vp)]
 
 
 class LinBlockT(C.Structure):

@@ -276,14 +276,14 @@ _WORKSPACES: Dict[Tuple[str, str], torch.Tensor] = {}
 _SEGMENT_CACHE: Dict[str, tuple] = {}
 
 
-def workspace(name: str, numel: int, device) -> torch.Tensor:
+def workspace(name: str, numel: int, device, zero: bool = False) -> torch.Tensor:
     """Grow-only fp32 scratch buffer shared by all message ops of a device (the seven message calls of a forward run
     back to back on one stream, so they can share it); avoids a multi-GB torch.empty per call."""
     key = (name, str(device))
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < numel:
         _WORKSPACES.pop(key, None)
-        buf = torch.empty(int(numel), device=device, dtype=torch.float32)
+        buf = (torch.zeros if zero else torch.empty)(int(numel), device=device, dtype=torch.float32)
         _WORKSPACES[key] = buf
     return buf
 
@@ -865,6 +865,7 @@ class MessagePackOp:
     R2_KC = 16        # channels per ring stage
     R2_ACC = 128      # accumulator columns per pass (shared memory [128][129] floats)
     R2_LMAX_FLOATS = 8192   # L' buffer: hi + lo images of all destination groups of a piece
+    R2_SIMT_MAX = 16        # slots with multiplicity <= 16 apply L' on the fp32 FMA pipes (no GEMM2, no hi/lo write-back)
 
     def _build_rot2_program(self):
         """Tables of the A-stationary edge-aligned message kernel (csrc/msgpack_rot2_kernel.cuh).
@@ -930,10 +931,23 @@ class MessagePackOp:
         assert self.rot2_n_steps == self.rot_n_steps, (self.rot2_n_steps, self.rot_n_steps)
 
         w_cache: Dict[tuple, int] = {}
-        l_cache: Dict[tuple, int] = {}
+        l_cache: Dict[tuple, tuple] = {}
+        SIMT_MAX = self.R2_SIMT_MAX
+        is_simt = [int(self.tc_types_c[t].mul) <= SIMT_MAX for t in range(ntypes)]
+        m4 = [(int(self.tc_types_c[t].mul) + 3) // 4 * 4 for t in range(ntypes)]
+
+        pw = [m4[t] if is_simt[t] else m8[t] for t in range(ntypes)]   # B columns per path: SIMT groups pack at 4-column granularity
+
+        def gcols(t, npaths):
+            return (npaths * pw[t] + 7) // 8 * 8
+
+        def l_size(t, npaths):
+            kc_ = gcols(t, npaths)
+            return kc_ * m4[t] if is_simt[t] else 2 * kc_ * int(self.tc_types_c[t].mpad)
 
         def l_block(groups):
-            """Concatenated (hi | lo) L' stacks of a piece's destination groups; returns (offset, floats, [l_rel per group])."""
+            """L' operands of a piece's destination groups, contiguous: tensor groups as (hi | lo) K-major stacks
+            [kcols/4][mp][4], SIMT groups as plain fp32 rows [kcols][m4]; returns (offset, floats, [l_rel per group])."""
             nonlocal wcur
             key = tuple((t, tuple(pi for pi, _ in paths)) for t, paths in groups)
             if key in l_cache:
@@ -943,21 +957,29 @@ class MessagePackOp:
             for t, paths in groups:
                 ty = self.tc_types_c[t]
                 mp, M = int(ty.mpad), int(ty.mul)
-                kcols = len(paths) * m8[t]
+                kcols = gcols(t, len(paths))
                 rels.append(wcur - off0)
                 for j, (pi, _) in enumerate(paths):
                     pa = self.tc_paths_c[pi]
                     b, tp, _t = self.tc_path_meta[pi]
-                    ww, wo = np.meshgrid(np.arange(M), np.arange(M), indexing="ij")      # k = j*m8 + w, n = w'
+                    ww, wo = np.meshgrid(np.arange(M), np.arange(M), indexing="ij")      # k = j*pw + w, n = w'
                     if pa.kind == 0:
                         f0, rows, Mt = f_slices[(b, t)]
                         tpaths = [q for q in self.paths_by_branch[b] if q.ir_out == self.irreps_out[t].ir]
                         ch_type0 = tpaths[0].ch_off
-                        add_image(wcur, mp, j * m8[t] + ww, wo, base[("F", b)] + f0 + (tp.ch_off - ch_type0 + ww) * Mt + wo, 1.0, kcols)
+                        srcidx = base[("F", b)] + f0 + (tp.ch_off - ch_type0 + ww) * Mt + wo
+                        if is_simt[t]:
+                            add(wcur + (j * pw[t] + ww) * m4[t] + wo, srcidx, 1.0, 2)
+                        else:
+                            add_image(wcur, mp, j * pw[t] + ww, wo, srcidx, 1.0, kcols)
                     else:
                         kk = np.arange(M)
-                        add_image(wcur, mp, j * m8[t] + kk, kk, np.full(M, self.src_total, dtype=np.int64), 1.0, kcols)
-                wcur += 2 * kcols * mp
+                        one = np.full(M, self.src_total, dtype=np.int64)
+                        if is_simt[t]:
+                            add(wcur + (j * pw[t] + kk) * m4[t] + kk, one, 1.0, 2)
+                        else:
+                            add_image(wcur, mp, j * pw[t] + kk, kk, one, 1.0, kcols)
+                wcur += l_size(t, len(paths))
             res = (off0, wcur - off0, rels)
             assert res[1] <= self.R2_LMAX_FLOATS
             l_cache[key] = res
@@ -977,9 +999,9 @@ class MessagePackOp:
             entries = []   # (u-range source index fn) per path: columns col .. col + mul
             for t, paths in groups:
                 M = int(self.tc_types_c[t].mul)
-                for pi, c_ in paths:
-                    entries.append((col, pi, M, c_))
-                    col += m8[t]
+                for pj, (pi, c_) in enumerate(paths):
+                    entries.append((col + pj * pw[t], pi, M, c_))
+                col += gcols(t, len(paths))
             for c, u0 in enumerate(range(0, kpad, KC2)):
                 kc = min(KC2, kpad - u0)
                 ku = np.arange(u0, min(u0 + kc, K))
@@ -1001,9 +1023,27 @@ class MessagePackOp:
             w_cache[key] = off0
             return off0
 
-        passes, pieces, batches, dsts = [], [], [], []
+        # SIMT slots are owned by ONE gate-warp half (their accumulator columns are updated by that warp only, in piece
+        # order: deterministic); balance the estimated work of the two halves
+        simt_cost = {}
+        for (m3_, t, bi, m1), plist_ in steps.items():
+            if is_simt[t]:
+                simt_cost[t] = simt_cost.get(t, 0) + gcols(t, len(plist_)) // 8 * (40 + 8 * m4[t] * 5 // 4)
+        owner, load = {}, [0, 0]
+        for t in sorted(simt_cost, key=lambda q: -simt_cost[q]):
+            h = 0 if load[0] <= load[1] else 1
+            owner[t] = h
+            load[h] += simt_cost[t]
+        self.rot2_simt_owner = owner
+
+        KIND_TENSOR, KIND_SIMT, KIND_DUMMY = 0, 1, 2
+        ONES = 0xFFFFFFFF
+        self.rot2_gstride = (max(self.n_channels) + 3) // 4 * 4 + 4   # gate columns per branch (+4: a 4-column block may overhang)
+        passes, pieces, dsts, gpfs = [], [], [], []
+        streams = ([], [])
         ccol = np.full((max(1, ntypes), 2 * max(lmax3, 0) + 1), -1, dtype=np.int32)    # C' row column of (slot, l3 + m3)
         out_col = 0
+        tensor_toggle = 0
         for m3 in range(-lmax3, lmax3 + 1):
             slots = [t for t in range(ntypes) if self.tc_types_c[t].l >= abs(m3) and any(k[0] == m3 and k[1] == t for k in steps)]
             # greedy subsets with <= ACC accumulator columns
@@ -1023,7 +1063,8 @@ class MessagePackOp:
                     acc0[t] = a
                     ccol[t, self.tc_types_c[t].l + m3] = out_col + a
                     a += int(self.tc_types_c[t].mul)
-                p_begin, b_begin = len(pieces), len(batches)
+                p_begin = len(pieces)
+                s_begin = (len(streams[0]), len(streams[1]))
                 for bi in range(self.rot_n_blocks):
                     blk = self.rot_blocks_c[bi]
                     for m1 in ([m3] if m3 == 0 else [m3, -m3]):
@@ -1034,64 +1075,100 @@ class MessagePackOp:
                             if (m3, t, bi, m1) not in steps:
                                 continue
                             plist_ = steps[(m3, t, bi, m1)]
-                            mp = int(self.tc_types_c[t].mpad)
-                            per = max(1, min(NB // m8[t], self.R2_LMAX_FLOATS // (2 * m8[t] * mp)))   # paths per destination group
+                            per = max(1, min(NB // pw[t], self.R2_LMAX_FLOATS // l_size(t, 1)))   # paths per destination group
+                            while per > 1 and (gcols(t, per) > NB or l_size(t, per) > self.R2_LMAX_FLOATS):
+                                per -= 1
                             for q in range(0, len(plist_), per):
                                 groups.append((t, plist_[q:q + per]))
                         # pack the destination groups into pieces
                         cur_g, cols, sw, lf = [], 0, 0, 0
                         packed = []
                         for t, paths in groups:
-                            mp = int(self.tc_types_c[t].mpad)
-                            kc_ = len(paths) * m8[t]
-                            assert kc_ <= NB and mp <= SW and 2 * kc_ * mp <= self.R2_LMAX_FLOATS
-                            if cur_g and (cols + kc_ > NB or sw + mp > SW or lf + 2 * kc_ * mp > self.R2_LMAX_FLOATS):
+                            mp = 0 if is_simt[t] else int(self.tc_types_c[t].mpad)
+                            kc_ = gcols(t, len(paths))
+                            lsz = l_size(t, len(paths))
+                            assert kc_ <= NB and mp <= SW and lsz <= self.R2_LMAX_FLOATS
+                            if cur_g and (cols + kc_ > NB or sw + mp > SW or lf + lsz > self.R2_LMAX_FLOATS):
                                 packed.append(cur_g)
                                 cur_g, cols, sw, lf = [], 0, 0, 0
                             cur_g.append((t, paths))
-                            cols += kc_; sw += mp; lf += 2 * kc_ * mp
+                            cols += kc_; sw += mp; lf += lsz
                         if cur_g:
                             packed.append(cur_g)
                         for gl in packed:
-                            cols = sum(len(paths) * m8[t] for t, paths in gl)
+                            cols = sum(gcols(t, len(paths)) for t, paths in gl)
                             ncols = (cols + 15) // 16 * 16
                             l_off, l_floats, rels = l_block(gl)
                             w_off = w_block(bi, gl, ncols)
                             d_begin = len(dsts)
                             col, s_off = 0, 0
-                            bt_begin = len(batches)
+                            mine = ([], [])        # batches of this piece per gate-warp half
+                            gst = self.rot2_gstride
                             for (t, paths), rel in zip(gl, rels):
                                 ty = self.tc_types_c[t]
                                 M, mp = int(ty.mul), int(ty.mpad)
-                                kc_ = len(paths) * m8[t]
-                                dsts.append(L.Rot2DstT(col, kc_, mp, s_off, acc0[t], M, rel))
-                                for pi, c in paths:
-                                    pa = self.tc_paths_c[pi]
-                                    for q in range(0, m8[t], 8):
-                                        nvalid = max(0, min(8, M - q))
-                                        if pa.kind == 0:
-                                            meta_ = (int(pa.pad0) + q) | (int(pa.branch) << 20) | (nvalid << 24)
-                                        else:
-                                            meta_ = 0xFFFFF | (nvalid << 24)
-                                        batches.append(L.Rot2BatchT(meta_, 1.0))   # scale folded into W (field kept for the ABI)
+                                kc_ = gcols(t, len(paths))
+                                if not is_simt[t]:
+                                    dsts.append(L.Rot2DstT(col, kc_, mp, s_off, acc0[t], M, rel))
+                                    s_off += mp
+                                nb_group = kc_ // 8
+
+                                def goff(c):
+                                    """gate block (4 columns x 128 edges) of group column c: float offset inside the tile's
+                                    [branch][gstride][128] gate block; ONES for un-gated / padding columns."""
+                                    pj, w0 = c // pw[t], c % pw[t]
+                                    if pj >= len(paths):
+                                        return ONES
+                                    pa = self.tc_paths_c[paths[pj][0]]
+                                    if pa.kind != 0 or w0 >= M:
+                                        return ONES
+                                    return (int(pa.branch) * gst + int(pa.pad0) + w0) * T
+
+                                for q in range(nb_group):
+                                    c8 = (col + 8 * q) // 8
+                                    ga_, gb_ = goff(8 * q), goff(8 * q + 4)
+                                    if is_simt[t]:
+                                        h = owner[t]
+                                        meta_ = KIND_SIMT | (c8 << 8) | (M << 16) | (acc0[t] << 21) | ((q == 0) << 4) | ((q == nb_group - 1) << 5)
+                                        mine[h].append([meta_, ga_, gb_, rel + 8 * q * m4[t]])
+                                    else:
+                                        h = tensor_toggle
+                                        tensor_toggle ^= 1
+                                        mine[h].append([KIND_TENSOR | (c8 << 8), ga_, gb_, 0])
                                 col += kc_
-                                s_off += mp
-                            for _ in range((ncols - cols) // 8):
-                                batches.append(L.Rot2BatchT(0xFFFFF, 0.0))          # padding columns: nvalid = 0
+                            for h in (0, 1):
+                                if not mine[h]:
+                                    mine[h].append([KIND_DUMMY, ONES, ONES, 0])     # the warp still waits and arrives
+                                mine[h][0][0] |= 1 << 2                               # first batch of the piece
+                                mine[h][-1][0] |= 1 << 3                              # last batch of the piece
+                                for meta_, ga_, gb_, lo_ in mine[h]:
+                                    streams[h].append(L.Rot2BatchT(meta_, ga_, gb_, lo_))
+                            gp0 = len(gpfs)
+                            for t, paths in gl:
+                                for pi, _ in paths:
+                                    pa = self.tc_paths_c[pi]
+                                    if pa.kind == 0:
+                                        gpfs.append(L.Rot2GpfT((int(pa.branch) * gst + int(pa.pad0)) * T, m4[t] * T * 4))
                             pieces.append(L.Rot2PieceT(int(blk.xoff) + (int(blk.l1) + m1) * 2 * int(blk.kpad) * T, w_off, l_off,
-                                                       l_floats, bt_begin, d_begin, int(blk.kpad), ncols, len(gl), 0))
-                passes.append(L.Rot2PassT(p_begin, len(pieces), a, out_col, b_begin, len(batches), 0, 0))
+                                                       l_floats, gp0, d_begin, int(blk.kpad), ncols, len(dsts) - d_begin, len(gpfs) - gp0))
+                passes.append(L.Rot2PassT(p_begin, len(pieces), a, out_col, s_begin[0], len(streams[0]), s_begin[1], len(streams[1])))
                 out_col += a
+        # the two streams live in one table: half 1 after half 0
+        n0 = len(streams[0])
+        for ps_ in passes:
+            ps_.stream1_begin += n0
+            ps_.stream1_end += n0
+        batches = streams[0] + streams[1]
         self.tc_w_total = (wcur + 3) // 4 * 4
         self.rot2_passes_c = (L.Rot2PassT * max(1, len(passes)))(*passes)
         self.rot2_pieces_c = (L.Rot2PieceT * max(1, len(pieces)))(*pieces)
         self.rot2_batches_c = (L.Rot2BatchT * max(1, len(batches)))(*batches)
         self.rot2_dsts_c = (L.Rot2DstT * max(1, len(dsts)))(*dsts)
+        self.rot2_gpf_c = (L.Rot2GpfT * max(1, len(gpfs)))(*gpfs)
+        self.rot2_n_gpf = len(gpfs)
         self.rot2_n = (len(passes), len(pieces), len(batches), len(dsts))
         self.rot2_ccol = ccol
         self.rot2_rowstride = out_col
-        assert out_col == sum(int(self.tc_types_c[t].mul) * (2 * int(self.tc_types_c[t].l) + 1) for t in range(ntypes)
-                              if any(k[1] == t for k in steps)) or True
 
     def rot_supported(self) -> bool:
         return (self.tc_supported() and self.rot_lmax <= 6 and len(self.irreps_out) <= 32 and self.rot_n_steps > 0
@@ -1124,7 +1201,7 @@ class MessagePackOp:
     def rot2_plan(self, device) -> "L.Rot2Plan":
         st = self._device_state(device)
         if "rot2_plan" not in st:
-            for name in ("passes", "pieces", "batches", "dsts"):
+            for name in ("passes", "pieces", "batches", "dsts", "gpf"):
                 arr = getattr(self, f"rot2_{name}_c")
                 st[f"rot2_{name}"] = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
             p = L.Rot2Plan()
@@ -1135,7 +1212,8 @@ class MessagePackOp:
                 p.slot_l[t], p.slot_mul[t], p.slot_out_off[t] = ty.l, ty.mul, ty.out_off
                 for m in range(13):
                     p.ccol[t][m] = int(self.rot2_ccol[t, m]) if m < self.rot2_ccol.shape[1] else -1
-            for name in ("passes", "pieces", "batches", "dsts"):
+            p.n_gpf = self.rot2_n_gpf
+            for name in ("passes", "pieces", "batches", "dsts", "gpf"):
                 setattr(p, name, st[f"rot2_{name}"].data_ptr())
                 setattr(p, f"{name}_host", C.cast(getattr(self, f"rot2_{name}_c"), C.c_void_p).value)
             st["rot2_plan"] = p
@@ -1236,8 +1314,10 @@ class MessagePackOp:
             dev = out.device
             dw = wigner_for(self, edge_vec)
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
-            gstride = (max(self.n_channels) + 3) // 4 * 4
-            g_ws = workspace("gate", nb * chunk * gstride, dev)                                  # [nb][tile][gstride][128]
+            gstride = self.rot2_gstride
+            # [tile][nb][gstride][128]; zero-initialised once: the kernel reads whole 4-column blocks, the columns past a
+            # branch's width are never written and multiply B columns that are exactly zero
+            g_ws = workspace("gate2", nb * chunk * gstride, dev, zero=True)
             xp_ws = workspace("xp", (chunk // self.ROT_TILE) * self.rot_tile_stride, dev)
             cp_ws = workspace("cp", max(1, E) * self.rot2_rowstride, dev)                        # aligned-frame messages of all edges
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))

@@ -221,29 +221,47 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
  *            -- the receiver reduction is a serial sum over a receiver-sorted segment (deterministic, no atomics).
  */
 typedef struct {
-  int32_t piece_begin, piece_end; /* pieces of the pass                                                    */
-  int32_t ncols;                  /* accumulator columns (<= 128)                                         */
-  int32_t out_col0;               /* first column of the pass in a cp row                                 */
-  int32_t batch_begin, batch_end; /* gate batches of the pass (contiguous over its pieces)                */
-  int32_t pad0, pad1;
+  int32_t piece_begin, piece_end;     /* pieces of the pass                                                  */
+  int32_t ncols;                      /* accumulator columns (<= 128)                                       */
+  int32_t out_col0;                   /* first column of the pass in a cp row                               */
+  int32_t stream0_begin, stream0_end; /* gate stream of warp half 0 (entries of `batches`)                  */
+  int32_t stream1_begin, stream1_end; /* gate stream of warp half 1                                         */
 } hgb_rot2_pass_t;
 
 typedef struct {
   int32_t a_off;       /* float offset of the image X'_{block, m1} inside a packed tile (hgb_rot_block_t layout)   */
-  int32_t w_off;       /* wbuf offset of the concatenated W: per chunk of 16 channels (hi | lo) [kc/4][ncols][4]   */
-  int32_t l_off;       /* wbuf offset of the piece's L' stacks (all destination groups, contiguous)                */
+  int32_t w_off;       /* wbuf offset of the concatenated W: per chunk of 16 channels (hi | lo) [kc/4][ncols][4];
+                          the w3j scale of every (path, m1, m3) step is folded into its columns                   */
+  int32_t l_off;       /* wbuf offset of the piece's L' operands (all destination groups, contiguous)              */
   int32_t l_floats;    /* their size (<= 8192 floats)                                                              */
-  int32_t batch_begin; /* ncols / 8 gate batches                                                                   */
-  int32_t dst_begin;
+  int32_t gpf_begin;   /* gate blocks of the piece (hgb_rot2_gpf_t entries), pulled into L2 ahead of the gate warps         */
+  int32_t dst_begin;   /* tensor-core destination groups (GEMM2)                                                   */
   int16_t kpad;        /* K of GEMM1 (multiple of 8)                                                               */
   int16_t ncols;       /* N of GEMM1 (multiple of 16, <= 96)                                                       */
-  int16_t ndst;
-  int16_t pad;
+  int16_t ndst;        /* may be 0: every destination of the piece applies L' on the FMA pipes                     */
+  int16_t gpf_n;
 } hgb_rot2_piece_t;
 
 typedef struct {
-  int32_t meta;        /* gate column | branch << 20 | nvalid << 24; column 0xFFFFF: un-gated (g = 1)              */
-  float scale;         /* w3j(l1,l2,l3)[m1, 0, m3] * sqrt(2 l2 + 1) of the path                                    */
+  uint32_t off;        /* float offset inside the tile's gate block [branch][gstride][128]                          */
+  uint32_t bytes;      /* contiguous bytes (columns x 512)                                                          */
+} hgb_rot2_gpf_t;
+
+/* Gate-stream entry: 8 consecutive B columns of a piece, processed by one gate-warp half (thread = edge):
+ *   b_j = B[z][8 col8 + j] * g[z][block(j)]   (g = 1 where the block offset is 0xFFFFFFFF: un-gated or padding columns)
+ *   kind 0 (tensor): b is split hi/lo and written back to TMEM, GEMM2 multiplies by the (hi | lo) L' stack;
+ *   kind 1 (FMA pipes, slots with multiplicity <= 16, paths packed at 4-column granularity): s[w'] += b_j L'[j][w'] with
+ *            plain fp32 L' rows [8][round4(mul)] at l_off inside the piece's L' block; group-first zeroes s, group-last
+ *            adds s into the accumulator columns acc_col0 .. acc_col0 + mul (each such slot belongs to ONE warp half, so its
+ *            columns are updated in a fixed order);
+ *   kind 2 (dummy): the half has no columns in this piece but still waits for GEMM1 and signals GEMM2.
+ * The radial gate of a chunk is laid out [tile][branch][gstride][128 edges] (hgb_radial_gate layout 2). */
+typedef struct {
+  int32_t meta;        /* kind | first-of-piece << 2 | last-of-piece << 3 | group-first << 4 | group-last << 5 | col8 << 8 |
+                          mul << 16 | acc_col0 << 21                                                               */
+  uint32_t goff_a;     /* float offset of the gate block of columns 0-3 inside the tile's gate block                */
+  uint32_t goff_b;     /* ... of columns 4-7                                                                       */
+  int32_t l_off;
 } hgb_rot2_batch_t;
 
 typedef struct {
@@ -265,10 +283,13 @@ typedef struct {
   const hgb_rot2_piece_t* pieces;     /* device */
   const hgb_rot2_batch_t* batches;    /* device */
   const hgb_rot2_dst_t* dsts;         /* device */
+  const hgb_rot2_gpf_t* gpf;          /* device */
+  int64_t n_gpf;
   const hgb_rot2_pass_t* passes_host;
   const hgb_rot2_piece_t* pieces_host;
   const hgb_rot2_batch_t* batches_host;
   const hgb_rot2_dst_t* dsts_host;
+  const hgb_rot2_gpf_t* gpf_host;
 } hgb_rot2_plan;
 
 /* g_ws / xp_ws: per-chunk workspaces as in hgb_msgpack_rot_forward; cp_ws: n_edges * rowstride floats (all edges).

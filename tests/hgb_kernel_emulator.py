@@ -420,8 +420,8 @@ def emulate_unrotate(op: MessagePackOp, CP: torch.Tensor, Dw: torch.Tensor, seg_
 
 
 def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, vec, rbf, seg_ptr=None, seg_order=None):
-    """Mirrors the 'rot2' pipeline: wigner -> rotate_pack -> radial gate -> msgpack_rot2_kernel (passes / pieces / gate
-    batches / destination groups from the rot2 tables) -> unrotate_kernel."""
+    """Mirrors the 'rot2' pipeline: wigner -> rotate_pack -> radial gate -> msgpack_rot2_kernel (passes / pieces, the two
+    gate streams with tensor / SIMT / dummy entries, tensor destination groups) -> unrotate_kernel."""
     from hamgnn_b200 import so3
     T, KC, KC2 = op.ROT_TILE, op.ROT_KC, op.R2_KC
     E = rbf.shape[0]
@@ -442,35 +442,78 @@ def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, v
         ps = op.rot2_passes_c[pi]
         assert ps.ncols <= op.R2_ACC
         acc = torch.zeros(E, ps.ncols, dtype=dt)
-        bt_expected = ps.batch_begin
+        cur = [ps.stream0_begin, ps.stream1_begin]
+        end = [ps.stream0_end, ps.stream1_end]
+        s_run = [None, None]
         for qi in range(ps.piece_begin, ps.piece_end):
             pc = op.rot2_pieces_c[qi]
-            assert pc.ncols % 16 == 0 and pc.ncols <= op.R2_NB and pc.kpad % 8 == 0 and pc.batch_begin == bt_expected
+            assert pc.ncols % 16 == 0 and pc.ncols <= op.R2_NB and pc.kpad % 8 == 0
             assert pc.w_off % 4 == 0 and pc.l_off % 4 == 0 and pc.l_floats % 4 == 0 and pc.l_floats <= op.R2_LMAX_FLOATS
             A = _decode_a(XP, pc.a_off, pc.kpad, E, T, KC)
             W = torch.cat([_decode_image(wbuf, pc.w_off + 2 * pc.ncols * KC2 * c, pc.ncols, min(KC2, pc.kpad - u0))
                            for c, u0 in enumerate(range(0, pc.kpad, KC2))], dim=0)
             B = A @ W
-            for k in range(pc.ncols // 8):
-                bt = op.rot2_batches_c[pc.batch_begin + k]
-                col, br, nv = bt.meta & 0xFFFFF, (bt.meta >> 20) & 0xF, (bt.meta >> 24) & 0xF
-                gv = torch.zeros(E, 8, dtype=dt)
-                if nv:
-                    gv[:, :nv] = 1.0 if col == 0xFFFFF else g[br][:, col:col + nv]
-                B[:, 8 * k:8 * k + 8] *= gv * bt.scale
-            bt_expected += pc.ncols // 8
+            Bg = torch.zeros_like(B)
+            covered = torch.zeros(pc.ncols // 8, dtype=torch.bool)
+            gst = op.rot2_gstride
+
+            def gate4(off):
+                if off == 0xFFFFFFFF:
+                    return torch.ones(E, 4, dtype=dt)
+                assert off % T == 0
+                br, col = divmod(off // T, gst)
+                assert br < len(g) and col + 4 <= gst
+                out = torch.zeros(E, 4, dtype=dt)           # columns beyond the branch's width: zero-initialised workspace
+                nvv = max(0, min(4, g[br].shape[1] - col))
+                out[:, :nvv] = g[br][:, col:col + nvv]
+                return out
+
+            for h in (0, 1):
+                first = True
+                while True:
+                    assert cur[h] < end[h]
+                    bt = op.rot2_batches_c[cur[h]]
+                    cur[h] += 1
+                    meta = bt.meta & 0xFFFFFFFF
+                    kind = meta & 3
+                    assert bool((meta >> 2) & 1) == first
+                    first = False
+                    if kind != 2:
+                        c8 = (meta >> 8) & 0xFF
+                        assert not covered[c8]
+                        covered[c8] = True
+                        gv = torch.cat([gate4(bt.goff_a), gate4(bt.goff_b)], dim=1)
+                        bg = B[:, 8 * c8:8 * c8 + 8] * gv
+                        if kind == 0:
+                            Bg[:, 8 * c8:8 * c8 + 8] = bg
+                        else:
+                            M, acc0 = (meta >> 16) & 0x1F, (meta >> 21) & 0xFF
+                            m4 = (M + 3) // 4 * 4
+                            assert M <= op.R2_SIMT_MAX and bt.l_off % 4 == 0 and bt.l_off + 8 * m4 <= pc.l_floats
+                            Lr = wbuf[pc.l_off + bt.l_off:pc.l_off + bt.l_off + 8 * m4].view(8, m4)
+                            if (meta >> 4) & 1:
+                                s_run[h] = torch.zeros(E, m4, dtype=dt)
+                            s_run[h] = s_run[h] + bg @ Lr
+                            if (meta >> 5) & 1:
+                                assert float(s_run[h][:, M:].abs().max()) == 0 if M < m4 else True
+                                acc[:, acc0:acc0 + M] += s_run[h][:, :M]
+                                s_run[h] = None
+                    if (meta >> 3) & 1:
+                        break
+            # every non-padding 8-column batch of the piece is gated exactly once
             s_used = 0
             for di in range(pc.dst_begin, pc.dst_begin + pc.ndst):
                 ds = op.rot2_dsts_c[di]
                 assert ds.col0 % 8 == 0 and ds.kcols % 8 == 0 and ds.col0 + ds.kcols <= pc.ncols and ds.mp % 16 == 0
                 assert ds.s_off == s_used and ds.s_off + ds.mp <= op.R2_SW and ds.acc_col0 + ds.mul <= ps.ncols
                 assert ds.l_rel + 2 * ds.kcols * ds.mp <= pc.l_floats
+                assert bool(covered[ds.col0 // 8:(ds.col0 + ds.kcols) // 8].all())
                 s_used += ds.mp
                 Lst = _decode_image(wbuf, pc.l_off + ds.l_rel, ds.mp, ds.kcols)          # [kcols, mp]
-                S = B[:, ds.col0:ds.col0 + ds.kcols] @ Lst
+                S = Bg[:, ds.col0:ds.col0 + ds.kcols] @ Lst
                 acc[:, ds.acc_col0:ds.acc_col0 + ds.mul] += S[:, :ds.mul]
                 assert float(S[:, ds.mul:].abs().max()) == 0 if ds.mul < ds.mp else True
-        assert bt_expected == ps.batch_end
+        assert cur == end and s_run == [None, None]
         assert not seen[ps.out_col0:ps.out_col0 + ps.ncols].any()
         seen[ps.out_col0:ps.out_col0 + ps.ncols] = True
         CP[:, ps.out_col0:ps.out_col0 + ps.ncols] = acc

@@ -43,7 +43,7 @@ def test_ctypes_struct_sizes_match_the_c_compiler():
                "hgb_linear_plan": L.LinearPlan, "hgb_gate_desc": L.GateDesc, "hgb_ham_plan": L.HamPlan,
                "hgb_rot_block_t": L.RotBlockT, "hgb_rot_step_t": L.RotStepT, "hgb_rot_plan": L.RotPlan,
                "hgb_rot2_pass_t": L.Rot2PassT, "hgb_rot2_piece_t": L.Rot2PieceT, "hgb_rot2_batch_t": L.Rot2BatchT,
-               "hgb_rot2_dst_t": L.Rot2DstT, "hgb_rot2_plan": L.Rot2Plan}
+               "hgb_rot2_dst_t": L.Rot2DstT, "hgb_rot2_gpf_t": L.Rot2GpfT, "hgb_rot2_plan": L.Rot2Plan}
     prog = '#include <stdio.h>\n#include "hamgnn_b200.h"\nint main(void){\n' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));\n' for n in structs) + "return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
