@@ -128,6 +128,7 @@ extern "C" int hgb_edge_embed(const float* pos, const float* nbr_shift, const in
                               int32_t num_radial, float* sh, float* rbf, float* edge_vec, float* edge_len,
                               void* stream) {
   HGB_DEVICE_GUARD(sh);
+  hgb::TimeScope ts_(HGB_K_EDGE_EMBED, stream);
   HGB_CHECK_ARG(n_edges >= 0, "hgb_edge_embed: negative edge count");
   HGB_CHECK_ARG(num_radial >= 1 && num_radial <= 128, "hgb_edge_embed: num_radial %d out of range [1,128]", num_radial);
   HGB_CHECK_ARG(n_ls >= 1 && n_ls <= HGB_MAX_L + 1, "hgb_edge_embed: bad number of SH irreps %d", n_ls);

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(HT) ham_finalize_so3_kernel(const __grid_const
 extern "C" int hgb_ham_assemble(const hgb_ham_plan* plan, const float* coef, int64_t n_rows, float* raw, void* stream) {
   HGB_DEVICE_GUARD(raw);
   HGB_CHECK_ARG(plan && coef && raw, "hgb_ham_assemble: NULL argument");
+  hgb::TimeScope ts_(HGB_K_HAM_ASSEMBLE, stream);
   HGB_CHECK_ARG(plan->nao > 0 && plan->nao <= 64 && plan->n_coef > 0, "hgb_ham_assemble: bad plan (nao=%d)", plan->nao);
   if (n_rows == 0) return 0;
   return hgb_csr_rows(plan->row_ptr, plan->col, plan->val, plan->nao * plan->nao, plan->n_coef, coef, n_rows, raw, stream);
@@ -241,6 +242,7 @@ extern "C" int hgb_ham_finalize(const hgb_ham_plan* plan, const float* raw, cons
                                 int64_t n_rows, int32_t symmetrize, float* out, void* stream) {
   HGB_DEVICE_GUARD(out);
   HGB_CHECK_ARG(plan && raw && z && out, "hgb_ham_finalize: NULL argument");
+  hgb::TimeScope ts_(HGB_K_HAM_FINALIZE, stream);
   HGB_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31), "hgb_ham_finalize: bad row count");
   if (n_rows == 0) return 0;
   FinArgs a;

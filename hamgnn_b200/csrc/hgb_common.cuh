@@ -11,6 +11,14 @@ namespace hgb {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void timing_begin(int id, void* stream);
+void timing_end(int id, void* stream);
+struct TimeScope {   // brackets the kernel launches of one scope with CUDA events when hgb_timing_enable(1) is in effect
+  int id;
+  void* st;
+  TimeScope(int id_, void* st_) : id(id_), st(st_) { timing_begin(id, st); }
+  ~TimeScope() { timing_end(id, st); }
+};
 
 // Kernels must launch on the device that owns the buffers, whatever the caller's current device is (a model moved to
 // cuda:1 without cudaSetDevice(1)): switch to the device of `p` for the duration of the entry point.

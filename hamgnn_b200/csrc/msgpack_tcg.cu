@@ -667,6 +667,7 @@ extern "C" int hgb_wigner(const hgb_rot_plan* rp, const float* edge_vec, int64_t
   HGB_CHECK_ARG(rp && edge_vec && dw && rp->wigner_j, "hgb_wigner: NULL argument");
   HGB_CHECK_ARG(rp->lmax >= 0 && rp->lmax <= rot::LMAX, "hgb_wigner: lmax %d unsupported (<= %d)", rp->lmax, rot::LMAX);
   HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_wigner: bad edge count");
+  hgb::TimeScope ts_(HGB_K_WIGNER, stream);
   for (int l = 0; l <= rp->lmax; ++l)
     HGB_CHECK_ARG(rp->doff[l] >= 0 && rp->doff[l] + (2 * l + 1) * (2 * l + 1) <= rp->dstride, "hgb_wigner: D^%d block outside the row", l);
   if (n_edges == 0) return 0;
@@ -995,12 +996,16 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
     const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
     const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
     {
+      hgb::TimeScope ts(HGB_K_RADIAL_GATE, stream);
       const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 2);
       if (rc != 0) return rc;
     }
     pa.e_lo = e_lo; pa.n_chunk = n;
-    rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
-    HGB_LAUNCH_OK("rotate_pack_kernel");
+    {
+      hgb::TimeScope ts(HGB_K_ROTATE_PACK, stream);
+      rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
+      HGB_LAUNCH_OK("rotate_pack_kernel");
+    }
     ka.e_lo = e_lo; ka.n_chunk = n;
     // HGB_ROT2_TRACE=<file>: per-role clock64 stamps of one CTA (pass HGB_ROT2_TRACE_PASS of tile 0) appended to <file>;
     // a diagnosis aid (one extra sync per launch), off unless the variable is set
@@ -1016,8 +1021,11 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
       HGB_CUDA_OK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * (10 * trace_pieces + 1024), st));
       ka.trace = d_trace;
     }
-    rot2::msgpack_rot2_kernel<<<(unsigned)(n_tiles * r2->n_passes), rot2::NTHR, rot2::SMEM_BYTES, st>>>(ka);
-    HGB_LAUNCH_OK("msgpack_rot2_kernel");
+    {
+      hgb::TimeScope ts(HGB_K_MSGPACK_ROT2, stream);
+      rot2::msgpack_rot2_kernel<<<(unsigned)(n_tiles * r2->n_passes), rot2::NTHR, rot2::SMEM_BYTES, st>>>(ka);
+      HGB_LAUNCH_OK("msgpack_rot2_kernel");
+    }
     if (d_trace) {
       static long long h_trace[10 * 128 + 1024];
       HGB_CUDA_OK(cudaStreamSynchronize(st));
@@ -1050,6 +1058,7 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
     }
   }
   if (n_out_rows > 0) {
+    hgb::TimeScope ts(HGB_K_UNROTATE, stream);
     rot2::unrotate_kernel<<<(unsigned)n_out_rows, (unsigned)(32 * ua.n_warps), 0, st>>>(ua);
     HGB_LAUNCH_OK("unrotate_kernel");
   }

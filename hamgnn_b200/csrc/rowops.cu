@@ -6,6 +6,7 @@
 // owns one output column (slot, channel w, component k) reads the TR row values of an input column with two
 // 128-bit loads and keeps TR accumulators in registers: per input channel u it issues 1 weight load + 2 shared
 // loads for 8 FMAs (the stride of 12 floats keeps the quarter-warp 128-bit accesses on distinct banks).
+#include <stdlib.h>
 #include "hgb_common.cuh"
 
 namespace {
@@ -174,6 +175,126 @@ __global__ void __launch_bounds__(RO_THREADS) resblock_kernel(const __grid_const
   store_tile(sh, a.y, r0, nr, DP);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// resblock2_kernel: the same Linear -> Gate -> Linear (+ residual) [-> Linear] chain on 16-row tiles.
+//
+// resblock_kernel (8 rows per CTA, one thread per output column, weights read through L1/L2 per input channel) ran the
+// off-site HamLayer of tbg_m8 at 51 GB/s = 0.8 % of the HBM roofline: every thread's inner loop is a
+// chain of dependent weight loads with 8 warps per SM to hide them.  Here
+//   * the row tiles are row-major in shared memory ([16][dim], three of them = 177 KB for D = 877);
+//   * a Linear block is evaluated by items (output chunk of 8 channels, row, component): the block's weights are staged
+//     once per CTA in shared memory ([u][mul_out padded to 4]) and read as warp-broadcast float4, the input value is one
+//     conflict-free LDS (row stride = dim is odd for the irreps in use) -- 8 FMAs per 3 shared loads, no global load in the loop;
+//   * 512 threads per CTA.
+constexpr int RB2_ROWS = 16;
+constexpr int RB2_THREADS = 512;
+constexpr int RB2_WFLOATS = 8192;   // weight staging buffer
+
+__device__ __forceinline__ void lin_apply2(const hgb_linblock_t* __restrict__ blocks, int nb, const float* __restrict__ w,
+                                           const float* sin, int ldin, float* sout, int ldout, float* sw) {
+  for (int b = 0; b < nb; ++b) {
+    const hgb_linblock_t B = blocks[b];
+    const int mo4 = (B.mul_out + 3) & ~3;
+    const int rows_per_chunk = min(B.mul_in, RB2_WFLOATS / mo4);
+    const int nwc = (B.mul_out + 7) >> 3;
+    const int per_wc = RB2_ROWS * B.dim;
+    const int items = nwc * per_wc;
+    for (int u0 = 0; u0 < B.mul_in; u0 += rows_per_chunk) {
+      const int rc = min(rows_per_chunk, B.mul_in - u0);
+      __syncthreads();   // the previous chunk's readers are done with sw; the previous block's writers with sout
+      for (int idx = threadIdx.x; idx < rc * mo4; idx += RB2_THREADS) {
+        const int ur = idx / mo4, wc = idx - ur * mo4;
+        sw[idx] = (wc < B.mul_out) ? __ldg(w + B.w_off + (size_t)(u0 + ur) * B.mul_out + wc) : 0.f;
+      }
+      __syncthreads();
+      for (int it = threadIdx.x; it < items; it += RB2_THREADS) {
+        const int wc = it / per_wc, rk = it - wc * per_wc;
+        const int r = rk / B.dim, k = rk - r * B.dim;
+        const float* xi = sin + (size_t)r * ldin + B.in_off + (size_t)u0 * B.dim + k;
+        const float* wr = sw + wc * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const bool two = wc * 8 + 4 < mo4;   // the last chunk of 8 may hold one float4 only
+#pragma unroll 4
+        for (int ur = 0; ur < rc; ++ur) {
+          const float xv = xi[(size_t)ur * B.dim];
+          const float4 w0 = *reinterpret_cast<const float4*>(wr + ur * mo4);
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          if (two) {
+            const float4 w1 = *reinterpret_cast<const float4*>(wr + ur * mo4 + 4);
+            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          }
+        }
+        float* o = sout + (size_t)r * ldout + B.out_off + (size_t)(wc * 8) * B.dim + k;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (wc * 8 + j < B.mul_out) o[(size_t)j * B.dim] += acc[j];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_rows2(float* s, int lds, const float* __restrict__ g, int64_t r0, int nr, int dim, bool add) {
+  for (int idx = threadIdx.x; idx < RB2_ROWS * dim; idx += RB2_THREADS) {
+    const int r = idx / dim, c = idx - r * dim;
+    const float v = (r < nr) ? __ldg(g + (r0 + r) * (int64_t)dim + c) : 0.f;
+    if (add) s[(size_t)r * lds + c] += v;
+    else s[(size_t)r * lds + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(RB2_THREADS, 1) resblock2_kernel(const __grid_constant__ ResArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = a.lin1.in_dim;
+  const int ldh = a.wide | 1;   // odd row stride: conflict-free column access across rows
+  float* sx = smem;                              // [16][D]    x, later y = x (+ extra) + Lin2(gated)
+  float* sh = sx + (size_t)RB2_ROWS * D;         // [16][wide] gate input, later the post-Linear output
+  float* sa = sh + (size_t)RB2_ROWS * ldh;    // [16][D]    gated row
+  float* sw = sa + (size_t)RB2_ROWS * D;         // weight staging
+  const int64_t r0 = (int64_t)blockIdx.x * RB2_ROWS;
+  const int nr = (int)min((int64_t)RB2_ROWS, a.n_rows - r0);
+  load_rows2(sx, D, a.x, r0, nr, D, false);
+  for (int idx = threadIdx.x; idx < RB2_ROWS * ldh; idx += RB2_THREADS) sh[idx] = 0.f;
+  lin_apply2(a.lin1.blocks, a.lin1.n_blocks, a.lin1.w, sx, D, sh, ldh, sw);   // starts with a barrier
+  // ---- e3nn Gate, element-wise
+  const hgb_gate_desc& g = a.gate;
+  for (int s = 0; s < g.n_scalar_slots; ++s) {
+    const int n = g.sc_n[s];
+    for (int idx = threadIdx.x; idx < n * RB2_ROWS; idx += RB2_THREADS) {
+      const int r = idx / n, c = idx - r * n;
+      const float v = sh[(size_t)r * ldh + g.sc_in_off[s] + c];
+      sa[(size_t)r * D + g.sc_out_off[s] + c] = (g.sc_act[s] == 0) ? hgb::ssp_f(v) * g.c_ssp : tanhf(v) * g.c_tanh;
+    }
+  }
+  for (int s = 0; s < g.n_gated; ++s) {
+    const int per = g.gd_mul[s] * g.gd_dim[s];
+    for (int idx = threadIdx.x; idx < per * RB2_ROWS; idx += RB2_THREADS) {
+      const int r = idx / per, c = idx - r * per;
+      const int u = c / g.gd_dim[s];
+      const float gate = hgb::ssp_f(sh[(size_t)r * ldh + g.gd_gate_off[s] + u]) * g.c_ssp;
+      sa[(size_t)r * D + g.gd_out_off[s] + c] = sh[(size_t)r * ldh + g.gd_in_off[s] + c] * gate;
+    }
+  }
+  if (a.extra) load_rows2(sx, D, a.extra, r0, nr, D, true);
+  lin_apply2(a.lin2.blocks, a.lin2.n_blocks, a.lin2.w, sa, D, sx, D, sw);   // sx = x (+ extra) + Lin2(gated)
+  if (!a.has_post) {
+    for (int idx = threadIdx.x; idx < nr * D; idx += RB2_THREADS) a.y[r0 * D + idx] = sx[idx];
+    return;
+  }
+  const int DP = a.post.out_dim;
+  for (int idx = threadIdx.x; idx < RB2_ROWS * ldh; idx += RB2_THREADS) sh[idx] = 0.f;
+  lin_apply2(a.post.blocks, a.post.n_blocks, a.post.w, sx, D, sh, ldh, sw);
+  for (int idx = threadIdx.x; idx < nr * DP; idx += RB2_THREADS) {
+    const int r = idx / DP, c = idx - r * DP;
+    a.y[(r0 + r) * DP + c] = sh[(size_t)r * ldh + c];
+  }
+}
+
 }  // namespace
 
 extern "C" int hgb_linear_forward(const hgb_linear_plan* plan, const float* x, const int64_t* rows, int64_t n_rows,
@@ -186,6 +307,7 @@ extern "C" int hgb_linear_forward_ld(const hgb_linear_plan* plan, const float* x
                                      float* y, int64_t ldy, int32_t accumulate, void* stream) {
   HGB_DEVICE_GUARD(y);
   HGB_CHECK_ARG(plan && x && y, "hgb_linear_forward: NULL argument");
+  hgb::TimeScope ts_(HGB_K_LINEAR, stream);
   HGB_CHECK_ARG(n_rows >= 0, "hgb_linear_forward: negative row count");
   HGB_CHECK_ARG(ldy >= plan->out_dim, "hgb_linear_forward: output row stride %lld < out_dim %d", (long long)ldy, plan->out_dim);
   if (n_rows == 0) return 0;
@@ -204,6 +326,7 @@ extern "C" int hgb_resblock_forward(const hgb_linear_plan* lin1, const hgb_gate_
                                     float* y, void* stream) {
   HGB_DEVICE_GUARD(y);
   HGB_CHECK_ARG(lin1 && gate && lin2 && x && y, "hgb_resblock_forward: NULL argument");
+  hgb::TimeScope ts_(HGB_K_RESBLOCK, stream);
   HGB_CHECK_ARG(lin1->out_dim == gate->in_dim && lin2->in_dim == gate->out_dim && lin2->out_dim == lin1->in_dim,
                 "hgb_resblock_forward: inconsistent dims lin1 %d->%d gate %d->%d lin2 %d->%d", lin1->in_dim, lin1->out_dim,
                 gate->in_dim, gate->out_dim, lin2->in_dim, lin2->out_dim);
@@ -217,6 +340,15 @@ extern "C" int hgb_resblock_forward(const hgb_linear_plan* lin1, const hgb_gate_
   a.x = x; a.extra = extra; a.n_rows = n_rows; a.y = y;
   a.wide = gate->in_dim;
   if (post && post->out_dim > a.wide) a.wide = post->out_dim;
+  // 16-row tiles with staged weights when they fit in shared memory (D = 877: 209 KB), else the 8-row kernel
+  const size_t smem2 = ((size_t)RB2_ROWS * (2 * lin1->in_dim + (a.wide | 1)) + RB2_WFLOATS) * sizeof(float);
+  const char* force_old = getenv("HGB_RESBLOCK_V1");
+  if (smem2 <= 227 * 1024 && !(force_old && force_old[0] == '1')) {
+    HGB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    resblock2_kernel<<<(unsigned)((n_rows + RB2_ROWS - 1) / RB2_ROWS), RB2_THREADS, smem2, (cudaStream_t)stream>>>(a);
+    HGB_LAUNCH_OK("resblock2_kernel");
+    return 0;
+  }
   const size_t smem = (size_t)LDR * (2 * lin1->in_dim + a.wide) * sizeof(float);
   HGB_CHECK_ARG(smem <= 220 * 1024, "hgb_resblock_forward: row tile does not fit in shared memory");
   HGB_CUDA_OK(cudaFuncSetAttribute(resblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

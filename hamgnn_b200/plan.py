@@ -1397,7 +1397,29 @@ class MessagePackOp:
         L.check(rc, "hgb_radial_gate")
         return g
 
-    # FLOP / byte accounting for bench.py (per edge, algorithmic minimum of this formulation)
+    def flops_alg(self, radial: bool = True) -> int:
+        """ALGORITHMIC FLOPs per edge of this fused message (SURVEY.md section 8d / BASELINE.md section 3): per tensor-product
+        path the cheaper of the two contraction orders with the sparse CG table, the mid->D Linear, the out Linear, the
+        direct Linear and (radial=True) the radial MLP.  Default MessagePackBlock: 0.95 + 0.54 + 2 x 0.60 + 2 x 0.04 +
+        2 x 0.476 = 3.71 MFLOP, the survey's 3.7 M."""
+        fl = 0
+        for b, br in enumerate(self.branches):
+            if radial:
+                fl += 2 * (self.rbf_dim * self.h1 + self.h1 * self.h2 + self.h2 * self.n_channels[b])
+            for p in self.paths_by_branch[b]:
+                d1, d3, K, M = p.ir_in.dim, p.ir_out.dim, p.mul_in_total, p.mul_out
+                nnz = len(_cg_table(p.ir_in.l, p.l2, p.ir_out.l)[0])
+                cg_first = 2 * nnz + 2 * K * min(nnz, d1 * d3) + 2 * K * M * d3      # T = w3j.Y, A = x T, B = A W
+                w_first = 2 * nnz + 2 * K * M * d1 + 2 * M * min(nnz, d1 * d3)       # X W first, then the CG contraction
+                fl += min(cg_first, w_first) + M * d3                                 # + the radial gate product
+                fl += 2 * M * M * d3                                                  # mid -> D Linear
+            if br.has_out_linear:
+                fl += sum(2 * m.mul * m.mul * m.ir.dim for m in self.irreps_out)
+        if self.direct_src is not None:
+            fl += sum(2 * m.mul * m.mul * m.ir.dim for m in self.irreps_out)
+        return fl
+
+    # FLOPs of the step formulation of the 'rot' backend (kept for comparison with round 1's numbers)
     def flops_per_edge(self) -> int:
         if getattr(self, "_flops", None) is not None:
             return self._flops

@@ -207,6 +207,21 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
                             float* out, const int64_t* out_index, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Measurement aid: per-kernel device time of the library's launches, CUDA events on the launching
+ * stream.  hgb_timing_enable(1) starts recording, hgb_timing_collect adds elapsed ms / launch counts per kernel id to the
+ * caller's arrays of HGB_N_KERNEL_IDS entries (synchronises the recorded events) and clears the records. */
+enum {
+  HGB_K_RADIAL_GATE = 0, HGB_K_ROTATE_PACK = 1, HGB_K_MSGPACK_ROT2 = 2, HGB_K_UNROTATE = 3, HGB_K_WIGNER = 4,
+  HGB_K_EDGE_EMBED = 5, HGB_K_LINEAR = 6, HGB_K_RESBLOCK = 7, HGB_K_HAM_ASSEMBLE = 8, HGB_K_HAM_FINALIZE = 9,
+  HGB_K_OTHER = 10, HGB_N_KERNEL_IDS = 16
+};
+int hgb_timing_enable(int32_t on);
+int hgb_timing_collect(float* ms_out, int64_t* count_out);
+/* Diagnosis tool (csrc/mma_probe.cu): cycles per tcgen05.mma.kind::tf32 (M 128, N n, K 8) issued back to back by one thread,
+ * out_dev[0] = issue cycles, [1] = cycles until the commit barrier fires, [2] = a concurrent tcgen05.ld round trip. */
+int hgb_mma_probe(int32_t n, int32_t count, int32_t ndest, int32_t ts, int32_t same_ab, long long* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a5-a9, A-stationary form of the rotated frame ("rot2", the default message path).  Same mathematics and same call
  * sites as hgb_msgpack_rot_forward (MessagePackBlock.forward hamgnn/nn/message_passing.py:191-231, ConvBlockE3's
  * scatter-sum hamgnn/nn/convolution.py:147-149, PairInteractionBlock hamgnn/nn/interaction_blocks.py:133-164); the
