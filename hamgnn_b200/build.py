@@ -30,7 +30,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    for macro in ("HGB_ROT2_GATE_GROUPS", "HGB_ROT2_PRODUCERS"):     # experiment switches of msgpack_rot2_kernel (defaults in the sources)
+        if os.environ.get(macro):
+            flags.append(f"-D{macro}={int(os.environ[macro])}")
+    out = os.environ.get("HGB_LIB_OUT", LIB)      # experiment builds go next to the product library
+    cmd = [nvcc] + flags + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -39,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stderr)
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -79,3 +79,76 @@ extern "C" int hgb_mma_probe(int32_t n, int32_t count, int32_t ndest, int32_t ts
   HGB_LAUNCH_OK("mma_probe_kernel");
   return 0;
 }
+
+// ---- cp.async.bulk probe: lane 0 of each of `nwarps` warps issues `count` bulk copies of `bytes` from a (L2-resident after the
+// first sweep) global buffer into its own ring of `depth` shared-memory slots, each with its own mbarrier; prefetch != 0 issues
+// cp.async.bulk.prefetch.L2 instead.  out[0] = cycles per copy seen by warp 0 (issue + completion with `depth` in flight),
+// out[1] = cycles of the issue instructions alone (first `depth` copies).
+namespace {
+struct TmaArgs { const float* src; int bytes, count, depth, prefetch; long long* out; };
+__global__ void __launch_bounds__(256, 1) tma_probe_kernel(const TmaArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bars[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 64; ++i) tc::mbar_init(&bars[i], 1);
+    tc::mbar_fence_init();
+  }
+  __syncthreads();
+  if (lane == 0) {
+    const int slot_floats = a.bytes / 4;
+    float* ring = smem + (size_t)warp * a.depth * slot_floats;
+    uint64_t* wb = bars + warp * 8;
+    const float* src = a.src + (size_t)warp * 8 * slot_floats;
+    long long t_issue = 0;
+    const long long t0 = clock64();
+    int s = 0, ph = 0;
+    for (int i = 0; i < a.count; ++i) {
+      if (a.prefetch) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)(i & 7) * slot_floats), "r"((uint32_t)a.bytes) : "memory");
+      } else {
+        if (i >= a.depth) tc::mbar_wait(&wb[s], (uint32_t)(ph ^ 1));
+        const uint32_t bar = tc::smem_u32(&wb[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)a.bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(ring + s * slot_floats)),
+                     "l"(src + (size_t)(i & 7) * slot_floats), "r"((uint32_t)a.bytes), "r"(bar)
+                     : "memory");
+      }
+      if (i == a.depth - 1) t_issue = clock64() - t0;
+      if (++s == a.depth) { s = 0; ph ^= 1; }
+    }
+    if (!a.prefetch) {
+      // drain: the last phase of every slot
+      int ss = s, pp = ph;
+      for (int k = 0; k < a.depth; ++k) {
+        // slot ss was last used in phase (pp ^ 1) if ss >= s ... simply wait for the most recent completed phase of each slot
+        const int last_phase = (ss < s) ? ph : (ph ^ 1);
+        tc::mbar_wait(&wb[ss], (uint32_t)last_phase);
+        if (++ss == a.depth) ss = 0;
+        (void)pp;
+      }
+    }
+    const long long t1 = clock64();
+    if (warp == 0) {
+      a.out[0] = (t1 - t0) / a.count;
+      a.out[1] = t_issue / a.depth;
+    }
+    (void)nw;
+  }
+}
+}  // namespace
+
+extern "C" int hgb_tma_probe(const float* src_dev, int32_t bytes, int32_t count, int32_t depth, long long* out_dev, void* stream) {
+  HGB_DEVICE_GUARD(out_dev);
+  // depth encodes: low 8 bits ring depth, bits 8-15 issuing warps (0 = 1), bit 16 = prefetch.L2 instead of a copy
+  const int nwarps = ((depth >> 8) & 0xFF) ? ((depth >> 8) & 0xFF) : 1, prefetch = (depth >> 16) & 1;
+  depth &= 0xFF;
+  HGB_CHECK_ARG(src_dev && out_dev && bytes >= 16 && bytes % 16 == 0 && depth >= 1 && depth <= 8 && nwarps <= 8 &&
+                    (size_t)bytes * depth * nwarps <= 200 * 1024 && count >= depth && count % depth == 0,
+                "hgb_tma_probe: bad arguments");
+  TmaArgs a{src_dev, bytes, count, depth, prefetch, out_dev};
+  HGB_CUDA_OK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  tma_probe_kernel<<<1, 32 * nwarps, 200 * 1024, (cudaStream_t)stream>>>(a);
+  HGB_LAUNCH_OK("tma_probe_kernel");
+  return 0;
+}

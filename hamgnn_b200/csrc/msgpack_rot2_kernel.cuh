@@ -79,8 +79,18 @@ constexpr int A_LO = KC2 * TILE;                       // float offset of the A 
 constexpr int W_AT = 2 * KC2 * TILE;                   // float offset of the W chunk inside a stage
 constexpr int STG = 2 * KC2 * TILE + 2 * KC2 * NB;     // floats per ring stage (28 KB)
 constexpr int LBUF = 8192;                             // floats per L' buffer (R2_LMAX_FLOATS)
-constexpr int NTHR = 480;                              // warps 0-7 gate, 8-11 accumulate, 12 TMA, 13 GEMM1, 14 GEMM2
-constexpr int W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
+constexpr int NH = HGB_ROT2_GATE_GROUPS;               // gate-warp groups (each = 4 warps, one per TMEM lane quadrant)
+constexpr int NGW = 4 * NH;                            // gate warps
+// A cp.async.bulk costs its issuing THREAD ~400 cycles whatever its size, and the cost does not add up across warps
+// (profiles/r02v_tma_probe.txt): with one producer thread and ~14 bulk operations per piece the producer paced the whole kernel
+// (~6 000 cycles per piece, profiles/r02r trace).  The three operands of a stage are therefore issued by three warps, and the
+// L2 prefetches of later pieces by the (otherwise mostly idle) accumulate warps.
+#ifndef HGB_ROT2_PRODUCERS
+#define HGB_ROT2_PRODUCERS 1
+#endif
+constexpr int NPROD = HGB_ROT2_PRODUCERS;              // 1: one warp issues A hi, A lo, W and L'; 3: one warp each (W warp also L')
+constexpr int NTHR = 32 * (NGW + 6 + NPROD);           // warps 0..NGW-1 gate, then 4 accumulate, NPROD TMA, GEMM1, GEMM2
+constexpr int W_ACC = NGW, W_TMA = NGW + 4, W_MMA1 = NGW + 4 + NPROD, W_MMA2 = NGW + 5 + NPROD;
 constexpr uint32_t TB = 0, TGL = 2 * NB, TS = 4 * NB;  // TMEM columns
 constexpr size_t SMEM_BYTES = (size_t)(NST * STG + 2 * LBUF + ACC_COLS * ACC_LD) * sizeof(float);
 
@@ -141,7 +151,7 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   const hgb_rot2_pass_t ps = a.passes[pass];
 
   if (tid == 0) {
-    for (int i = 0; i < 17; ++i) tc::mbar_init(&bars[i], ((i >= 10 && i < 12) || i == 16) ? 8 : (i >= 14 ? 4 : 1));   // gfull / simtdone / sfree: one arrival per warp
+    for (int i = 0; i < 17; ++i) tc::mbar_init(&bars[i], i < NST ? 3 : (((i >= 10 && i < 12) || i == 16) ? NGW : (i >= 14 ? 4 : 1)));   // gfull / simtdone / sfree: one arrival per warp
     tc::mbar_fence_init();
   }
   if (warp == W_MMA1) tmem_alloc_dyn(&tmem_slot, 512);
@@ -153,34 +163,15 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
   const float* __restrict__ wbuf = a.wbuf;
   const uint32_t dhi = tc::smem_desc_hi(128);
 
-  if (warp == W_TMA) {
-    // =============================== TMA producer ===============================
-    const float* xt = a.xp + (size_t)tile * a.tile_stride;
-    // The ring holds about one piece, so the operands of the pieces after it are pulled into L2 ahead of time (the packed
-    // inputs of a chunk are GBs: the first CTA of a tile to touch an image reads it from DRAM, ~2 000 cycles)
-    const float* gtile = a.g + (size_t)tile * a.gtile_floats;
-    auto prefetch_piece = [&](int qi) {
-      if (qi >= ps.piece_end) return;
-      const PieceRec pp = load_piece(a.pieces + qi);
-      if (lane == 0) {
-        bulk_prefetch_l2(xt + pp.a_off, (uint32_t)(2 * pp.kpad * TILE) * 4u);
-        bulk_prefetch_l2(wbuf + pp.w_off, (uint32_t)(2 * pp.kpad * pp.ncols) * 4u);
-        bulk_prefetch_l2(wbuf + pp.l_off, (uint32_t)pp.l_floats * 4u);
-      }
-      // the gate blocks of the piece (the gate tensor of a chunk is GBs, written by the pre-pass): lane k takes run k
-      if (lane < pp.gpf_n) {
-        const uint2 gr = __ldg(reinterpret_cast<const uint2*>(a.gpf + pp.gpf_begin + lane));
-        bulk_prefetch_l2(gtile + gr.x, gr.y);
-      }
-    };
-    prefetch_piece(ps.piece_begin + 1);
-    prefetch_piece(ps.piece_begin + 2);
-    int n = 0, c_all = 0;
-    for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
-      const PieceRec pc = load_piece(a.pieces + qi);
-      prefetch_piece(qi + 3);
-      if (lane == 0) {
-        R2_TRACE(0, n, 0);
+  if (warp >= W_TMA && warp < W_TMA + NPROD) {
+    // =============================== TMA producers: A hi | A lo | W and L' ===============================
+    const int role = (NPROD == 1) ? -1 : warp - W_TMA;   // -1: every operand
+    if (lane == 0) {
+      const float* xt = a.xp + (size_t)tile * a.tile_stride;
+      int n = 0, c_all = 0;
+      for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
+        const PieceRec pc = load_piece(a.pieces + qi);
+        if (role <= 0) R2_TRACE(0, n, 0);
         for (int u0 = 0, c = 0; u0 < pc.kpad; u0 += KC2, ++c, ++c_all) {
           const int kc = min(KC2, pc.kpad - u0), s = c_all % NST;
           if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
@@ -189,23 +180,31 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
           // the packed image is chunked by 32 channels, (hi | lo) per chunk: this stage is half of such a chunk
           const int c32 = c >> 1, kc32 = min(KC32, pc.kpad - c32 * KC32);
           const float* ahi = xt + pc.a_off + (size_t)c32 * (2 * KC32 * TILE) + (size_t)(c & 1) * (KC2 * TILE);
-          expect_tx_a(B_FULL + 8 * s, 2 * ab + wb);
-          bulk_g2s_a(sa, ahi, ab, B_FULL + 8 * s);
-          bulk_g2s_a(sa + A_LO * 4, ahi + (size_t)kc32 * TILE, ab, B_FULL + 8 * s);
-          bulk_g2s_a(sa + W_AT * 4, wbuf + pc.w_off + (size_t)c * (2 * KC2 * pc.ncols), wb, B_FULL + 8 * s);
+          if (role <= 0) {
+            expect_tx_a(B_FULL + 8 * s, ab);
+            bulk_g2s_a(sa, ahi, ab, B_FULL + 8 * s);
+          }
+          if (role < 0 || role == 1) {
+            expect_tx_a(B_FULL + 8 * s, ab);
+            bulk_g2s_a(sa + A_LO * 4, ahi + (size_t)kc32 * TILE, ab, B_FULL + 8 * s);
+          }
+          if (role < 0 || role == 2) {
+            expect_tx_a(B_FULL + 8 * s, wb);
+            bulk_g2s_a(sa + W_AT * 4, wbuf + pc.w_off + (size_t)c * (2 * KC2 * pc.ncols), wb, B_FULL + 8 * s);
+          }
         }
-        // the L' stacks are needed last (GEMM2 of this piece): issued after the operands of GEMM1
-        const int lb = n & 1;
-        if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read this L' buffer
-        const uint32_t lbytes = (uint32_t)pc.l_floats * 4u;
-        expect_tx_a(B_LFULL + 8 * lb, lbytes);
-        bulk_g2s_a(lbuf0 + (uint32_t)(lb * LBUF) * 4u, wbuf + pc.l_off, lbytes, B_LFULL + 8 * lb);
-        R2_TRACE(0, n, 1);
-      } else {
-        for (int u0 = 0; u0 < pc.kpad; u0 += KC2) ++c_all;
+        if (role < 0 || role == 2) {
+          // the L' operands are needed last (GEMM2 / FMA-pipe batches of this piece)
+          const int lb = n & 1;
+          if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read this L' buffer
+          const uint32_t lbytes = (uint32_t)pc.l_floats * 4u;
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(lbuf0 + (uint32_t)(lb * LBUF) * 4u, wbuf + pc.l_off, lbytes, B_LFULL + 8 * lb);
+        }
+        if (role <= 0) R2_TRACE(0, n, 1);
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp == W_MMA1) {
     // =============================== GEMM1 issuer ===============================
     const uint32_t lbo_a = TILE * 16, astep = (2 * lbo_a) >> 4;
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
       }
       R2_TRACE(3, n, 1);
     }
-  } else if (warp < 8) {
+  } else if (warp < NGW) {
     // =============================== gate (thread = edge = TMEM lane) ===============================
     // Two warps per lane quadrant; half h walks its own stream of 8-column batches (host: FMA-pipe slots belong to one
     // half, tensor batches alternate).  Two-stage software pipeline: the gate values of batch k + 1 are in flight while
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
     const float* gz = a.g + (size_t)tile * a.gtile_floats + (live ? zt : 0);
     float* acc = accs + zt;
     const float* lbase = smem + NST * STG;
-    const int sb = h ? ps.stream1_begin : ps.stream0_begin, se = h ? ps.stream1_end : ps.stream0_end;
+    const int sb = ps.stream_begin[h], se = ps.stream_end[h];
     const uint4* recs = reinterpret_cast<const uint4*>(a.batches);
     auto load_gates = [&](const uint4& r, float (&gq)[8]) {
       if (r.y == 0xFFFFFFFFu) {
@@ -388,36 +387,61 @@ __global__ void __launch_bounds__(NTHR, 1) msgpack_rot2_kernel(const __grid_cons
         ++n;
       }
     };
-    uint4 r0 = make_uint4(2u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u), r1 = r0;
+    // records travel four batches ahead (a record load used right away cost 10 % of all stall samples, profiles/r02p),
+    // gate values one batch ahead
+    const uint4 rdummy = make_uint4(2u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    uint4 r0 = rdummy, r1 = rdummy, r2 = rdummy, r3 = rdummy;
     float g0[8], g1[8];
-    if (sb < se) { r0 = __ldg(recs + sb); load_gates(r0, g0); }
+    if (sb < se) r0 = __ldg(recs + sb);
     if (sb + 1 < se) r1 = __ldg(recs + sb + 1);
+    if (sb + 2 < se) r2 = __ldg(recs + sb + 2);
+    if (sb + 3 < se) r3 = __ldg(recs + sb + 3);
+    if (sb < se) load_gates(r0, g0);
 #pragma unroll 1
     for (int bb = sb; bb < se; bb += 2) {
-      uint4 r2 = r0, r3 = r0;
+      uint4 r4 = rdummy, r5 = rdummy;
+      if (bb + 4 < se) r4 = __ldg(recs + bb + 4);
+      if (bb + 5 < se) r5 = __ldg(recs + bb + 5);
       if (bb + 1 < se) load_gates(r1, g1);
-      if (bb + 2 < se) r2 = __ldg(recs + bb + 2);
       process(r0, g0);
       if (bb + 1 < se) {
         if (bb + 2 < se) load_gates(r2, g0);
-        if (bb + 3 < se) r3 = __ldg(recs + bb + 3);
         process(r1, g1);
       }
-      r0 = r2; r1 = r3;
+      r0 = r2; r1 = r3; r2 = r4; r3 = r5;
     }
     __syncwarp();
     if (lane == 0) arrive_a(B_SIMT);   // every FMA-pipe contribution of this warp is in C'
   } else {
     // =============================== accumulate: C' += S, finally store the pass's columns of cp ===============================
-    const int q = warp - 8, zl = q * 32 + lane;
+    const int q = warp - W_ACC, zl = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float* acc = accs + zl;
+    // L2 prefetch of the operands of piece qi (the ring holds about one piece; the packed inputs and the gate tensor of a
+    // chunk are GBs, so the first CTA of a tile to touch a block reads it from DRAM): one operand per accumulate warp
+    const float* xt = a.xp + (size_t)tile * a.tile_stride;
+    const float* gtile = a.g + (size_t)tile * a.gtile_floats;
+    auto prefetch_piece = [&](int qi) {
+      if (qi >= ps.piece_end) return;
+      const PieceRec pp = load_piece(a.pieces + qi);
+      if (q == 0 && lane == 0) bulk_prefetch_l2(xt + pp.a_off, (uint32_t)(2 * pp.kpad * TILE) * 4u);
+      if (q == 1 && lane == 0) bulk_prefetch_l2(wbuf + pp.w_off, (uint32_t)(2 * pp.kpad * pp.ncols) * 4u);
+      if (q == 2 && lane == 0) bulk_prefetch_l2(wbuf + pp.l_off, (uint32_t)pp.l_floats * 4u);
+      if (q == 3 && lane < pp.gpf_n) {
+        const uint2 gr = __ldg(reinterpret_cast<const uint2*>(a.gpf + pp.gpf_begin + lane));
+        bulk_prefetch_l2(gtile + gr.x, gr.y);
+      }
+    };
+    prefetch_piece(ps.piece_begin + 1);
+    prefetch_piece(ps.piece_begin + 2);
+    prefetch_piece(ps.piece_begin + 3);
     int n = 0;
     for (int qi = ps.piece_begin; qi < ps.piece_end; ++qi, ++n) {
       const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(a.pieces + qi) + 1);
       const int dst_begin = (int)w1.y, ndst = (int)(w1.w & 0xffffu);
       uint4 drec = make_uint4(0, 0, 0, 0);   // lane d holds destination group d of the piece
       if (lane < ndst) drec = __ldg(reinterpret_cast<const uint4*>(a.dsts + dst_begin + lane));
+      prefetch_piece(qi + 4);
       warp_wait_a(B_S2 + 8 * (n & 1), (uint32_t)((n >> 1) & 1));
       tc::fence_after_sync();
       if (q == 0) R2_TRACE(4, n, 0);

@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "msgpack_tcr_kernel.cuh"
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
-#include "msgpack_rot_s2_kernel.cuh"
 #include "msgpack_rot2_kernel.cuh"
 
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
@@ -784,20 +783,6 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     a.n_slots = ns;
     a.dbl = (k == 1) ? 0 : 1;
   }
-  // experimental variant for the padded-multiplicity-16 slots (msgpack_rot_s2_kernel.cuh), opt-in
-  bool use_s2 = false;
-  {
-    const char* s2 = getenv("HGB_ROT_S2");
-    if (s2 && s2[0] == '1') {
-      use_s2 = true;
-      for (int t = 0; t < plan->n_types; ++t) {
-        if (klass[t] != 0) continue;
-        HGB_CHECK_ARG(plan->types_host[t].mpad == rot::S2_MP, "hgb_msgpack_rot_forward: HGB_ROT_S2 needs padded multiplicity 16 in slot %d", t);
-        for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si)
-          HGB_CHECK_ARG(rp->steps_host[si].pad2 > 0 && rp->steps_host[si].pad2 % 4 == 0, "hgb_msgpack_rot_forward: step %d has no fp32 L' copy", si);
-      }
-    }
-  }
   rot::RpArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.blocks = rp->blocks; pa.n_blocks = rp->n_blocks; pa.tile_stride = rp->tile_stride; pa.dstride = rp->dstride;
@@ -825,13 +810,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
-      if (k == 0 && use_s2) {
-        constexpr size_t smem = rot::rot_s2_smem_bytes();
-        static_assert(smem <= 75 * 1024, "msgpack_rot_s2_kernel: 3 CTAs/SM budget");
-        HGB_CUDA_OK(cudaFuncSetAttribute(rot::msgpack_rot_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rot::msgpack_rot_s2_kernel<<<(unsigned)(n_tiles * cls[k].n_slots), rot::S2_NTHR, smem, st>>>(cls[k]);
-        HGB_LAUNCH_OK("msgpack_rot_s2_kernel");
-      } else if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
+      if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
       else if (k == 1) rc = launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
@@ -883,10 +862,11 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
   for (int p = 0; p < r2->n_passes; ++p) {
     const hgb_rot2_pass_t& ps = r2->passes_host[p];
     HGB_CHECK_ARG(ps.piece_begin >= 0 && ps.piece_begin < ps.piece_end && ps.piece_end <= r2->n_pieces && ps.ncols >= 1 &&
-                      ps.ncols <= rot2::ACC_COLS && ps.out_col0 == col_cover && ps.stream0_begin >= 0 &&
-                      ps.stream0_begin <= ps.stream0_end && ps.stream0_end <= r2->n_batches && ps.stream1_begin >= 0 &&
-                      ps.stream1_begin <= ps.stream1_end && ps.stream1_end <= r2->n_batches,
+                      ps.ncols <= rot2::ACC_COLS && ps.out_col0 == col_cover,
                   "hgb_msgpack_rot2_forward: bad pass %d", p);
+    for (int h = 0; h < rot2::NH; ++h)
+      HGB_CHECK_ARG(ps.stream_begin[h] >= 0 && ps.stream_begin[h] <= ps.stream_end[h] && ps.stream_end[h] <= r2->n_batches,
+                    "hgb_msgpack_rot2_forward: bad gate stream %d of pass %d", h, p);
     col_cover += ps.ncols;
     for (int q = ps.piece_begin; q < ps.piece_end; ++q) {
       const hgb_rot2_piece_t& pc = r2->pieces_host[q];
@@ -914,8 +894,8 @@ extern "C" int hgb_msgpack_rot2_forward(const hgb_msgpack_plan* plan, const hgb_
       }
     }
     // the two gate streams: each visits every piece of the pass once (first ... last flags), in piece order
-    for (int h = 0; h < 2; ++h) {
-      const int sb = h ? ps.stream1_begin : ps.stream0_begin, se = h ? ps.stream1_end : ps.stream0_end;
+    for (int h = 0; h < rot2::NH; ++h) {
+      const int sb = ps.stream_begin[h], se = ps.stream_end[h];
       int q = ps.piece_begin, open = 0;
       for (int b = sb; b < se; ++b) {
         const hgb_rot2_batch_t& bt = r2->batches_host[b];

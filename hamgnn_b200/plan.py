@@ -865,7 +865,8 @@ class MessagePackOp:
     R2_KC = 16        # channels per ring stage
     R2_ACC = 128      # accumulator columns per pass (shared memory [128][129] floats)
     R2_LMAX_FLOATS = 8192   # L' buffer: hi + lo images of all destination groups of a piece
-    R2_SIMT_MAX = 16        # slots with multiplicity <= 16 apply L' on the fp32 FMA pipes (no GEMM2, no hi/lo write-back)
+    R2_NH = L.ROT2_GATE_GROUPS   # gate-warp groups per TMEM lane quadrant (gate streams per pass)
+    R2_SIMT_MAX = int(os.environ.get("HGB_R2_SIMT_MAX", "16"))        # slots with multiplicity <= 16 apply L' on the fp32 FMA pipes (no GEMM2, no hi/lo write-back)
 
     def _build_rot2_program(self):
         """Tables of the A-stationary edge-aligned message kernel (csrc/msgpack_rot2_kernel.cuh).
@@ -1029,9 +1030,10 @@ class MessagePackOp:
         for (m3_, t, bi, m1), plist_ in steps.items():
             if is_simt[t]:
                 simt_cost[t] = simt_cost.get(t, 0) + gcols(t, len(plist_)) // 8 * (40 + 8 * m4[t] * 5 // 4)
-        owner, load = {}, [0, 0]
+        NH = self.R2_NH
+        owner, load = {}, [0] * NH
         for t in sorted(simt_cost, key=lambda q: -simt_cost[q]):
-            h = 0 if load[0] <= load[1] else 1
+            h = int(np.argmin(load))
             owner[t] = h
             load[h] += simt_cost[t]
         self.rot2_simt_owner = owner
@@ -1040,7 +1042,7 @@ class MessagePackOp:
         ONES = 0xFFFFFFFF
         self.rot2_gstride = (max(self.n_channels) + 3) // 4 * 4 + 4   # gate columns per branch (+4: a 4-column block may overhang)
         passes, pieces, dsts, gpfs = [], [], [], []
-        streams = ([], [])
+        streams = tuple([] for _ in range(NH))
         ccol = np.full((max(1, ntypes), 2 * max(lmax3, 0) + 1), -1, dtype=np.int32)    # C' row column of (slot, l3 + m3)
         out_col = 0
         tensor_toggle = 0
@@ -1064,7 +1066,7 @@ class MessagePackOp:
                     ccol[t, self.tc_types_c[t].l + m3] = out_col + a
                     a += int(self.tc_types_c[t].mul)
                 p_begin = len(pieces)
-                s_begin = (len(streams[0]), len(streams[1]))
+                s_begin = [len(st_) for st_ in streams]
                 for bi in range(self.rot_n_blocks):
                     blk = self.rot_blocks_c[bi]
                     for m1 in ([m3] if m3 == 0 else [m3, -m3]):
@@ -1102,7 +1104,7 @@ class MessagePackOp:
                             w_off = w_block(bi, gl, ncols)
                             d_begin = len(dsts)
                             col, s_off = 0, 0
-                            mine = ([], [])        # batches of this piece per gate-warp half
+                            mine = tuple([] for _ in range(NH))        # batches of this piece per gate-warp group
                             gst = self.rot2_gstride
                             for (t, paths), rel in zip(gl, rels):
                                 ty = self.tc_types_c[t]
@@ -1133,10 +1135,10 @@ class MessagePackOp:
                                         mine[h].append([meta_, ga_, gb_, rel + 8 * q * m4[t]])
                                     else:
                                         h = tensor_toggle
-                                        tensor_toggle ^= 1
+                                        tensor_toggle = (tensor_toggle + 1) % NH
                                         mine[h].append([KIND_TENSOR | (c8 << 8), ga_, gb_, 0])
                                 col += kc_
-                            for h in (0, 1):
+                            for h in range(NH):
                                 if not mine[h]:
                                     mine[h].append([KIND_DUMMY, ONES, ONES, 0])     # the warp still waits and arrives
                                 mine[h][0][0] |= 1 << 2                               # first batch of the piece
@@ -1151,14 +1153,20 @@ class MessagePackOp:
                                         gpfs.append(L.Rot2GpfT((int(pa.branch) * gst + int(pa.pad0)) * T, m4[t] * T * 4))
                             pieces.append(L.Rot2PieceT(int(blk.xoff) + (int(blk.l1) + m1) * 2 * int(blk.kpad) * T, w_off, l_off,
                                                        l_floats, gp0, d_begin, int(blk.kpad), ncols, len(dsts) - d_begin, len(gpfs) - gp0))
-                passes.append(L.Rot2PassT(p_begin, len(pieces), a, out_col, s_begin[0], len(streams[0]), s_begin[1], len(streams[1])))
+                ps_ = L.Rot2PassT(p_begin, len(pieces), a, out_col)
+                for h in range(NH):
+                    ps_.stream_begin[h], ps_.stream_end[h] = s_begin[h], len(streams[h])
+                passes.append(ps_)
                 out_col += a
-        # the two streams live in one table: half 1 after half 0
-        n0 = len(streams[0])
-        for ps_ in passes:
-            ps_.stream1_begin += n0
-            ps_.stream1_end += n0
-        batches = streams[0] + streams[1]
+        # the streams live in one table, group after group
+        base_ = 0
+        batches = []
+        for h in range(NH):
+            for ps_ in passes:
+                ps_.stream_begin[h] += base_
+                ps_.stream_end[h] += base_
+            batches += streams[h]
+            base_ += len(streams[h])
         self.tc_w_total = (wcur + 3) // 4 * 4
         self.rot2_passes_c = (L.Rot2PassT * max(1, len(passes)))(*passes)
         self.rot2_pieces_c = (L.Rot2PieceT * max(1, len(pieces)))(*pieces)

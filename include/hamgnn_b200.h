@@ -220,6 +220,8 @@ int hgb_timing_collect(float* ms_out, int64_t* count_out);
 /* Diagnosis tool (csrc/mma_probe.cu): cycles per tcgen05.mma.kind::tf32 (M 128, N n, K 8) issued back to back by one thread,
  * out_dev[0] = issue cycles, [1] = cycles until the commit barrier fires, [2] = a concurrent tcgen05.ld round trip. */
 int hgb_mma_probe(int32_t n, int32_t count, int32_t ndest, int32_t ts, int32_t same_ab, long long* out_dev, void* stream);
+/* cycles per cp.async.bulk of `bytes` (one thread, `depth` copies in flight, L2-resident source): out_dev[0] pipelined, [1] issue. */
+int hgb_tma_probe(const float* src_dev, int32_t bytes, int32_t count, int32_t depth, long long* out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5-a9, A-stationary form of the rotated frame ("rot2", the default message path).  Same mathematics and same call
@@ -235,12 +237,15 @@ int hgb_mma_probe(int32_t n, int32_t count, int32_t ndest, int32_t ts, int32_t s
  *   unrotate: out[row][slot][w][k] = sum over the row's edge segment, sum_m3 D^{l3}_e[m3][k] cp[e][ccol[slot][m3] + w]
  *            -- the receiver reduction is a serial sum over a receiver-sorted segment (deterministic, no atomics).
  */
+#ifndef HGB_ROT2_GATE_GROUPS
+#define HGB_ROT2_GATE_GROUPS 2
+#endif
 typedef struct {
   int32_t piece_begin, piece_end;     /* pieces of the pass                                                  */
   int32_t ncols;                      /* accumulator columns (<= 128)                                       */
   int32_t out_col0;                   /* first column of the pass in a cp row                               */
-  int32_t stream0_begin, stream0_end; /* gate stream of warp half 0 (entries of `batches`)                  */
-  int32_t stream1_begin, stream1_end; /* gate stream of warp half 1                                         */
+  int32_t stream_begin[HGB_ROT2_GATE_GROUPS]; /* gate stream of each gate-warp group (entries of `batches`)  */
+  int32_t stream_end[HGB_ROT2_GATE_GROUPS];
 } hgb_rot2_pass_t;
 
 typedef struct {

@@ -442,9 +442,10 @@ def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, v
         ps = op.rot2_passes_c[pi]
         assert ps.ncols <= op.R2_ACC
         acc = torch.zeros(E, ps.ncols, dtype=dt)
-        cur = [ps.stream0_begin, ps.stream1_begin]
-        end = [ps.stream0_end, ps.stream1_end]
-        s_run = [None, None]
+        NH = op.R2_NH
+        cur = [ps.stream_begin[h] for h in range(NH)]
+        end = [ps.stream_end[h] for h in range(NH)]
+        s_run = [None] * NH
         for qi in range(ps.piece_begin, ps.piece_end):
             pc = op.rot2_pieces_c[qi]
             assert pc.ncols % 16 == 0 and pc.ncols <= op.R2_NB and pc.kpad % 8 == 0
@@ -468,7 +469,7 @@ def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, v
                 out[:, :nvv] = g[br][:, col:col + nvv]
                 return out
 
-            for h in (0, 1):
+            for h in range(NH):
                 first = True
                 while True:
                     assert cur[h] < end[h]
@@ -513,7 +514,7 @@ def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, v
                 S = Bg[:, ds.col0:ds.col0 + ds.kcols] @ Lst
                 acc[:, ds.acc_col0:ds.acc_col0 + ds.mul] += S[:, :ds.mul]
                 assert float(S[:, ds.mul:].abs().max()) == 0 if ds.mul < ds.mp else True
-        assert cur == end and s_run == [None, None]
+        assert cur == end and s_run == [None] * NH
         assert not seen[ps.out_col0:ps.out_col0 + ps.ncols].any()
         seen[ps.out_col0:ps.out_col0 + ps.ncols] = True
         CP[:, ps.out_col0:ps.out_col0 + ps.ncols] = acc

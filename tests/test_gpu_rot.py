@@ -121,30 +121,3 @@ def test_full_forward_rot_backend(cfg_name, gname, gate):
     finally:
         P.BACKEND, P.GATE_BACKEND = old
     assert max(errs["rot"]) < TOL, errs
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HGB_TEST_EXPERIMENTAL") != "1",
-                    reason="msgpack_rot_s2_kernel (HGB_ROT_S2=1) is an opt-in experiment that has not run on a GPU yet")
-def test_experimental_s2_variant(setup, monkeypatch):
-    """Same single-message checks with the padded-multiplicity-16 slots on msgpack_rot_s2_kernel (L' on the FMA pipes)."""
-    cfg_name, pre, out, opre, oout, batch, d, rep, res, dev = setup
-    monkeypatch.setenv("HGB_ROT_S2", "1")
-    torch.manual_seed(11)
-    E, N, D = batch.edge_index.shape[1], batch.num_nodes, pre.irreps_node_features.dim
-    x, e = torch.randn(N, D), torch.randn(E, D)
-    s, r = batch.edge_index
-    with torch.no_grad():
-        ref_msg = opre.convolutions[0].conv_tp(x.double()[s], x.double()[r], e.double(), d["edge_attrs"], d["edge_embedding"])
-    sh, rbf, vec = d["edge_attrs"].float().to(dev), d["edge_embedding"].float().to(dev), d["edge_vectors"].float().to(dev)
-    old = P.BACKEND
-    try:
-        P.BACKEND = "rot"
-        cb = pre.convolutions[0].conv_tp
-        msg = torch.empty(E, D, device=dev)
-        cb.op.forward(cb.weights(), [x.to(dev), x.to(dev), e.to(dev)], [s.to(dev), r.to(dev), None], sh, rbf, E, msg, edge_vec=vec)
-        torch.cuda.synchronize()
-    finally:
-        P.BACKEND = old
-    err = rel_err(msg.cpu(), ref_msg)
-    print(f"[{cfg_name} rot s2] rel err message {err:.2e}")
-    assert err < TOL
