@@ -225,3 +225,35 @@ def test_graph_data_module_npz(tmp_path):
         graph_data_module(dataset="x.lmdb").setup()
     with pytest.raises(ValueError):
         graph_data_module(dataset="x.bin").setup()
+
+
+def test_strict_reference_state_dict_loader():
+    """load_reference_state_dict: e3nn's constant buffers are accepted, a renamed / missing / mis-shaped weight raises
+    (`strict=False` drops mismatched names silently)."""
+    from hamgnn_b200.hamgnn_conv import HamGNNConvE3, load_reference_state_dict
+    cfg = dict(irreps_node_features="8x0e+8x0o+4x1o+4x1e+3x2o+5x2e+2x3o+2x3e+2x4e", num_layers=2, num_radial=16, radial_MLP=[16, 16],
+               irreps_edge_sh="0e+1o+2e+3o+4e")
+    torch.manual_seed(1)
+    src = HamGNNConvE3(cfg)
+    sd = dict(src.state_dict())
+    # what an e3nn 0.5.0 checkpoint carries in addition (SURVEY.md Appendix A.8)
+    sd["convolutions.0.conv_tp.node_tensor_product.output_mask"] = torch.ones(10)
+    sd["convolutions.0.conv_tp.node_tensor_product._compiled_main_left_right._w3j_1_1_2"] = torch.zeros(3, 3, 5)
+    sd["convolutions.0.skip_linear.bias"] = torch.zeros(0)
+    sd["pair_embedding.linear_up_src.output_mask"] = torch.ones(96)
+    dst = HamGNNConvE3(cfg)
+    load_reference_state_dict(dst, sd)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    bad = dict(sd)
+    bad["convolutions.0.conv_tp.node_tensor_product.weights"] = bad.pop("convolutions.0.conv_tp.node_tensor_product.weight")   # renamed
+    with pytest.raises(RuntimeError):
+        load_reference_state_dict(dst, bad)
+    bad = dict(sd)
+    bad["chemical_embedding.linear.weight"] = torch.zeros(3)
+    with pytest.raises(RuntimeError):
+        load_reference_state_dict(dst, bad)
+    bad = dict(sd)
+    bad["convolutions.0.skip_linear.bias"] = torch.zeros(4)       # a non-empty bias is not something the kernels evaluate
+    with pytest.raises(RuntimeError):
+        load_reference_state_dict(dst, bad)
