@@ -439,7 +439,7 @@ def main():
     if sharding_check is not None:
         line["sharding_check"] = sharding_check
     if red is not None:
-        line["collectives"] = {"all_reduce_calls_per_step": red.calls / (args.steps * 2 + args.warmup + 2), "bytes_each": N * D * 4}
+        line["collectives"] = {"all_reduce_calls_per_step": red.calls / (args.steps * 3 + args.warmup + 2), "bytes_each": N * D * 4}
     if world == 1 and not args.no_cpu_baseline:
         cores = physical_cores()
         frac = args.cpu_sample_frac if args.cpu_sample_frac else (0.01 if E_total > 100000 else 1.0)

@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(RO_THREADS) resblock_kernel(const __grid_const
 //     once per CTA in shared memory ([u][mul_out padded to 4]) and read as warp-broadcast float4, the input value is one
 //     conflict-free LDS (row stride = dim is odd for the irreps in use) -- 8 FMAs per 3 shared loads, no global load in the loop;
 //   * 512 threads per CTA.
-constexpr int RB2_ROWS = 16;
-constexpr int RB2_THREADS = 512;
-constexpr int RB2_WFLOATS = 8192;   // weight staging buffer
+// <RB2_ROWS, RB2_THREADS, RB2_WFLOATS>: <16, 512, 8192> = 209 KB, one CTA per SM; <8, 256, 4096> = 105 KB, two CTAs per SM (one
+// stages weights while the other computes)
 
+template <int RB2_ROWS, int RB2_THREADS, int RB2_WFLOATS>
 __device__ __forceinline__ void lin_apply2(const hgb_linblock_t* __restrict__ blocks, int nb, const float* __restrict__ w,
                                            const float* sin, int ldin, float* sout, int ldout, float* sw) {
   for (int b = 0; b < nb; ++b) {
@@ -239,6 +239,7 @@ __device__ __forceinline__ void lin_apply2(const hgb_linblock_t* __restrict__ bl
   __syncthreads();
 }
 
+template <int RB2_ROWS, int RB2_THREADS>
 __device__ __forceinline__ void load_rows2(float* s, int lds, const float* __restrict__ g, int64_t r0, int nr, int dim, bool add) {
   for (int idx = threadIdx.x; idx < RB2_ROWS * dim; idx += RB2_THREADS) {
     const int r = idx / dim, c = idx - r * dim;
@@ -248,7 +249,8 @@ __device__ __forceinline__ void load_rows2(float* s, int lds, const float* __res
   }
 }
 
-__global__ void __launch_bounds__(RB2_THREADS, 1) resblock2_kernel(const __grid_constant__ ResArgs a) {
+template <int RB2_ROWS, int RB2_THREADS, int RB2_WFLOATS>
+__global__ void __launch_bounds__(RB2_THREADS, (RB2_ROWS <= 8 ? 2 : 1)) resblock2_kernel(const __grid_constant__ ResArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int D = a.lin1.in_dim;
   const int ldh = a.wide | 1;   // odd row stride: conflict-free column access across rows
@@ -258,9 +260,9 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) resblock2_kernel(const __grid_
   float* sw = sa + (size_t)RB2_ROWS * D;         // weight staging
   const int64_t r0 = (int64_t)blockIdx.x * RB2_ROWS;
   const int nr = (int)min((int64_t)RB2_ROWS, a.n_rows - r0);
-  load_rows2(sx, D, a.x, r0, nr, D, false);
+  load_rows2<RB2_ROWS, RB2_THREADS>(sx, D, a.x, r0, nr, D, false);
   for (int idx = threadIdx.x; idx < RB2_ROWS * ldh; idx += RB2_THREADS) sh[idx] = 0.f;
-  lin_apply2(a.lin1.blocks, a.lin1.n_blocks, a.lin1.w, sx, D, sh, ldh, sw);   // starts with a barrier
+  lin_apply2<RB2_ROWS, RB2_THREADS, RB2_WFLOATS>(a.lin1.blocks, a.lin1.n_blocks, a.lin1.w, sx, D, sh, ldh, sw);   // starts with a barrier
   // ---- e3nn Gate, element-wise
   const hgb_gate_desc& g = a.gate;
   for (int s = 0; s < g.n_scalar_slots; ++s) {
@@ -280,18 +282,39 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) resblock2_kernel(const __grid_
       sa[(size_t)r * D + g.gd_out_off[s] + c] = sh[(size_t)r * ldh + g.gd_in_off[s] + c] * gate;
     }
   }
-  if (a.extra) load_rows2(sx, D, a.extra, r0, nr, D, true);
-  lin_apply2(a.lin2.blocks, a.lin2.n_blocks, a.lin2.w, sa, D, sx, D, sw);   // sx = x (+ extra) + Lin2(gated)
+  if (a.extra) load_rows2<RB2_ROWS, RB2_THREADS>(sx, D, a.extra, r0, nr, D, true);
+  lin_apply2<RB2_ROWS, RB2_THREADS, RB2_WFLOATS>(a.lin2.blocks, a.lin2.n_blocks, a.lin2.w, sa, D, sx, D, sw);   // sx = x (+ extra) + Lin2(gated)
   if (!a.has_post) {
     for (int idx = threadIdx.x; idx < nr * D; idx += RB2_THREADS) a.y[r0 * D + idx] = sx[idx];
     return;
   }
   const int DP = a.post.out_dim;
   for (int idx = threadIdx.x; idx < RB2_ROWS * ldh; idx += RB2_THREADS) sh[idx] = 0.f;
-  lin_apply2(a.post.blocks, a.post.n_blocks, a.post.w, sx, D, sh, ldh, sw);
+  lin_apply2<RB2_ROWS, RB2_THREADS, RB2_WFLOATS>(a.post.blocks, a.post.n_blocks, a.post.w, sx, D, sh, ldh, sw);
   for (int idx = threadIdx.x; idx < nr * DP; idx += RB2_THREADS) {
     const int r = idx / DP, c = idx - r * DP;
     a.y[(r0 + r) * DP + c] = sh[(size_t)r * ldh + c];
+  }
+}
+
+
+// out[i][c] = sum of rows[order[j]][c] for j in [ptr[i], ptr[i+1]), added serially in list order: the deterministic receiver
+// reduction (torch_scatter.scatter(..., reduce='sum'), hamgnn/nn/convolution.py:147-149) for message kernels that write one row
+// per edge.  One CTA per output row, a thread per column (coalesced row reads), four rows in flight per thread.
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ rows, int n_cols, const int64_t* __restrict__ ptr,
+                                                          const int64_t* __restrict__ order, float* __restrict__ out) {
+  const int64_t i = blockIdx.x;
+  const int64_t j0 = ptr[i], j1 = ptr[i + 1];
+  for (int c = threadIdx.x; c < n_cols; c += 256) {
+    float acc = 0.f;
+    int64_t j = j0;
+    for (; j + 4 <= j1; j += 4) {
+      const float v0 = __ldg(rows + order[j] * n_cols + c), v1 = __ldg(rows + order[j + 1] * n_cols + c);
+      const float v2 = __ldg(rows + order[j + 2] * n_cols + c), v3 = __ldg(rows + order[j + 3] * n_cols + c);
+      acc += v0; acc += v1; acc += v2; acc += v3;   // list order
+    }
+    for (; j < j1; ++j) acc += __ldg(rows + order[j] * n_cols + c);
+    out[i * n_cols + c] = acc;
   }
 }
 
@@ -340,19 +363,42 @@ extern "C" int hgb_resblock_forward(const hgb_linear_plan* lin1, const hgb_gate_
   a.x = x; a.extra = extra; a.n_rows = n_rows; a.y = y;
   a.wide = gate->in_dim;
   if (post && post->out_dim > a.wide) a.wide = post->out_dim;
-  // 16-row tiles with staged weights when they fit in shared memory (D = 877: 209 KB), else the 8-row kernel
-  const size_t smem2 = ((size_t)RB2_ROWS * (2 * lin1->in_dim + (a.wide | 1)) + RB2_WFLOATS) * sizeof(float);
+  // row tiles with staged weights when they fit in shared memory, else the 8-row kernel
   const char* force_old = getenv("HGB_RESBLOCK_V1");
-  if (smem2 <= 227 * 1024 && !(force_old && force_old[0] == '1')) {
-    HGB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    resblock2_kernel<<<(unsigned)((n_rows + RB2_ROWS - 1) / RB2_ROWS), RB2_THREADS, smem2, (cudaStream_t)stream>>>(a);
-    HGB_LAUNCH_OK("resblock2_kernel");
-    return 0;
+  const char* rows_env = getenv("HGB_RESBLOCK_ROWS");
+  const int want_rows = rows_env ? atoi(rows_env) : 16;   // measured: 8 rows x 2 CTAs per SM is no faster (profiles/README.md r03a)
+  const size_t tile_floats = (size_t)(2 * lin1->in_dim + (a.wide | 1));
+  if (!(force_old && force_old[0] == '1')) {
+    const size_t smem8 = (8 * tile_floats + 4096) * sizeof(float), smem16 = (16 * tile_floats + 8192) * sizeof(float);
+    if (want_rows == 8 && 2 * (smem8 + 1024) <= 227 * 1024) {
+      HGB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<8, 256, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      resblock2_kernel<8, 256, 4096><<<(unsigned)((n_rows + 7) / 8), 256, smem8, (cudaStream_t)stream>>>(a);
+      HGB_LAUNCH_OK("resblock2_kernel");
+      return 0;
+    }
+    if (smem16 <= 227 * 1024) {
+      HGB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<16, 512, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      resblock2_kernel<16, 512, 8192><<<(unsigned)((n_rows + 15) / 16), 512, smem16, (cudaStream_t)stream>>>(a);
+      HGB_LAUNCH_OK("resblock2_kernel");
+      return 0;
+    }
   }
   const size_t smem = (size_t)LDR * (2 * lin1->in_dim + a.wide) * sizeof(float);
   HGB_CHECK_ARG(smem <= 220 * 1024, "hgb_resblock_forward: row tile does not fit in shared memory");
   HGB_CUDA_OK(cudaFuncSetAttribute(resblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   resblock_kernel<<<(unsigned)((n_rows + TR - 1) / TR), RO_THREADS, smem, (cudaStream_t)stream>>>(a);
   HGB_LAUNCH_OK("resblock_kernel");
+  return 0;
+}
+
+extern "C" int hgb_segment_sum(const float* rows, int32_t n_cols, const int64_t* seg_ptr, const int64_t* seg_order,
+                               int64_t n_out_rows, float* out, void* stream) {
+  HGB_DEVICE_GUARD(out);
+  HGB_CHECK_ARG(rows && seg_ptr && seg_order && out, "hgb_segment_sum: NULL argument");
+  HGB_CHECK_ARG(n_cols > 0 && n_out_rows >= 0 && n_out_rows < (1ll << 31), "hgb_segment_sum: bad sizes");
+  if (n_out_rows == 0) return 0;
+  hgb::TimeScope ts_(HGB_K_OTHER, stream);
+  segment_sum_kernel<<<(unsigned)n_out_rows, 256, 0, (cudaStream_t)stream>>>(rows, n_cols, seg_ptr, seg_order, out);
+  HGB_LAUNCH_OK("segment_sum_kernel");
   return 0;
 }

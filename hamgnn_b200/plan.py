@@ -258,7 +258,12 @@ class KernelProfiler:
 PROFILER: Optional[KernelProfiler] = None
 # which fused-message kernel runs: 'tc' = tcgen05 3xTF32 (csrc/msgpack_tc.cu), 'tcg' = tcgen05 with the radial gate
 # pre-computed to HBM (csrc/msgpack_tcg.cu), 'simt' = fp32 FMA (csrc/msgpack.cu)
-BACKEND = os.environ.get("HGB_MSGPACK", "rot2")
+# 'rot'  = edge-aligned frame, one (path, m1) step at a time, 2 CTAs / SM (csrc/msgpack_rot_kernel.cuh) + hgb_segment_sum: the default,
+#          838 ms per forward of tbg_m28;
+# 'rot2' = the A-stationary regrouping of the same steps (csrc/msgpack_rot2_kernel.cuh): half the DRAM traffic, 4x fewer pipeline
+#          hand-offs, 936 ms -- both are bound by per-instruction costs of tcgen05.mma / cp.async.bulk;
+# 'tcg' / 'tc' / 'simt' = round-1 kernels, only when asked for by name.
+BACKEND = os.environ.get("HGB_MSGPACK", "rot")
 # radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
 GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND in ("rot", "rot2") else "simt")
 
@@ -1347,6 +1352,13 @@ class MessagePackOp:
             nb = len(self.branches)
             E = int(n_edges)
             dw = wigner_for(self, edge_vec)
+            # receiver reduction without atomics: the kernel writes one message row per edge, hgb_segment_sum adds the rows of
+            # every receiver in a fixed order (deterministic; HGB_ROT_ATOMIC=1 restores the red.global.add epilogue)
+            seg_out = None
+            if out_index is not None and os.environ.get("HGB_ROT_ATOMIC") != "1":
+                seg_out, seg_index = out, out_index
+                out = workspace("msg_rows", max(1, E) * self.irreps_out.dim, out.device).view(max(1, E), self.irreps_out.dim)[:E]
+                out_index = None
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
             g_ws = workspace("gate", nb * chunk * gstride, out.device)   # [nb][tile][gstride][128]
@@ -1380,6 +1392,12 @@ class MessagePackOp:
         else:
             rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
                                               int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
+        if use_rot and seg_out is not None:
+            L.check(rc, "hgb_msgpack_rot_forward")
+            seg_ptr, seg_order = segments_for(seg_index, seg_out.shape[0])
+            rc = L.load().hgb_segment_sum(out.data_ptr(), self.irreps_out.dim, seg_ptr.data_ptr(), seg_order.data_ptr(),
+                                          seg_out.shape[0], seg_out.data_ptr(), L.stream_ptr(seg_out.device))
+            out = seg_out
         if prof is not None:
             prof.end(out.device)
         L.check(rc, "hgb_msgpack_rot2_forward" if use_rot2 else "hgb_msgpack_rot_forward" if use_rot else

@@ -207,6 +207,13 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
                             float* out, const int64_t* out_index, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a9, deterministic receiver reduction for message kernels that write one row per edge (the 'rot' backend): replaces
+ * torch_scatter.scatter(messages, receiver, reduce='sum') (hamgnn/nn/convolution.py:147-149).  out[i][:] = sum over
+ * j in [seg_ptr[i], seg_ptr[i+1]) of rows[seg_order[j]][:], added in list order (no atomics: bit-reproducible). */
+int hgb_segment_sum(const float* rows, int32_t n_cols, const int64_t* seg_ptr, const int64_t* seg_order, int64_t n_out_rows,
+                    float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement aid: per-kernel device time of the library's launches, CUDA events on the launching
  * stream.  hgb_timing_enable(1) starts recording, hgb_timing_collect adds elapsed ms / launch counts per kernel id to the
  * caller's arrays of HGB_N_KERNEL_IDS entries (synchronises the recorded events) and clears the records. */

@@ -88,6 +88,18 @@ def test_single_message_calls(setup, chunk):
             got[backend] = (msg.cpu(), agg.cpu(), pair.cpu())
     finally:
         P.BACKEND, P.ROT_CHUNK_EDGES = old
+    # the receiver reduction of the rot path is a serial segment sum (hgb_segment_sum): bit-reproducible
+    P.BACKEND = "rot"
+    try:
+        if chunk is not None:
+            P.ROT_CHUNK_EDGES = chunk
+        cb = pre.convolutions[0].conv_tp
+        agg2 = torch.full((N, D), float("nan"), device=dev)
+        cb.op.forward(cb.weights(), [xd, xd, ed], [sd, rd, None], sh, rbf, E, agg2, out_index=rd, edge_vec=vec)
+        torch.cuda.synchronize()
+    finally:
+        P.BACKEND, P.ROT_CHUNK_EDGES = old
+    assert torch.equal(agg2.cpu(), got["rot"][1]), "rot aggregate must be bit-reproducible run to run"
     for backend in ("tcg", "rot"):
         em, ea, ep = (rel_err(got[backend][0], ref_msg), rel_err(got[backend][1], ref_agg), rel_err(got[backend][2], ref_pair))
         print(f"[{cfg_name} {backend} chunk={chunk}] rel err message {em:.2e} scatter {ea:.2e} edge update {ep:.2e}")

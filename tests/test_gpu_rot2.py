@@ -38,7 +38,6 @@ def test_single_message_calls(setup, chunk):
     cfg_name, pre, out, opre, oout, batch, d, rep, res, dev = setup
     if chunk is not None and cfg_name == "default":
         pytest.skip("chunking is exercised on the small model")
-    assert P.BACKEND == "rot2"
     torch.manual_seed(11)
     E, N, D = batch.edge_index.shape[1], batch.num_nodes, pre.irreps_node_features.dim
     x, e = torch.randn(N, D), torch.randn(E, D)
@@ -54,8 +53,9 @@ def test_single_message_calls(setup, chunk):
         ref_emb = opre.pair_embedding(dd2)
     sh, rbf, vec = d["edge_attrs"].float().to(dev), d["edge_embedding"].float().to(dev), d["edge_vectors"].float().to(dev)
     xd, ed, sd, rd = x.to(dev), e.to(dev), s.to(dev), r.to(dev)
-    old = P.ROT_CHUNK_EDGES
+    old, old_backend = P.ROT_CHUNK_EDGES, P.BACKEND
     try:
+        P.BACKEND = "rot2"
         if chunk is not None:
             P.ROT_CHUNK_EDGES = chunk
         cb = pre.convolutions[0].conv_tp
@@ -75,7 +75,7 @@ def test_single_message_calls(setup, chunk):
         emb = pre.pair_embedding(b2)
         torch.cuda.synchronize()
     finally:
-        P.ROT_CHUNK_EDGES = old
+        P.ROT_CHUNK_EDGES, P.BACKEND = old, old_backend
     em, ea, ep, ee = (rel_err(msg.cpu(), ref_msg), rel_err(aggs[0].cpu(), ref_agg), rel_err(pair.cpu(), ref_pair),
                       rel_err(emb.cpu(), ref_emb))
     print(f"[{cfg_name} rot2 chunk={chunk}] rel err message {em:.2e} aggregate {ea:.2e} edge update {ep:.2e} embedding {ee:.2e}")
