@@ -388,10 +388,19 @@ def main():
             ent["hbm_frac_of_measured_peak"] = ent["hbm_gbs_algorithmic"] / hbm_peak
             ent["tflops_algorithmic"] = f_alg / (ms / steps * 1e-3) / 1e12
         per_kernel[name] = ent
-    dom = ktime.get("msgpack_rot2")
+    dom_name = "msgpack_rot2" if P.BACKEND == "rot2" else "msgpack_rot"
+    alg["msgpack_rot"] = alg["msgpack_rot2"]
+    alg["segment_sum"] = ((E_local * (MSG // 2) + N_local * (MSG // 2)) * D * 4.0, E_local * (MSG // 2) * D * 1.0)
+    for name in ("msgpack_rot", "segment_sum"):
+        if name in ktime and name in per_kernel:
+            ms = ktime[name][0]
+            per_kernel[name]["hbm_gbs_algorithmic"] = alg[name][0] / (ms / steps * 1e-3) / 1e9
+            per_kernel[name]["hbm_frac_of_measured_peak"] = per_kernel[name]["hbm_gbs_algorithmic"] / hbm_peak
+            per_kernel[name]["tflops_algorithmic"] = alg[name][1] / (ms / steps * 1e-3) / 1e12
+    dom = ktime.get(dom_name)
     traffic_note = None
     roof = {"kernel": None}
-    if dom is not None and P.BACKEND == "rot2":
+    if dom is not None:
         ms_d, cnt_d = dom
         fl_per_launch = E_local * MSG * f_msg * steps / cnt_d
         avg_ms = ms_d / cnt_d
@@ -400,18 +409,21 @@ def main():
         tj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tj):      # dram__bytes_read.sum + dram__bytes_write.sum of msgpack_rot2_kernel, ncu --set full (per edge of a launch)
             t = json.load(open(tj))
-            traffic = t["msgpack_rot2_dram_bytes_per_edge"] * (E_local * MSG * steps / cnt_d)
+            traffic = t[f"{dom_name}_dram_bytes_per_edge"] * (E_local * MSG * steps / cnt_d)
             traffic_note = t.get("source")
         b_alg_launch = alg["msgpack_rot2"][0] * steps / cnt_d
-        roof = {"kernel": "msgpack_rot2_kernel (A-stationary edge-aligned MessagePackBlock: TMA ring + tcgen05 3xTF32, FMA-pipe L' for multiplicity <= 16)",
+        roof = {"kernel": ("msgpack_rot2_kernel (A-stationary edge-aligned MessagePackBlock: TMA ring + tcgen05 3xTF32, FMA-pipe L' for multiplicity <= 16)"
+                           if dom_name == "msgpack_rot2" else
+                           "msgpack_rot_kernel<16,3> + <32,2> + <64,2> (edge-aligned MessagePackBlock, one launch per slot class and edge chunk, timed "
+                           "together: TMA ring + tcgen05 3xTF32, 2 CTAs / SM)"),
                 "bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                 "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_note,
                 "traffic_over_algorithmic_bytes": (traffic / b_alg_launch) if traffic else None,
                 "avg_launch_ms": avg_ms, "launches_timed": cnt_d, "kernel_share_of_step": ms_d / (ms_step_timed * steps),
                 "flop_per_edge_algorithmic": f_msg, "flop_per_message_incl_radial_mlp": f_msg + f_rad,
                 "flop_per_message_rot_formulation_r1": conv_op.flops_per_edge(),
-                "hbm_view": {"achieved": per_kernel["msgpack_rot2"]["hbm_gbs_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
-                             "frac": per_kernel["msgpack_rot2"]["hbm_frac_of_measured_peak"],
+                "hbm_view": {"achieved": per_kernel[dom_name]["hbm_gbs_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
+                             "frac": per_kernel[dom_name]["hbm_frac_of_measured_peak"],
                              "alg_bytes_per_edge": alg["msgpack_rot2"][0] / max(1, E_local * MSG)},
                 "fused_conv_hbm_view_survey_8d": {"alg_bytes_per_edge": 4 * (877 + 36 + 64) + 16 + 2 * 877 * 4 * N_local / max(1, E_local),
                                                   "note": "compulsory bytes of an ideal single-pass fusion (SURVEY 8d); this design stages rotated operands and the radial gate in HBM"}}

@@ -340,10 +340,12 @@ __device__ __forceinline__ void rot_epilogue(uint32_t tc0, int mul, uint32_t cma
 // short (K/8 and mp/8 instructions x 3): its accumulator adds truncate, and a chain over all ~50 paths of a slot
 // cost 4x the fp32 rounding error of the whole network (scripts/error_budget.py, profiles/r01o_error_budget.log).
 // RW = padded-multiplicity capacity of the class (registers, stage size); ty.mpad <= RW is the MMA N.
-// warps 0-3 gate / accumulate, 4 GEMM1, 5 TMA (A chunks) + gate L2 prefetch, 6 GEMM2 + TMA (L' image of the next step), 7 TMA (W chunks).
+// warps 0-3 gate / accumulate, 4 GEMM1, 5 TMA (A chunks), 6 GEMM2, 7 TMA (W chunks), 8 TMA (L' images) + gate L2 prefetch.
+// Measured on tbg_m28 (profiles/README.md r03): one producer warp 871 ms, A | W+L' 854 ms, A | W | L' 838 ms, L' issued by the
+// GEMM2 warp 893 ms (the ~400-cycle issue lands on the gate -> GEMM2 -> accumulate chain).
 // One cp.async.bulk costs its issuing thread ~400 cycles whatever its size, but the cost does not add up across warps
 // (profiles/r02v_tma_probe.txt): with a single producer thread the 3-5 bulk copies of a step paced the kernel.
-constexpr int NTHR2 = 256;
+constexpr int NTHR2 = 288;
 
 // barrier helpers on precomputed 32-bit shared addresses (no generic -> shared conversion per use)
 __device__ __forceinline__ void wait_a(uint32_t addr, uint32_t parity) {
@@ -425,40 +427,51 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
   const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
   const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
 
-  if (warp == 5 || warp == 7) {
-    // =============================== TMA producers: A chunks | W chunks + L' images + gate prefetch ===============================
+  if (warp == 5 || warp == 7 || warp == 8) {
+    // =============================== TMA producers: A chunks | W chunks | L' images + gate prefetch ===============================
     if (lane == 0) {
       const float* xt = a.xp + (size_t)tile * a.tile_stride;
-      const bool isA = warp == 5;
-      // gate block of a step: mul columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 GPF steps
-      // before the epilogue warps load it (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident)
-      constexpr int GPF = 3;
-      const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
-      const float* gt = a.g + (size_t)tile * a.gstride * TILE;
-      auto prefetch_gate = [&](int sj) {
-        if (sj < se) {
-          const hgb_rot_step_t* ps = a.steps + sj;
-          if (ps->branch >= 0) bulk_prefetch_l2(gt + (size_t)ps->branch * g_bstride + (size_t)ps->g_off * TILE, (uint32_t)(mul * TILE) * 4u);
-        }
-      };
-      if (isA)
+      if (warp == 8) {
+        // gate block of a step: mul columns x 128 edges, contiguous in the tile-major gate tensor -> pulled into L2 GPF steps
+        // before the epilogue warps load it (the gate tensor of a chunk is GBs, written by the pre-pass: not L2 resident)
+        constexpr int GPF = 3;
+        const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+        const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+        auto prefetch_gate = [&](int sj) {
+          if (sj < se) {
+            const hgb_rot_step_t* ps = a.steps + sj;
+            if (ps->branch >= 0) bulk_prefetch_l2(gt + (size_t)ps->branch * g_bstride + (size_t)ps->g_off * TILE, (uint32_t)(mul * TILE) * 4u);
+          }
+        };
         for (int j = 0; j < GPF; ++j) prefetch_gate(sb + j);
-      int n = 0, c_all = 0;
-      for (int si = sb; si < se; ++si, ++n) {
-        const hgb_rot_step_t st = a.steps[si];
-        if (isA) prefetch_gate(si + GPF);
-        const int kpad = st.kpad;
-        for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
-          const int kc = min(KC, kpad - u0), s = c_all % NST;
-          if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
-          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
-          const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
-          if (isA) {
-            expect_tx_a(B_FULL + 8 * s, ab);
-            bulk_g2s_a(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
-          } else {
-            expect_tx_a(B_FULL + 8 * s, wb);
-            bulk_g2s_a(sa + 2 * KC * TILE * 4, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
+        int n = 0;
+        const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
+        for (int si = sb; si < se; ++si, ++n) {
+          const hgb_rot_step_t st = a.steps[si];
+          prefetch_gate(si + GPF);
+          const int lb = n & 1;
+          if (n >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((n >> 1) - 1) & 1));   // GEMM2(n-2) has read the L' buffer
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(sl0 + (uint32_t)(lb * 2 * RW * RW) * 4u, wbuf + st.lf_off, lbytes, B_LFULL + 8 * lb);
+        }
+      } else {
+        const bool isA = warp == 5;
+        int c_all = 0;
+        for (int si = sb; si < se; ++si) {
+          const hgb_rot_step_t st = a.steps[si];
+          const int kpad = st.kpad;
+          for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
+            const int kc = min(KC, kpad - u0), s = c_all % NST;
+            if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
+            const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
+            const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
+            if (isA) {
+              expect_tx_a(B_FULL + 8 * s, ab);
+              bulk_g2s_a(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
+            } else {
+              expect_tx_a(B_FULL + 8 * s, wb);
+              bulk_g2s_a(sa + 2 * KC * TILE * 4, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
+            }
           }
         }
       }
@@ -495,21 +508,9 @@ __global__ void __launch_bounds__(NTHR2, (RW == 64 ? 1 : 2)) msgpack_rot_kernel(
       kpad = kpad_next;
     }
   } else if (warp == 6) {
-    // =============================== GEMM2 issuer (+ the L' image of the next step) ===============================
+    // =============================== GEMM2 issuer ===============================
     int n = 0;
-    const uint32_t lbytes = (uint32_t)(2 * mp * mp) * 4u;
-    auto load_l = [&](int sj, int nj) {   // one lane: L' image of step sj -> buffer nj & 1 (GEMM2(nj - 2) must have read it)
-      if (sj < se && lane == 0) {
-        const int lb = nj & 1;
-        if (nj >= 2) wait_a(B_S2 + 8 * lb, (uint32_t)(((nj >> 1) - 1) & 1));
-        expect_tx_a(B_LFULL + 8 * lb, lbytes);
-        bulk_g2s_a(sl0 + (uint32_t)(lb * 2 * RW * RW) * 4u, wbuf + a.steps[sj].lf_off, lbytes, B_LFULL + 8 * lb);
-      }
-      __syncwarp();
-    };
-    load_l(sb, 0);
     for (int si = sb; si < se; ++si, ++n) {
-      load_l(si + 1, n + 1);
       const int gi = dbl ? (n & 1) : 0;
       warp_wait_a(B_GFULL + 8 * gi, (uint32_t)((dbl ? (n >> 1) : n) & 1));
       warp_wait_a(B_LFULL + 8 * (n & 1), (uint32_t)((n >> 1) & 1));

@@ -800,12 +800,17 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
     const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
     {
+      hgb::TimeScope ts(HGB_K_RADIAL_GATE, stream);
       const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 1);
       if (rc != 0) return rc;
     }
     pa.e_lo = e_lo; pa.n_chunk = n;
-    rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
-    HGB_LAUNCH_OK("rotate_pack_kernel");
+    {
+      hgb::TimeScope ts(HGB_K_ROTATE_PACK, stream);
+      rot::rotate_pack_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
+      HGB_LAUNCH_OK("rotate_pack_kernel");
+    }
+    hgb::TimeScope ts_msg(HGB_K_MSGPACK_ROT, stream);   // the three slot classes of msgpack_rot_kernel together
     for (int k = 0; k < 3; ++k) {
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;

@@ -397,7 +397,7 @@ extern "C" int hgb_segment_sum(const float* rows, int32_t n_cols, const int64_t*
   HGB_CHECK_ARG(rows && seg_ptr && seg_order && out, "hgb_segment_sum: NULL argument");
   HGB_CHECK_ARG(n_cols > 0 && n_out_rows >= 0 && n_out_rows < (1ll << 31), "hgb_segment_sum: bad sizes");
   if (n_out_rows == 0) return 0;
-  hgb::TimeScope ts_(HGB_K_OTHER, stream);
+  hgb::TimeScope ts_(HGB_K_SEGMENT_SUM, stream);
   segment_sum_kernel<<<(unsigned)n_out_rows, 256, 0, (cudaStream_t)stream>>>(rows, n_cols, seg_ptr, seg_order, out);
   HGB_LAUNCH_OK("segment_sum_kernel");
   return 0;

@@ -188,7 +188,7 @@ def check(rc: int, what: str):
 
 
 KERNEL_IDS = ["radial_gate", "rotate_pack", "msgpack_rot2", "unrotate", "wigner", "edge_embed", "linear", "resblock",
-              "ham_assemble", "ham_finalize", "other"]
+              "ham_assemble", "ham_finalize", "other", "msgpack_rot", "segment_sum"]
 
 
 def timing_enable(on: bool) -> None:

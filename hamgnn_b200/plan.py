@@ -1357,7 +1357,7 @@ class MessagePackOp:
             seg_out = None
             if out_index is not None and os.environ.get("HGB_ROT_ATOMIC") != "1":
                 seg_out, seg_index = out, out_index
-                out = workspace("msg_rows", max(1, E) * self.irreps_out.dim, out.device).view(max(1, E), self.irreps_out.dim)[:E]
+                out = workspace("msg_rows", max(1, E) * self.irreps_out.dim, out.device)[:E * self.irreps_out.dim].view(E, self.irreps_out.dim)
                 out_index = None
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4

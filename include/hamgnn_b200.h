@@ -220,7 +220,7 @@ int hgb_segment_sum(const float* rows, int32_t n_cols, const int64_t* seg_ptr, c
 enum {
   HGB_K_RADIAL_GATE = 0, HGB_K_ROTATE_PACK = 1, HGB_K_MSGPACK_ROT2 = 2, HGB_K_UNROTATE = 3, HGB_K_WIGNER = 4,
   HGB_K_EDGE_EMBED = 5, HGB_K_LINEAR = 6, HGB_K_RESBLOCK = 7, HGB_K_HAM_ASSEMBLE = 8, HGB_K_HAM_FINALIZE = 9,
-  HGB_K_OTHER = 10, HGB_N_KERNEL_IDS = 16
+  HGB_K_OTHER = 10, HGB_K_MSGPACK_ROT = 11, HGB_K_SEGMENT_SUM = 12, HGB_N_KERNEL_IDS = 16
 };
 int hgb_timing_enable(int32_t on);
 int hgb_timing_collect(float* ms_out, int64_t* count_out);
