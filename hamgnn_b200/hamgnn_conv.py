@@ -299,7 +299,7 @@ class HamGNNConvE3(nn.Module):
                 raise NotImplementedError(f"rbf_func={c['rbf_func']} is a config variant outside the B200 hot path "
                                           "(SURVEY.md section 2 row 8); only 'bessel' is implemented")
             raise ValueError(f"Unsupported radial basis function: {c['rbf_func']}")
-        for flag in ("use_corr_prod", "use_kan", "build_internal_graph", "lite_mode", "apply_charge_doping"):
+        for flag in ("use_corr_prod", "use_kan", "lite_mode", "apply_charge_doping"):
             if c[flag]:
                 raise NotImplementedError(f"HamGNN_pre.{flag}=True is outside the B200 hot path of this round "
                                           "(SURVEY.md section 8f)")
@@ -312,6 +312,9 @@ class HamGNNConvE3(nn.Module):
         self.num_layers = int(c["num_layers"])
         self.radial_MLP = list(c["radial_MLP"])
         self.legacy_edge_update = bool(c["legacy_edge_update"])
+        self.build_internal_graph = bool(c["build_internal_graph"])
+        self.radius_scale = float(c.get("radius_scale", 1.0))
+        self.radius_type = str(c.get("radius_type", "openmx")).lower()
         self.irreps_edge_sh = Irreps(c["irreps_edge_sh"])
         self.irreps_node_features = Irreps(c["irreps_node_features"])
         for m in self.irreps_edge_sh:
@@ -370,6 +373,15 @@ class HamGNNConvE3(nn.Module):
                                "torch.no_grad() (backward kernels are the first 'next' row, SURVEY.md section 8f)")
         if torch.get_default_dtype() != torch.float32:
             raise NotImplementedError("the B200 path computes in fp32 (reference default precision: 32)")
+        matching = None
+        if self.build_internal_graph:
+            # message passing on a graph built here from (z, pos, cell) with radius_scale x the OpenMX cutoffs; the edge features
+            # of the DFT edges of `data` are picked out at the end (hamgnn_conv.py:252-283, base_model.py:237-288)
+            from .graph_build import generate_graph
+            from .graph_data import Data
+            g = generate_graph(data, self.radius_scale, self.radius_type)
+            matching = g.pop("matching_edges")
+            data = Data(**{k: g[k] for k in ("z", "pos", "batch", "edge_index", "cell_shift", "nbr_shift")})
         z = data["z"]
         L.require_cuda(z)
         zkey = (z.data_ptr(), z._version, z.numel())
@@ -387,4 +399,5 @@ class HamGNNConvE3(nn.Module):
         for i in range(self.num_layers):
             self.convolutions[i](data)
             self.pair_interactions[i](data)
-        return AttrDict(node_attr=data["node_features"], edge_attr=data["edge_features"])
+        edge_attr = data["edge_features"] if matching is None else data["edge_features"][matching]
+        return AttrDict(node_attr=data["node_features"], edge_attr=edge_attr)

@@ -207,6 +207,21 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
                             float* out, const int64_t* out_index, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f4: graph construction on the device.  hgb_neighbor_list replaces neighbor_list_and_relative_vec
+ * (hamgnn/models/base_model.py:87-178: ASE primitive_neighbor_list on the CPU with per-atom cutoffs) for one crystal:
+ * directed edges i -> (j, S), S in [-reps, reps]^3, iff 0 < |pos_j + S.cell - pos_i| < radius_i + radius_j (fp64), sorted by
+ * (i, j, S).  Two passes: deg != NULL counts the edges of every atom; after an exclusive scan (offset[N+1]) the second call
+ * (deg == NULL) writes edge_index [2][E], cell_shift [E][3] (int64) and nbr_shift [E][3] = S.cell (fp32).
+ * hgb_edge_lookup replaces find_matching_columns_of_A_in_B (:180-233) and the inverse-edge search of the data generator
+ * (DFT_interfaces/openmx/graph_data_gen.py:293-295): out[e] = index of query edge e -- or of its inverse (dst, src, -S) -- in
+ * the sorted graph, -1 if absent. */
+int hgb_neighbor_list(const double* pos, const double* radius, const double* cell_host, const int32_t* reps_host, int64_t n_atoms,
+                      int64_t* deg, const int64_t* offset, int64_t n_edges, int64_t* edge_index, int64_t* cell_shift, float* nbr_shift,
+                      void* stream);
+int hgb_edge_lookup(const int64_t* q_index, const int64_t* q_shift, int64_t n_query, int32_t inverse, const int64_t* g_index,
+                    const int64_t* g_shift, const int64_t* g_offset, int64_t n_graph_edges, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a9, deterministic receiver reduction for message kernels that write one row per edge (the 'rot' backend): replaces
  * torch_scatter.scatter(messages, receiver, reduce='sum') (hamgnn/nn/convolution.py:147-149).  out[i][:] = sum over
  * j in [seg_ptr[i], seg_ptr[i+1]) of rows[seg_order[j]][:], added in list order (no atomics: bit-reproducible). */
