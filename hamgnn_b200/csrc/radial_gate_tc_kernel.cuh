@@ -25,6 +25,36 @@ constexpr int TN = 64;     // gate columns per MMA tile
 constexpr int KMAX = 64;   // h2 <= 64
 constexpr int WRING = 3;
 
+// Barrier wait of this kernel: a plain try_wait loop (try_wait itself parks the thread for a hardware time slice).  The
+// tcr::warp_wait it used in round 1 adds a try_wait suspend hint of 10 us and a nanosleep back-off: 36 % of this kernel's
+// stall samples were `stall_sleep` (profiles/r02y), every MMA <-> epilogue hand-off of its 57 tiles overslept.
+__device__ __forceinline__ void spin_wait(uint64_t* mbar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t addr = tc::smem_u32(mbar);
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "mov.u32 %0, 1;\n"
+        "HGB_GTC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra HGB_GTC_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x4000000;\n\t"
+        "@p bra HGB_GTC_WAIT;\n\t"
+        "mov.u32 %0, 0;\n"
+        "HGB_GTC_DONE:\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok) __trap();
+  }
+  __syncwarp();
+}
+
 struct Sm {
   static constexpr int AHI = 0;
   static constexpr int ALO = AHI + KMAX * ROWS;
@@ -158,14 +188,14 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
     for (int t = 0; t < ntiles; ++t) {
       if (t + 1 < ntiles) {
         // slot (t + 1) % 3 was last read by the MMAs of tile t - 2
-        if (t >= 2) tcr::warp_wait(&wdone[(t - 2) % WRING], (uint32_t)(((t - 2) / WRING) & 1));
+        if (t >= 2) spin_wait(&wdone[(t - 2) % WRING], (uint32_t)(((t - 2) / WRING) & 1));
         load_tile(t + 1);
       }
       cp_async_commit();
       cp_async_wait_group<1>();   // tile t has landed
       tc::fence_proxy_async();
       __syncwarp();
-      if (t >= 2) tcr::warp_wait(&dempty[t & 1], (uint32_t)(((t >> 1) - 1) & 1));   // accumulator drained (tile t - 2)
+      if (t >= 2) spin_wait(&dempty[t & 1], (uint32_t)(((t >> 1) - 1) & 1));   // accumulator drained (tile t - 2)
       if (lane == 0) {
         tc::fence_after_sync();
         const float* wt = smem + Sm::RING + (t % WRING) * Sm::TILE;
@@ -190,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
     const bool live = tid < ne;
     float* grow = a.g + ((size_t)b * a.n_edges + (size_t)(e0 + (live ? tid : 0))) * a.gstride;
     for (int t = 0; t < ntiles; ++t) {
-      tcr::warp_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
+      spin_wait(&dfull[t & 1], (uint32_t)((t >> 1) & 1));
       tc::fence_after_sync();
       const int n0 = t * TN;
 #pragma unroll
