@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "msgpack_tcr_kernel.cuh"
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
+#include "msgpack_rot16_kernel.cuh"
 #include "msgpack_rot2_kernel.cuh"
 
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
@@ -818,6 +819,157 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
       else if (k == 1) rc = launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
+      if (rc != 0) return rc;
+    }
+  }
+  return 0;
+}
+
+// ============================================================================================== rot16 (fp16 x 2 split) host side
+namespace {
+template <int RW, int NST>
+int launch_rot16_class(const rot16::Rot16Args& ra, int n_tiles, cudaStream_t st) {
+  constexpr size_t smem = rot16::rot16_smem_bytes<RW, NST>();
+  static_assert(smem <= 227 * 1024, "msgpack_rot16_kernel shared memory");
+  HGB_CUDA_OK(cudaFuncSetAttribute(rot16::msgpack_rot16_kernel<RW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rot16::msgpack_rot16_kernel<RW, NST><<<(unsigned)(n_tiles * ra.n_slots), rot::NTHR2, smem, st>>>(ra);
+  HGB_LAUNCH_OK("msgpack_rot16_kernel");
+  return 0;
+}
+}  // namespace
+
+extern "C" int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan, const hgb_rot_plan* rp, const float* const* src,
+                                         const int64_t* const* src_rows, const float* dw, const float* rbf,
+                                         const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off, int32_t gstride,
+                                         float* g_ws, float* xp_ws, float* sx_ws, const float* wbuf16, int64_t wbuf16_words,
+                                         const float* img_inv, int32_t n_images, int64_t chunk_edges, int64_t n_edges,
+                                         float* out, const int64_t* out_index, int32_t flags, void* stream) {
+  HGB_DEVICE_GUARD(out);
+  HGB_CHECK_ARG(plan && rp && src && dw && rbf && out && g_ws && xp_ws && sx_ws && wbuf16 && img_inv && w3_off && nch,
+                "hgb_msgpack_rot16_forward: NULL argument");
+  HGB_CHECK_ARG(plan->types_host && plan->paths_host && rp->blocks_host && rp->steps_host && rp->blocks && rp->steps,
+                "hgb_msgpack_rot16_forward: host and device copies of the tables are required");
+  HGB_CHECK_ARG(plan->n_sources >= 1 && plan->n_sources <= 4 && plan->n_branches >= 1 && plan->n_branches <= 2,
+                "hgb_msgpack_rot16_forward: bad source/branch count");
+  HGB_CHECK_ARG(plan->h2 <= 64 && plan->h1 <= 64 && plan->rbf_dim <= 64,
+                "hgb_msgpack_rot16_forward: radial MLP [%d,%d,%d] unsupported (all widths <= 64)", plan->rbf_dim, plan->h1, plan->h2);
+  HGB_CHECK_ARG(plan->n_types <= 32 && rp->lmax >= 0 && rp->lmax <= rot::LMAX, "hgb_msgpack_rot16_forward: too many output slots or l > %d", rot::LMAX);
+  HGB_CHECK_ARG(n_edges >= 0 && n_edges < (1ll << 31), "hgb_msgpack_rot16_forward: bad edge count");
+  HGB_CHECK_ARG(chunk_edges >= rot::TILE && chunk_edges % rot::TILE == 0, "hgb_msgpack_rot16_forward: chunk_edges must be a positive multiple of %d", rot::TILE);
+  HGB_CHECK_ARG(rp->tile_stride > 0 && rp->tile_stride % 4 == 0 && rp->n_blocks >= 1 && rp->n_blocks < 32768, "hgb_msgpack_rot16_forward: bad packed-input layout");
+  HGB_CHECK_ARG(n_images >= 1 && n_images <= 65536 && wbuf16_words > 0, "hgb_msgpack_rot16_forward: bad image table");
+  if (n_edges == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b = 0; b < plan->n_branches; ++b)
+    HGB_CHECK_ARG(nch[b] > 0 && nch[b] <= gstride, "hgb_msgpack_rot16_forward: gate width %d exceeds stride %d", nch[b], gstride);
+  for (int s = 0; s < plan->n_sources; ++s) HGB_CHECK_ARG(src[s] != nullptr, "hgb_msgpack_rot16_forward: source %d is NULL", s);
+
+  // ---- validate the tables (host copies); offsets are in 32-bit words, kpad of a block in channels, kpad of a step in words
+  for (int i = 0; i < rp->n_blocks; ++i) {
+    const hgb_rot_block_t& b = rp->blocks_host[i];
+    HGB_CHECK_ARG(b.l1 >= 0 && b.l1 <= rp->lmax && b.nsrc >= 1 && b.nsrc <= 2 && b.src0 >= 0 && b.src0 + b.nsrc <= plan->n_sources,
+                  "hgb_msgpack_rot16_forward: bad block %d", i);
+    HGB_CHECK_ARG(b.kpad % 16 == 0 && b.kpad >= b.nsrc * b.mul && b.mul >= 1 && b.in_off >= 0 &&
+                      b.in_off + b.mul * (2 * b.l1 + 1) <= plan->src_dim[b.src0],
+                  "hgb_msgpack_rot16_forward: block %d outside its source row", i);
+    HGB_CHECK_ARG(b.xoff >= 0 && b.xoff % 4 == 0 && (int64_t)b.xoff + (int64_t)(2 * b.l1 + 1) * b.kpad * rot::TILE <= rp->tile_stride,
+                  "hgb_msgpack_rot16_forward: block %d outside the packed tile", i);
+  }
+  int klass[32], order[32];
+  double cost[32];
+  for (int t = 0; t < plan->n_types; ++t) {
+    const hgb_type_t& ty = plan->types_host[t];
+    const int d3 = 2 * ty.l + 1;
+    HGB_CHECK_ARG(ty.l >= 0 && ty.l <= rp->lmax && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
+                  "hgb_msgpack_rot16_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
+    klass[t] = ty.mpad <= 16 ? 0 : (ty.mpad <= 32 ? 1 : 2);
+    {
+      const int dbl = (klass[t] == 1) ? 0 : 1;
+      HGB_CHECK_ARG((4 + 2 * dbl) * ty.mpad + d3 * ty.mul <= 512, "hgb_msgpack_rot16_forward: slot %d needs more than 512 TMEM columns", t);
+    }
+    HGB_CHECK_ARG(rp->step_begin[t] >= 0 && rp->step_begin[t] <= rp->step_begin[t + 1], "hgb_msgpack_rot16_forward: bad step range of slot %d", t);
+    double c = 0;
+    int last_m3 = -1, open_group = 0;
+    for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si) {
+      const hgb_rot_step_t& s = rp->steps_host[si];
+      const uint32_t wimg = (uint32_t)s.pad2 & 0xffffu, limg = (uint32_t)s.pad2 >> 16;
+      HGB_CHECK_ARG(s.kpad >= 8 && s.kpad % 8 == 0 && s.m3 >= 0 && s.m3 < d3 && s.kind == 0 && s.a_off >= 0 && s.a_off % 4 == 0 &&
+                        (int64_t)s.a_off + (int64_t)2 * s.kpad * rot::TILE <= rp->tile_stride && s.w_off >= 0 && s.w_off % 4 == 0 &&
+                        (int64_t)s.w_off + (int64_t)2 * ty.mpad * s.kpad <= wbuf16_words && s.lf_off >= 0 && s.lf_off % 4 == 0 &&
+                        (int64_t)s.lf_off + (int64_t)ty.mpad * ty.mpad <= wbuf16_words && (s.new_path & 1) && s.pad >= 0 &&
+                        s.pad < rp->n_blocks && (int)wimg < n_images && (int)limg < n_images,
+                    "hgb_msgpack_rot16_forward: bad step %d", si);
+      HGB_CHECK_ARG(s.branch < plan->n_branches && (s.branch < 0 || (s.g_off >= 0 && s.g_off + ty.mul <= nch[s.branch])),
+                    "hgb_msgpack_rot16_forward: gate columns of step %d out of range", si);
+      HGB_CHECK_ARG(open_group ? (s.m3 == last_m3) : (s.m3 > last_m3), "hgb_msgpack_rot16_forward: step %d breaks the m3 grouping", si);
+      last_m3 = s.m3;
+      open_group = (s.new_path & 4) ? 0 : 1;
+      c += (double)(2 * s.kpad + ty.mpad) * ty.mpad + 600.0;
+    }
+    HGB_CHECK_ARG(open_group == 0, "hgb_msgpack_rot16_forward: slot %d ends inside an m3 group", t);
+    cost[t] = c;
+    order[t] = t;
+  }
+  for (int i = 0; i < plan->n_types; ++i)
+    for (int j = i + 1; j < plan->n_types; ++j)
+      if (cost[order[j]] > cost[order[i]]) { int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+
+  rot16::Rot16Args cls[3];
+  for (int k = 0; k < 3; ++k) {
+    rot16::Rot16Args& a = cls[k];
+    memset(&a, 0, sizeof(a));
+    a.plan = *plan;
+    a.steps = rp->steps;
+    for (int t = 0; t <= plan->n_types; ++t) a.step_begin[t] = rp->step_begin[t];
+    a.tile_stride = rp->tile_stride; a.dstride = rp->dstride;
+    for (int l = 0; l <= rp->lmax; ++l) a.doff[l] = rp->doff[l];
+    a.gstride = gstride; a.out = out; a.out_index = out_index; a.xp = reinterpret_cast<const uint32_t*>(xp_ws); a.g = g_ws; a.dw = dw;
+    a.sx = sx_ws; a.n_blocks = rp->n_blocks; a.img_inv = img_inv; a.wbuf16 = wbuf16; a.swap_halves = flags & 1;
+    int ns = 0;
+    for (int q = 0; q < plan->n_types; ++q) {
+      const int t = order[q];
+      if (klass[t] != k) continue;
+      if (rp->step_begin[t] == rp->step_begin[t + 1] && out_index != nullptr) continue;
+      a.slot[ns++] = t;
+    }
+    a.n_slots = ns;
+    a.dbl = (k == 1) ? 0 : 1;
+  }
+  rot16::Rp16Args pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.blocks = rp->blocks; pa.n_blocks = rp->n_blocks; pa.tile_stride = rp->tile_stride; pa.dstride = rp->dstride;
+  for (int l = 0; l <= rp->lmax; ++l) pa.doff[l] = rp->doff[l];
+  for (int s = 0; s < plan->n_sources; ++s) {
+    pa.src[s] = src[s];
+    pa.src_rows[s] = src_rows ? src_rows[s] : nullptr;
+    pa.src_dim[s] = plan->src_dim[s];
+  }
+  pa.dw = dw; pa.xp = reinterpret_cast<uint32_t*>(xp_ws); pa.sx = sx_ws;
+  pa.blocks_per_cta = (rp->n_blocks + 3) / 4;
+  const unsigned rp_gy = (unsigned)((rp->n_blocks + pa.blocks_per_cta - 1) / pa.blocks_per_cta);
+
+  for (int64_t e_lo = 0; e_lo < n_edges; e_lo += chunk_edges) {
+    const int64_t n = (n_edges - e_lo < chunk_edges) ? (n_edges - e_lo) : chunk_edges;
+    const int n_tiles = (int)((n + rot::TILE - 1) / rot::TILE);
+    {
+      hgb::TimeScope ts(HGB_K_RADIAL_GATE, stream);
+      const int rc = launch_radial_gate(plan, rbf + e_lo * plan->rbf_dim, w3_off, nch, w3img_off, gstride, g_ws, n, st, 1);
+      if (rc != 0) return rc;
+    }
+    pa.e_lo = e_lo; pa.n_chunk = n;
+    {
+      hgb::TimeScope ts(HGB_K_ROTATE_PACK, stream);
+      rot16::rotate_pack16_kernel<<<dim3((unsigned)n_tiles, rp_gy), rot::TILE, 0, st>>>(pa);
+      HGB_LAUNCH_OK("rotate_pack16_kernel");
+    }
+    hgb::TimeScope ts_msg(HGB_K_MSGPACK_ROT, stream);
+    for (int k = 0; k < 3; ++k) {
+      if (cls[k].n_slots == 0) continue;
+      cls[k].e_lo = e_lo; cls[k].n_chunk = n;
+      int rc = 0;
+      if (k == 0) rc = launch_rot16_class<16, 3>(cls[k], n_tiles, st);
+      else if (k == 1) rc = launch_rot16_class<32, 2>(cls[k], n_tiles, st);
+      else rc = launch_rot16_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }
   }
