@@ -18,7 +18,7 @@
 // row = channels 2j | 2j+1 << 16), so descriptors, chunking (32 words = 64 channels per chunk) and TMEM addressing are those of
 // msgpack_rot_kernel with kpad -> kpad / 2; the packed gated product occupies mp / 2 TMEM columns.
 #pragma once
-#include <cuda_fp16.h>
+
 
 namespace rot16 {
 using namespace tcmsg;

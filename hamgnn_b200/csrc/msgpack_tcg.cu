@@ -8,6 +8,7 @@
 // Everything else (tables, packing, A-operand generation, 3xTF32 split, GEMM1 / GEMM2 structure) is identical to
 // msgpack_tc.cu.  Price: 2 x 4 B x n_channels (28.7 KB) of extra HBM write + read per message.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "hgb_common.cuh"
 #include "tc_common.cuh"
 #include "msgpack_tc_helpers.cuh"

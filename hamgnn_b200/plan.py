@@ -265,7 +265,8 @@ PROFILER: Optional[KernelProfiler] = None
 # 'tcg' / 'tc' / 'simt' = round-1 kernels, only when asked for by name.
 BACKEND = os.environ.get("HGB_MSGPACK", "rot")
 # radial gate pre-pass of the 'tcg' backend: 'tc' = tcgen05 GEMM (radial_gate_tc_kernel), 'simt' = fp32 FMA (radial_gate_kernel)
-GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND in ("rot", "rot2") else "simt")
+GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND in ("rot", "rot2", "rot16") else "simt")
+ROT16_FLAGS = int(os.environ.get("HGB_ROT16_FLAGS", "0"))   # bit 0: debug, swapped halves of the packed TMEM words
 
 
 # edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)
@@ -462,6 +463,7 @@ class MessagePackOp:
         self._build_pack_program()
         self._build_tc_program()
         self._build_rot_program()
+        self._build_rot16_program()
         self._build_rot2_program()
         self._finish_tc_program()
         self._dev: Dict[str, dict] = {}
@@ -674,6 +676,7 @@ class MessagePackOp:
         types = (L.TypeT * len(self.irreps_out))()
         plist = []
         meta = []      # parallel to plist: (branch, TPPath | None for the direct Linear, output slot)
+        specs = []     # parallel to plist: dense operand specs (W source index [K, M], W scale, L' source index [M, Mt] | None)
         simt_iter = iter(range(self.n_paths))
         for t, m in enumerate(self.irreps_out):
             mp = (m.mul + 15) // 16 * 16
@@ -707,10 +710,14 @@ class MessagePackOp:
                     plist.append(L.PathT(0, b, br.src0, br.nsrc, sp.in_off, sp.mul_in, sp.l1, sp.l2, sp.l3, sp.sh_off,
                                          sp.cg_off, sp.cg_kstart, w_off, w3_off, lf_off, p.ch_off))  # pad0 = first gate column
                     meta.append((b, p, t))
+                    kk, nn = np.meshgrid(np.arange(K), np.arange(M), indexing="ij")
+                    specs.append((base[("tp", b)] + p.w_off + kk * M + nn, coef,
+                                  base[("F", b)] + f0 + (p.ch_off - ch_type0 + ww) * Mt + wo))
             # same (l1, l2) paths of the two branches adjacent: they share T_z (the rows-in-lanes kernel builds it once)
             order = sorted(range(begin, len(plist)), key=lambda i: (plist[i].l1, plist[i].l2, plist[i].branch))
             plist[begin:] = [plist[i] for i in order]
             meta[begin:] = [meta[i] for i in order]
+            specs[begin:] = [specs[i] for i in order]
             if self.direct_src is not None:
                 sp = self.paths_c[next(simt_iter)]
                 bl = [x for x in self.direct_blocks[0] if x.i_out == t][0]
@@ -727,6 +734,8 @@ class MessagePackOp:
                 wcur += 2 * mp * Kpad
                 plist.append(L.PathT(1, 0, self.direct_src, 1, sp.in_off, sp.mul_in, sp.l1, 0, sp.l3, 0, 0, 0, 0, 0, lf_off, 0))
                 meta.append((0, None, t))
+                kk, nn = np.meshgrid(np.arange(K), np.arange(bl.mul_out), indexing="ij")
+                specs.append((base[("direct", 0)] + bl.w_off + kk * bl.mul_out + nn, bl.scale, None))
             types[t] = L.TypeT(m.mul, mp, m.ir.l, out_offs[t], begin, len(plist), 0, 0)
         # identity L' images (hi = I, lo = 0), one per padded multiplicity: the rotated-frame kernel runs the un-gated
         # direct Linear through the same GEMM1 -> gate -> GEMM2 pipeline with g = 1 and L' = I
@@ -768,6 +777,7 @@ class MessagePackOp:
             wcur += mp * mp
         self.tc_w_total = wcur
         self.tc_path_meta = meta
+        self.tc_path_specs = specs
         self._tc_lists = (dst, src, scale, part)     # the rot2 program appends its images, then _finish_tc_program()
 
     def _finish_tc_program(self):
@@ -863,6 +873,183 @@ class MessagePackOp:
             d = 2 * l + 1
             jt[self.rot_doff[l]:self.rot_doff[l] + d * d] = so3.wigner_J(l).reshape(-1)
         self.rot_wigner_j = jt
+
+    # -------------------------------------------------------------------------------- rotated frame, fp16 x 2 split operands
+    def _build_rot16_program(self):
+        """Tables of msgpack_rot16_kernel (csrc/msgpack_rot16_kernel.cuh): the steps of the 'rot' program with every operand
+        stored as a (hi | lo) pair of fp16 images, two channels per 32-bit word (word j of a row = channels 2j | 2j+1 << 16),
+        laid out in words exactly like a tf32 image of half the channels.  Every W / L' image carries its own power-of-two
+        scale (largest element just below 2^15); the inverse scales go to the kernel as `img_inv`.  Offsets in 32-bit words.
+
+        Packing program (consumed by pack_rot16): per operand element the halfword index of its hi value, the distance to its
+        lo value, the source element, the fp32 factor and the image it belongs to."""
+        T, KC = self.ROT_TILE, self.ROT_KC      # KC = 32 words = 64 channels per ring chunk
+        blocks: List[L.RotBlockT] = []
+        bkey: Dict[Tuple[int, int, int, int, int], int] = {}
+        xcur = 0
+
+        def block_of(src0, nsrc, in_off, mul, l1):
+            nonlocal xcur
+            key = (src0, nsrc, in_off, mul, l1)
+            if key not in bkey:
+                kpad = (nsrc * mul + 15) // 16 * 16
+                bkey[key] = len(blocks)
+                blocks.append(L.RotBlockT(src0, nsrc, in_off, mul, l1, kpad, xcur, 0))
+                xcur += (2 * l1 + 1) * kpad * T
+            return bkey[key]
+
+        dst, dlo, src, scale, img = [], [], [], [], []
+        wcur = 0
+        n_images = 0
+
+        def add_image(word0, N, kk, nn, srcidx, sc, kw, image):
+            """element (channel kk, row nn) of a (hi | lo) image of kw word-columns and N rows starting at word `word0`."""
+            kwd = kk // 2
+            word = word0 + (kwd // 4) * (N * 4) + nn * 4 + (kwd % 4)
+            d = np.asarray(2 * word + (kk % 2), dtype=np.int64).ravel()
+            dst.append(d)
+            dlo.append(np.full(d.shape, 2 * N * kw, dtype=np.int64))
+            src.append(np.broadcast_to(np.asarray(srcidx, dtype=np.int64), np.asarray(kk).shape).ravel())
+            scale.append(np.full(d.shape, sc, dtype=np.float32))
+            img.append(np.full(d.shape, image, dtype=np.int64))
+
+        w_img: Dict[int, Tuple[int, int]] = {}     # path -> (word offset, image index) of its W images
+        l_img: Dict[int, Tuple[int, int]] = {}     # path -> (word offset, image index) of its L' image
+        ident: Dict[int, Tuple[int, int]] = {}
+        for mp in sorted({int(ty.mpad) for ty in self.tc_types_c}):
+            kk = np.arange(mp)
+            add_image(wcur, mp, kk, kk, self.src_total, 1.0, mp // 2, n_images)
+            ident[mp] = (wcur, n_images)
+            wcur += mp * mp
+            n_images += 1
+        for t in range(len(self.irreps_out)):
+            ty = self.tc_types_c[t]
+            mp = int(ty.mpad)
+            for p in range(ty.path_begin, ty.path_end):
+                pa = self.tc_paths_c[p]
+                wsrc, wscale, lsrc = self.tc_path_specs[p]
+                K, M = wsrc.shape
+                kpad = (K + 15) // 16 * 16
+                kw = kpad // 2
+                w_img[p] = (wcur, n_images)
+                for c, w0 in enumerate(range(0, kw, KC)):
+                    kc = min(KC, kw - w0)
+                    ku = np.arange(2 * w0, min(2 * (w0 + kc), K))
+                    if len(ku):
+                        kk, nn = np.meshgrid(ku, np.arange(M), indexing="ij")
+                        add_image(wcur + 2 * mp * KC * c, mp, kk - 2 * w0, nn, wsrc[kk, nn], wscale, kc, n_images)
+                wcur += 2 * mp * kw
+                n_images += 1
+                if lsrc is not None:
+                    Ml, Mt = lsrc.shape
+                    kk, nn = np.meshgrid(np.arange(Ml), np.arange(Mt), indexing="ij")
+                    l_img[p] = (wcur, n_images)
+                    add_image(wcur, mp, kk, nn, lsrc, 1.0, mp // 2, n_images)
+                    wcur += mp * mp
+                    n_images += 1
+        steps: List[L.RotStepT] = []
+        step_begin = [0]
+        for t in range(len(self.irreps_out)):
+            ty = self.tc_types_c[t]
+            l3, mp = ty.l, int(ty.mpad)
+            for m3 in range(-l3, l3 + 1):
+                group: List[L.RotStepT] = []
+                for p in range(ty.path_begin, ty.path_end):
+                    pa = self.tc_paths_c[p]
+                    l1 = pa.l1
+                    bi = block_of(pa.src0, pa.nsrc, pa.in_off, pa.mul_in, l1)
+                    blk = blocks[bi]
+                    per_m = blk.kpad * T          # words: (hi | lo) x kpad / 2 words x T rows
+                    if pa.kind == 0:
+                        w = so3.wigner_3j(l1, pa.l2, l3)
+                        m1 = m3 if (l1 + pa.l2 + l3) % 2 == 0 else -m3
+                        if abs(m1) > l1:
+                            continue
+                        c = float(w[l1 + m1, pa.l2, l3 + m3]) * math.sqrt(2 * pa.l2 + 1)
+                        if c == 0.0:
+                            continue
+                        group.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, w_img[p][0], l_img[p][0], pa.pad0, c, blk.kpad // 2, 0,
+                                                pa.branch, l3 + m3, 1, bi, w_img[p][1] | (l_img[p][1] << 16)))
+                    else:
+                        group.append(L.RotStepT(blk.xoff + (l1 + m3) * per_m, w_img[p][0], ident[mp][0], 0, 1.0, blk.kpad // 2, 0,
+                                                -1, l3 + m3, 1, bi, w_img[p][1] | (ident[mp][1] << 16)))
+                if group:
+                    group[-1].new_path |= 4
+                steps.extend(group)
+            step_begin.append(len(steps))
+        assert len(steps) == self.rot_n_steps and n_images <= 32767
+        self.rot16_blocks_c = (L.RotBlockT * max(1, len(blocks)))(*blocks)
+        self.rot16_steps_c = (L.RotStepT * max(1, len(steps)))(*steps)
+        self.rot16_n_blocks = len(blocks)
+        self.rot16_step_begin = step_begin
+        self.rot16_tile_stride = xcur
+        self.rot16_w_words = wcur
+        self.rot16_n_images = n_images
+        self._r16_dst = np.concatenate(dst)
+        self._r16_dlo = np.concatenate(dlo)
+        self._r16_src = np.concatenate(src)
+        self._r16_scale = np.concatenate(scale)
+        self._r16_img = np.concatenate(img)
+
+    def rot16_supported(self) -> bool:
+        return self.rot_supported() and self.rot16_n_blocks < 32768
+
+    def rot16_plan(self, device) -> "L.RotPlan":
+        st = self._device_state(device)
+        if "rot16_plan" not in st:
+            st["rot16_blocks"] = torch.from_numpy(np.frombuffer(bytes(self.rot16_blocks_c), dtype=np.uint8).copy()).to(device)
+            st["rot16_steps"] = torch.from_numpy(np.frombuffer(bytes(self.rot16_steps_c), dtype=np.uint8).copy()).to(device)
+            base = self.rot_plan(device)
+            rp = L.RotPlan()
+            rp.n_blocks, rp.tile_stride, rp.lmax, rp.dstride = self.rot16_n_blocks, self.rot16_tile_stride, self.rot_lmax, self.rot_dstride
+            for l, o in enumerate(self.rot_doff):
+                rp.doff[l] = o
+            for t, b in enumerate(self.rot16_step_begin):
+                rp.step_begin[t] = b
+            rp.blocks, rp.steps = st["rot16_blocks"].data_ptr(), st["rot16_steps"].data_ptr()
+            rp.blocks_host = C.cast(self.rot16_blocks_c, C.c_void_p).value
+            rp.steps_host = C.cast(self.rot16_steps_c, C.c_void_p).value
+            rp.wigner_j = base.wigner_j
+            st["rot16_plan"] = rp
+        return st["rot16_plan"]
+
+    def pack_rot16(self, weights: dict) -> dict:
+        """fp16 (hi | lo) images of every W / L' of the rot16 program + their inverse power-of-two scales.  Cached per weight
+        version like pack_tc (which supplies the plan struct and the radial-MLP weights)."""
+        st = self.pack_tc(weights)
+        if st.get("r16_ver") != st["tc_ver"]:
+            dev = weights["tp"][0].device
+            if "r16_dst" not in st:
+                for k in ("dst", "dlo", "src", "scale", "img"):
+                    st[f"r16_{k}"] = torch.from_numpy(getattr(self, f"_r16_{k}")).to(dev)
+            with torch.no_grad():
+                vals = self._flat_weights(weights)[st["r16_src"]] * st["r16_scale"]
+                amax = torch.zeros(self.rot16_n_images, device=dev, dtype=torch.float32)
+                amax.scatter_reduce_(0, st["r16_img"], vals.abs(), reduce="amax", include_self=True)
+                _, ex = torch.frexp(amax)                       # amax < 2^ex
+                s = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), 15 - ex), torch.ones_like(amax))
+                v = vals * s[st["r16_img"]]
+                hi = v.to(torch.float16)
+                lo = (v - hi.float()).to(torch.float16)
+                buf = torch.zeros(2 * self.rot16_w_words, device=dev, dtype=torch.float16)
+                buf.index_copy_(0, st["r16_dst"], hi)
+                buf.index_copy_(0, st["r16_dst"] + st["r16_dlo"], lo)
+                st["r16_wbuf"] = buf
+                st["r16_inv"] = (1.0 / s).contiguous()
+            st["r16_ver"] = st["tc_ver"]
+        return st
+
+    def _flat_weights(self, weights: dict) -> torch.Tensor:
+        """All weights of the block as one fp32 vector in the order of `_src_base` (+ a trailing constant 1)."""
+        dev = weights["tp"][0].device
+        parts = []
+        for b in range(len(self.branches)):
+            parts += [weights["tp"][b].reshape(-1), weights["fc"][b][0].reshape(-1), weights["fc"][b][1].reshape(-1),
+                      weights["fc"][b][2].reshape(-1), self._fold(b, weights["lin_mid"][b], weights["lin_out"][b])]
+        if self.direct_src is not None:
+            parts.append(weights["direct"].reshape(-1))
+        parts.append(torch.ones(1, device=dev))   # constant source element (identity images)
+        return torch.cat(parts).float()
 
     # -------------------------------------------------------------------------------- rotated frame, A-stationary program
     R2_NB = 96        # B columns per piece (TMEM: B0 B1 GL0 GL1 of 96 columns + S0 S1 of 64)
@@ -1253,14 +1440,7 @@ class MessagePackOp:
                 st["tc_scale"] = torch.from_numpy(self._tc_scale).to(dev)
                 st["tc_part"] = torch.from_numpy(self._tc_part).to(dev)
             with torch.no_grad():
-                parts = []
-                for b in range(len(self.branches)):
-                    parts += [weights["tp"][b].reshape(-1), weights["fc"][b][0].reshape(-1), weights["fc"][b][1].reshape(-1),
-                              weights["fc"][b][2].reshape(-1), self._fold(b, weights["lin_mid"][b], weights["lin_out"][b])]
-                if self.direct_src is not None:
-                    parts.append(weights["direct"].reshape(-1))
-                parts.append(torch.ones(1, device=dev))   # constant source element (identity images)
-                cat = torch.cat(parts).float()
+                cat = self._flat_weights(weights)
                 vals = cat[st["tc_src"]] * st["tc_scale"]
                 hi = _tf32_round(vals)                                              # round-to-nearest tf32
                 lo = _tf32_round(vals - hi)
@@ -1294,7 +1474,8 @@ class MessagePackOp:
                 out_index: Optional[torch.Tensor] = None, edge_vec: Optional[torch.Tensor] = None):
         L.require_cuda(sh, rbf, out, *sources)
         backend = BACKEND
-        if backend in ("rot", "rot2") and (edge_vec is None or not (self.rot2_supported() if backend == "rot2" else self.rot_supported())):
+        if backend in ("rot", "rot2", "rot16") and (edge_vec is None or not (
+                self.rot2_supported() if backend == "rot2" else self.rot16_supported() if backend == "rot16" else self.rot_supported())):
             # Outside the rotated-frame kernels' limits (multiplicity > 64, l > 6, ...) the fp32-FMA kernel is the only other
             # backend inside the 1e-5 budget; the older tensor-core backends (tc / tcg, 9e-6 .. 1.1e-5)
             # run only when asked for by name.
@@ -1305,10 +1486,11 @@ class MessagePackOp:
                               "(~8x slower, same accuracy)", RuntimeWarning, stacklevel=2)
                 self._warned_fallback = True
             backend = "simt"
-        use_tc = (backend in ("tc", "tcg", "rot", "rot2")) and self.tc_supported()
-        use_rot = use_tc and backend == "rot"
+        use_tc = (backend in ("tc", "tcg", "rot", "rot2", "rot16")) and self.tc_supported()
+        use_rot16 = use_tc and backend == "rot16"
+        use_rot = use_tc and backend in ("rot", "rot16")
         use_rot2 = use_tc and backend == "rot2"
-        st = self.pack_tc(weights) if use_tc else self.pack(weights)[0]
+        st = (self.pack_rot16(weights) if use_rot16 else self.pack_tc(weights)) if use_tc else self.pack(weights)[0]
         ns = len(self.src_dims)
         if len(sources) != ns or len(rows) != ns:
             raise L.HgbError(f"MessagePackOp.forward: expected {ns} sources, got {len(sources)}")
@@ -1362,16 +1544,27 @@ class MessagePackOp:
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
             g_ws = workspace("gate", nb * chunk * gstride, out.device)   # [nb][tile][gstride][128]
-            xp_ws = workspace("xp", (chunk // self.ROT_TILE) * self.rot_tile_stride, out.device)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
             nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
             w3i = None
             if GATE_BACKEND == "tc" and self.tc_w3img_off is not None:
                 w3i = (C.c_int32 * 2)(*(list(self.tc_w3img_off) + [0] * (2 - nb)))
-            rc = L.load().hgb_msgpack_rot_forward(C.byref(st["tc_plan"]), C.byref(self.rot_plan(out.device)), srcs, rws,
-                                                  dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride, g_ws.data_ptr(),
-                                                  xp_ws.data_ptr(), chunk, E, out.data_ptr(), L.ptr(out_index),
-                                                  L.stream_ptr(out.device))
+            if use_rot16:
+                nt = chunk // self.ROT_TILE
+                xp_ws = workspace("xp", nt * self.rot16_tile_stride, out.device)
+                sx_ws = workspace("sx", nt * self.rot16_n_blocks * self.ROT_TILE, out.device)
+                rc = L.load().hgb_msgpack_rot16_forward(C.byref(st["tc_plan"]), C.byref(self.rot16_plan(out.device)), srcs, rws,
+                                                        dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride,
+                                                        g_ws.data_ptr(), xp_ws.data_ptr(), sx_ws.data_ptr(),
+                                                        st["r16_wbuf"].data_ptr(), self.rot16_w_words, st["r16_inv"].data_ptr(),
+                                                        self.rot16_n_images, chunk, E, out.data_ptr(), L.ptr(out_index),
+                                                        ROT16_FLAGS, L.stream_ptr(out.device))
+            else:
+                xp_ws = workspace("xp", (chunk // self.ROT_TILE) * self.rot_tile_stride, out.device)
+                rc = L.load().hgb_msgpack_rot_forward(C.byref(st["tc_plan"]), C.byref(self.rot_plan(out.device)), srcs, rws,
+                                                      dw.data_ptr(), L.f32c(rbf).data_ptr(), w3o, nch, w3i, gstride, g_ws.data_ptr(),
+                                                      xp_ws.data_ptr(), chunk, E, out.data_ptr(), L.ptr(out_index),
+                                                      L.stream_ptr(out.device))
         elif use_tc and backend == "tcg":
             nb = len(self.branches)
             gstride = (max(self.n_channels) + 3) // 4 * 4
@@ -1393,7 +1586,7 @@ class MessagePackOp:
             rc = L.load().hgb_msgpack_forward(C.byref(st["plan"]), srcs, rws, L.f32c(sh).data_ptr(), L.f32c(rbf).data_ptr(),
                                               int(n_edges), out.data_ptr(), L.ptr(out_index), L.stream_ptr(out.device))
         if use_rot and seg_out is not None:
-            L.check(rc, "hgb_msgpack_rot_forward")
+            L.check(rc, "hgb_msgpack_rot16_forward" if use_rot16 else "hgb_msgpack_rot_forward")
             seg_ptr, seg_order = segments_for(seg_index, seg_out.shape[0])
             rc = L.load().hgb_segment_sum(out.data_ptr(), self.irreps_out.dim, seg_ptr.data_ptr(), seg_order.data_ptr(),
                                           seg_out.shape[0], seg_out.data_ptr(), L.stream_ptr(seg_out.device))

@@ -206,6 +206,23 @@ int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_pla
                             int32_t gstride, float* g_ws, float* xp_ws, int64_t chunk_edges, int64_t n_edges,
                             float* out, const int64_t* out_index, void* stream);
 
+/* The same fused MessagePackBlock (hamgnn/nn/message_passing.py:26-231) through the rotated frame with fp16 x 2 split
+ * operands (csrc/msgpack_rot16_kernel.cuh): every operand a = hi + lo, hi = fp16(a s), lo = fp16(a s - hi), s a power of
+ * two per packed image / per (edge, input block) / per (edge, step) row, three kind::f16 MMAs (K = 16 per instruction
+ * instead of K = 8 for kind::tf32) accumulate lo.hi + hi.lo + hi.hi in fp32.  rot_host: the fp16 program -- block kpad in
+ * channels (multiple of 16), block xoff / step a_off, w_off, lf_off / tile_stride in 32-bit WORDS, step kpad = words per
+ * operand row, step pad = input block, step pad2 = W image | L' image << 16 (indices into img_inv).  wbuf16: the packed
+ * fp16 images (wbuf16_words 32-bit words), img_inv[n_images]: inverse scale per image.  xp_ws: ceil(chunk / 128) *
+ * tile_stride words; sx_ws: ceil(chunk / 128) * n_blocks * 128 floats (inverse row scales written by the rotate-pack
+ * kernel).  flags bit 0: debug, swap the two halves of every packed TMEM word.  Other arguments as
+ * hgb_msgpack_rot_forward. */
+int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_plan* rot_host, const float* const* src_host,
+                              const int64_t* const* src_rows_host, const float* dw, const float* rbf,
+                              const int32_t* w3_off_host, const int32_t* nch_host, const int32_t* w3img_off_host,
+                              int32_t gstride, float* g_ws, float* xp_ws, float* sx_ws, const float* wbuf16,
+                              int64_t wbuf16_words, const float* img_inv, int32_t n_images, int64_t chunk_edges,
+                              int64_t n_edges, float* out, const int64_t* out_index, int32_t flags, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * f4: graph construction on the device.  hgb_neighbor_list replaces neighbor_list_and_relative_vec
  * (hamgnn/models/base_model.py:87-178: ASE primitive_neighbor_list on the CPU with per-atom cutoffs) for one crystal:

@@ -520,3 +520,139 @@ def emulate_msgpack_rot2(op: MessagePackOp, wbuf: torch.Tensor, sources, rows, v
         CP[:, ps.out_col0:ps.out_col0 + ps.ncols] = acc
     assert seen.all()
     return emulate_unrotate(op, CP, Dw, seg_ptr, seg_order)
+
+
+# ------------------------------------------------------------------------------------------------ rotated frame, fp16 x 2 split
+def _pow2_scale(amax: torch.Tensor, shift: int):
+    """pow2_scale of msgpack_rot16_kernel.cuh: s = 2^(141 - E - shift), E = biased fp32 exponent of amax (s = 1 for E = 0)."""
+    E = (amax.float().view(torch.int32) >> 23) & 0xff
+    sb = torch.where(E == 0, torch.full_like(E, 127), (127 + 141 - E - shift).clamp(1, 253))
+    return torch.ldexp(torch.ones_like(amax, dtype=torch.float64), (sb - 127)), torch.ldexp(torch.ones_like(amax, dtype=torch.float64), (127 - sb))
+
+
+def _split16(v: torch.Tensor):
+    hi = v.float().to(torch.float16)
+    lo = (v.float() - hi.float()).to(torch.float16)
+    return hi.double(), lo.double()
+
+
+def _mm3(ah, al, bh, bl):
+    """lo.hi + hi.lo + hi.hi, what the three kind::f16 MMAs accumulate (the products are exact in fp32)."""
+    return al @ bh + ah @ bl + ah @ bh
+
+
+def _decode_image16(buf16: torch.Tensor, word0: int, N: int, kw: int):
+    """(hi, lo) dense [2 kw channels, N] from a packed fp16 image of kw word-columns starting at 32-bit word `word0`."""
+    k = torch.arange(2 * kw)[:, None]
+    n = torch.arange(N)[None, :]
+    kwd = k // 2
+    h = 2 * (word0 + (kwd // 4) * (N * 4) + n * 4 + (kwd % 4)) + (k % 2)
+    return buf16[h].double(), buf16[h + 2 * N * kw].double()
+
+
+def emulate_rotate_pack16(op: MessagePackOp, sources, rows, Dw: torch.Tensor):
+    """rotate_pack16_kernel: per (edge, block) a power-of-two scale from the row maximum of the UNROTATED block (bound
+    sqrt(d1) < 4 on the rotation), then x' s split into fp16 hi / lo, two channels per word.  Returns the halfword buffer
+    [n_tiles, 2 tile_stride] and sx [n_tiles, n_blocks, 128]."""
+    T, KC = op.ROT_TILE, op.ROT_KC
+    E = Dw.shape[0]
+    nt = (E + T - 1) // T
+    XP = torch.zeros(nt, 2 * op.rot16_tile_stride, dtype=torch.float16)
+    SX = torch.ones(nt, op.rot16_n_blocks, T, dtype=torch.float64)
+    gathered = [s if r is None else s[r] for s, r in zip(sources, rows)]
+    zz = torch.arange(E)
+    tile, zl = zz // T, zz % T
+    for bi in range(op.rot16_n_blocks):
+        b = op.rot16_blocks_c[bi]
+        d1 = 2 * b.l1 + 1
+        K = b.nsrc * b.mul
+        kw = b.kpad // 2
+        x = torch.cat([gathered[b.src0 + s][:, b.in_off:b.in_off + b.mul * d1] for s in range(b.nsrc)], dim=1).reshape(E, K, d1)
+        s, inv = _pow2_scale(x.abs().amax(dim=(1, 2)), 0 if b.l1 == 0 else 2)
+        SX[tile, bi, zl] = inv
+        Dl = Dw[:, op.rot_doff[b.l1]:op.rot_doff[b.l1] + d1 * d1].reshape(E, d1, d1)
+        xr = torch.einsum("zmi,zui->zum", Dl, x * s[:, None, None])
+        assert float(xr.abs().max()) < 32768.0
+        hi, lo = _split16(xr)
+        for m in range(d1):
+            base = b.xoff + m * 2 * kw * T
+            for u in range(K):
+                w = u // 2
+                c, wl = w // KC, w % KC
+                kc = min(KC, kw - c * KC)
+                word = base + c * 2 * KC * T + (wl // 4) * (T * 4) + zl * 4 + (wl % 4)
+                XP[tile, 2 * word + (u % 2)] = hi[:, u, m].to(torch.float16)
+                XP[tile, 2 * (word + kc * T) + (u % 2)] = lo[:, u, m].to(torch.float16)
+    return XP, SX
+
+
+def _decode_a16(XP, a_off, kw, E, T, KC):
+    zz = torch.arange(E)
+    tile, zl = zz // T, zz % T
+    hs, ls = [], []
+    for u in range(2 * kw):
+        w = u // 2
+        c, wl = w // KC, w % KC
+        kc = min(KC, kw - c * KC)
+        word = a_off + c * 2 * KC * T + (wl // 4) * (T * 4) + zl * 4 + (wl % 4)
+        hs.append(XP[tile, 2 * word + (u % 2)].double())
+        ls.append(XP[tile, 2 * (word + kc * T) + (u % 2)].double())
+    return torch.stack(hs, dim=1), torch.stack(ls, dim=1)
+
+
+def emulate_msgpack_rot16(op: MessagePackOp, st: dict, sources, rows, vec, rbf, out_rows=None, n_out=None):
+    """Mirrors wigner -> rotate_pack16 -> radial gate -> msgpack_rot16_kernel from the rot16 tables, the packed fp16 images
+    (st['r16_wbuf'], st['r16_inv'] from MessagePackOp.pack_rot16) and the kernel's scale bookkeeping; fp16 quantisation
+    and the dropped lo.lo products are emulated, sums run in fp64."""
+    from hamgnn_b200 import so3
+    T, KC = op.ROT_TILE, op.ROT_KC
+    E = rbf.shape[0]
+    dt = torch.float64
+    wbuf = st["tc_wbuf"].double().cpu()
+    buf16 = st["r16_wbuf"].cpu()
+    inv_img = st["r16_inv"].double().cpu()
+    D = op.irreps_out.dim
+    Dw = torch.from_numpy(emulate_wigner(np.asarray(vec), op)).to(dt)
+    XP, SX = emulate_rotate_pack16(op, sources, rows, Dw)
+    zz = torch.arange(E)
+    tile, zl = zz // T, zz % T
+    act = so3.normalize2mom_const("silu")
+    g = []
+    for b in range(len(op.branches)):
+        w1 = wbuf[op.tc_fc1_off[b]:op.tc_fc1_off[b] + op.rbf_dim * op.h1].view(op.rbf_dim, op.h1)
+        w2 = wbuf[op.tc_fc2_off[b]:op.tc_fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
+        w3 = wbuf[op.tc_w3_off[b]:op.tc_w3_off[b] + op.h2 * op.n_channels[b]].view(op.h2, op.n_channels[b])
+        g.append(_silu(_silu(rbf @ w1) * act @ w2) * act @ w3)
+    msg = torch.zeros(E, D, dtype=dt)
+    for t in range(len(op.irreps_out)):
+        ty = op.tc_types_c[t]
+        d3, mp = 2 * ty.l + 1, ty.mpad
+        Cacc = torch.zeros(E, d3, mp, dtype=dt)
+        for si in range(op.rot16_step_begin[t], op.rot16_step_begin[t + 1]):
+            s_ = op.rot16_steps_c[si]
+            kw = s_.kpad
+            wimg, limg = s_.pad2 & 0xffff, (s_.pad2 >> 16) & 0xffff
+            ah, al = _decode_a16(XP, s_.a_off, kw, E, T, KC)
+            wh, wl = [], []
+            for c, w0 in enumerate(range(0, kw, KC)):
+                h_, l_ = _decode_image16(buf16, s_.w_off + 2 * mp * KC * c, mp, min(KC, kw - w0))
+                wh.append(h_); wl.append(l_)
+            B = _mm3(ah, al, torch.cat(wh, 0), torch.cat(wl, 0))
+            sc = s_.scale * inv_img[wimg] * SX[tile, s_.pad, zl]
+            gv = torch.zeros(E, mp, dtype=dt)
+            if s_.branch >= 0:
+                gv[:, :ty.mul] = g[s_.branch][:, s_.g_off:s_.g_off + ty.mul] * sc[:, None]
+            else:
+                gv[:, :ty.mul] = sc[:, None]
+            P = B * gv
+            ps, pinv = _pow2_scale(P.abs().amax(dim=1), 0)
+            ph, pl = _split16(P * ps[:, None])
+            lh, ll = _decode_image16(buf16, s_.lf_off, mp, mp // 2)
+            S = pl @ lh + ph @ ll + ph @ lh      # GEMM2: (gl.bh) + (bq.bl) + (bq.bh)
+            Cacc[:, s_.m3, :] += S * (pinv * inv_img[limg])[:, None]
+        D3 = Dw[:, op.rot_doff[ty.l]:op.rot_doff[ty.l] + d3 * d3].reshape(E, d3, d3)
+        out = torch.einsum("zmk,zmw->zwk", D3, Cacc[:, :, :ty.mul])
+        msg[:, ty.out_off:ty.out_off + ty.mul * d3] = out.reshape(E, ty.mul * d3)
+    if out_rows is None:
+        return msg
+    return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)

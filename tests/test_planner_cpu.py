@@ -208,6 +208,16 @@ def test_rotated_frame_program_matches_oracle(small):
     with torch.no_grad():
         ref_emb = opre.pair_embedding(dd2)
     assert rel_err(got, ref_emb) < 2e-6
+    # ---- the fp16 x 2 split program (rot16 tables, packed fp16 images with power-of-two scales): same bar
+    st16 = pe.conv_tp.op.pack_rot16(pe.conv_tp.weights())
+    got16 = EM.emulate_msgpack_rot16(pe.conv_tp.op, st16, [h], [None], vec, d["edge_embedding"])
+    assert rel_err(got16, ref_emb) < 2e-6
+    st16 = pb.conv_tp.op.pack_rot16(pb.conv_tp.weights(pb.skip_linear.weight))
+    got16 = EM.emulate_msgpack_rot16(pb.conv_tp.op, st16, [xs, xt, e], [s, r, None], vec, d["edge_embedding"])
+    assert rel_err(got16, ref_pair) < 2e-6
+    st16 = cb.op.pack_rot16(cb.weights())
+    got16 = EM.emulate_msgpack_rot16(cb.op, st16, [x, x, e], [s, r, None], vec, d["edge_embedding"])
+    assert rel_err(got16, ref_msg) < 2e-6
     # ---- the A-stationary regrouping of the same steps (rot2 tables) + the segmented receiver reduction
     got2 = EM.emulate_msgpack_rot2(pe.conv_tp.op, st["tc_wbuf"].double(), [h], [None], vec, d["edge_embedding"])
     assert rel_err(got2, ref_emb) < 2e-6
