@@ -1,0 +1,299 @@
+// Edge-aligned fused MessagePackBlock, variant with L' on the fp32 FMA pipes ("rotf").  Included by msgpack_tcg.cu after
+// msgpack_rot_kernel.cuh: same step tables, same packed operands, same rotate-pack / radial-gate pre-passes, same epilogue.
+//
+// Why (profiles/README.md, r05): in msgpack_rot_kernel a step of a slot with multiplicity <= 32 takes 3 100 - 4 700 cycles per
+// CTA although its tensor-core work is ~100 cycles: the gate / accumulate warps execute a ~350-instruction serial chain per step
+// (wait B -> tcgen05.ld -> gate -> tf32 split -> 2 x tcgen05.st -> fence -> arrive -> [GEMM2: 3 MMAs per 8 channels] ->
+// wait S -> tcgen05.ld -> add) at ~8 cycles per instruction, and everything that lengthens that chain (fp16 packing: +34 %,
+// deeper gate prefetch with spills: +10 % per level) lengthens the kernel by the same factor.  For these slots the second
+// contraction C'_{m3} += (B.g) L'_p is tiny (mul^2 <= 1 024 FMAs per edge and step), so it runs here on the FMA pipes straight
+// from the registers that hold the gated product: no tf32 split, no write-back to TMEM, no GEMM2 issue / commit / wait, no S
+// round trip.  L'_p is the un-split fp32 row-major [mpad][mpad] image (hgb_rot_step_t.pad2) in a 4-deep shared-memory ring,
+// read as warp-broadcast float4.  With GEMM2 gone TMEM holds FOUR GEMM1 accumulators (B0..B3), so the GEMM1 warp runs up to
+// three steps ahead of the gate warps.  fp32 accuracy: GEMM1 as before (3xTF32, chains <= 48 MMAs), everything after it is
+// plain fp32 FMA (better than the split path).
+//
+// warps 0-3 gate + L' + accumulate (thread = edge = TMEM lane), 4 GEMM1 issuer, 5 TMA A chunks, 6 TMA W chunks,
+// 7 TMA L' images + gate L2 prefetch: 256 threads, 2 CTAs / SM (128 registers per thread).
+#pragma once
+
+namespace rotf {
+using namespace tcmsg;
+using rot::TILE;
+using rot::KC;
+using rot::wait_a;
+using rot::warp_wait_a;
+using rot::arrive_a;
+using rot::expect_tx_a;
+using rot::bulk_g2s_a;
+using rot::commit_a;
+using rot::elect_one;
+using rot::bulk_prefetch_l2;
+using rot::tmem_alloc_dyn;
+using rot::tmem_dealloc_dyn;
+using rot::tmem_st1;
+
+// acc[0 .. 4 MC) += sum_{w < mul} p[w] L'[w][0 .. 4 MC): rows leave by a branch (the executed work follows the multiplicity),
+// L' rows are warp-broadcast float4 loads from shared memory
+template <int RW, int MC>
+__device__ __forceinline__ void fma_rows(float (&acc)[RW], const float (&p)[RW], const float4* __restrict__ Ls, int rq, int mul) {
+#pragma unroll
+  for (int w = 0; w < RW; ++w) {
+    if (w >= mul) break;   // warp-uniform
+    const float pw = p[w];
+#pragma unroll
+    for (int q = 0; q < MC; ++q) {
+      const float4 l = Ls[w * rq + q];
+      acc[4 * q + 0] = fmaf(pw, l.x, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(pw, l.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(pw, l.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(pw, l.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+constexpr int NTHRF = 256;
+constexpr int NB = 4;    // GEMM1 accumulators in flight
+constexpr int NLB = 4;   // L' buffers in flight
+
+template <int RW, int NST>
+__global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_constant__ rot::RotArgs a) {
+  constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
+  constexpr int NBAR = 2 * NST + 2 * NLB + 2 * NB;
+  extern __shared__ __align__(128) float smem[];
+  // barriers: full[NST] | empty[NST] | lfull[NLB] | lfree[NLB] | bfull[NB] | bfree[NB]
+  __shared__ uint64_t bars[NBAR];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar0 = tc::smem_u32(bars);
+  const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_LFREE = B_LFULL + 8 * NLB,
+                 B_BFULL = B_LFREE + 8 * NLB, B_BFREE = B_BFULL + 8 * NB;
+  const uint32_t stage0 = tc::smem_u32(smem);
+  float* const lsm = smem + NST * STG;                           // NLB x RW^2 floats
+  const uint32_t sl0 = stage0 + (uint32_t)(NST * STG) * 4u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x / a.n_slots;
+  const int t = a.slot[blockIdx.x - tile * a.n_slots];
+  const hgb_type_t ty = a.plan.types[t];
+  const int d3 = 2 * ty.l + 1, mp = ty.mpad, mul = ty.mul;
+  const int sb = a.step_begin[t], se = a.step_begin[t + 1];
+  // TMEM columns: B0 | B1 | B2 | B3 | C' (d3 x mul, exact stride)
+  const uint32_t TC = (uint32_t)(NB * mp);
+  uint32_t ncols = 32;
+  while (ncols < TC + (uint32_t)(d3 * mul)) ncols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NBAR; ++i) {
+      const bool four = (i >= 2 * NST + NLB && i < 2 * NST + 2 * NLB) || i >= 2 * NST + 2 * NLB + NB;   // lfree, bfree: one arrival per gate warp
+      tc::mbar_init(&bars[i], four ? 4 : (i < NST ? 2 : 1));                                           // full: A + W producers
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const float* __restrict__ wbuf = a.plan.wbuf;
+  const uint32_t idesc = tc::idesc_tf32_m128(mp);
+  const uint32_t dhi = tc::smem_desc_hi(128);
+  const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
+  const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
+
+  if (warp >= 5) {
+    // =============================== TMA producers: A chunks | W chunks | L' images + gate prefetch ===============================
+    if (lane == 0) {
+      const float* xt = a.xp + (size_t)tile * a.tile_stride;
+      if (warp == 7) {
+        constexpr int GPF = 4;
+        const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+        const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+        auto prefetch_gate = [&](int sj) {
+          if (sj < se) {
+            const hgb_rot_step_t* ps = a.steps + sj;
+            if (ps->branch >= 0) bulk_prefetch_l2(gt + (size_t)ps->branch * g_bstride + (size_t)ps->g_off * TILE, (uint32_t)(mul * TILE) * 4u);
+          }
+        };
+        for (int j = 0; j < GPF; ++j) prefetch_gate(sb + j);
+        int n = 0;
+        const uint32_t lbytes = (uint32_t)(mp * mp) * 4u;
+        for (int si = sb; si < se; ++si, ++n) {
+          const hgb_rot_step_t st = a.steps[si];
+          prefetch_gate(si + GPF);
+          const int lb = n % NLB;
+          if (n >= NLB) wait_a(B_LFREE + 8 * lb, (uint32_t)(((n / NLB) - 1) & 1));   // the gate warps have read L'(n - NLB)
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(sl0 + (uint32_t)(lb * RW * RW) * 4u, wbuf + st.pad2, lbytes, B_LFULL + 8 * lb);
+        }
+      } else {
+        const bool isA = warp == 5;
+        int c_all = 0;
+        for (int si = sb; si < se; ++si) {
+          const hgb_rot_step_t st = a.steps[si];
+          const int kpad = st.kpad;
+          for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
+            const int kc = min(KC, kpad - u0), s = c_all % NST;
+            if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
+            const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
+            const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
+            if (isA) {
+              expect_tx_a(B_FULL + 8 * s, ab);
+              bulk_g2s_a(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
+            } else {
+              expect_tx_a(B_FULL + 8 * s, wb);
+              bulk_g2s_a(sa + 2 * KC * TILE * 4, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // =============================== GEMM1 issuer ===============================
+    int n = 0, c_all = 0;
+    int kpad = (sb < se) ? a.steps[sb].kpad : 0;
+    for (int si = sb; si < se; ++si, ++n) {
+      const int kpad_next = (si + 1 < se) ? a.steps[si + 1].kpad : 0;
+      const int b = n % NB;
+      if (n >= NB) warp_wait_a(B_BFREE + 8 * b, (uint32_t)(((n / NB) - 1) & 1));   // the gate warps have read B(n - NB)
+      const uint32_t dcol = tmem + (uint32_t)(b * mp);
+      for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
+        const int kc = min(KC, kpad - u0), s = c_all % NST;
+        warp_wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
+        tc::fence_after_sync();
+        if (elect_one()) {
+          const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
+          const uint32_t ah = tc::smem_desc_lo(sa, lbo_a), al = ah + (((uint32_t)kc * TILE * 4) >> 4);
+          const uint32_t wh = tc::smem_desc_lo(sa + 2 * KC * TILE * 4, lbo_n), wl = wh + (((uint32_t)mp * kc * 4) >> 4);
+          for (int k8 = 0; k8 < (kc >> 3); ++k8) {
+            const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
+            const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl_ = tc::desc64(wl + k8 * bstep, dhi);
+            tc::mma_tf32(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+            tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
+            tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+          }
+          commit_a(B_EMPTY + 8 * s);
+          if (u0 + KC >= kpad) commit_a(B_BFULL + 8 * b);
+        }
+        __syncwarp();
+      }
+      kpad = kpad_next;
+    }
+  } else {
+    // =============================== gate, L', accumulate, final rotation (thread = edge = TMEM lane) ===============================
+    const int64_t el = (int64_t)tile * TILE + tid;
+    const bool live = el < a.n_chunk;
+    const int64_t e = a.e_lo + el;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);
+    const int mc = (mul + 3) >> 2;   // output quads that carry data
+    float gv[RW], acc[RW];
+#pragma unroll
+    for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
+    float gA = 0.f, gB = 0.f;
+    uint32_t cmask = 0;
+    const uint4* steps4 = reinterpret_cast<const uint4*>(a.steps);
+    auto load_gate = [&](const uint4& w0, const uint4& w1) {
+      const float sc = __uint_as_float(w1.x);
+      const int br = (int)(int8_t)(w1.y >> 24);
+      gA = (br < 0) ? 0.f : sc;
+      gB = (br < 0) ? sc : 0.f;
+      const float* gp = grow + (size_t)max(br, 0) * g_bstride + (size_t)((br < 0) ? 0 : (int)w0.w) * TILE;
+#pragma unroll
+      for (int j = 0; j < RW; ++j)
+        if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
+    };
+    int n = 0;
+    uint32_t cur_fm = 0;
+    if (se > sb) {
+      const uint4 w0 = __ldg(steps4 + 2 * sb), w1 = __ldg(steps4 + 2 * sb + 1);
+      cur_fm = w1.z;
+      load_gate(w0, w1);
+    }
+    for (int si = sb; si < se; ++si, ++n) {
+      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+      const bool more = si + 1 < se;
+      if (more) { n0 = __ldg(steps4 + 2 * (si + 1)); n1 = __ldg(steps4 + 2 * (si + 1) + 1); }
+      const int m3 = (int)(cur_fm & 0xff), flags = (int)((cur_fm >> 8) & 0xff);
+      cmask |= 1u << m3;
+      const int b = n % NB, lb = n % NLB;
+      // ---- B(n) -> registers, gated
+      warp_wait_a(B_BFULL + 8 * b, (uint32_t)((n / NB) & 1));
+      tc::fence_after_sync();
+      const uint32_t bq = tmem + lane_base + (uint32_t)(b * mp);
+      float p[RW];
+#pragma unroll
+      for (int c0 = 0; c0 < RW; c0 += 8) {
+        if (c0 < mul) {   // warp-uniform
+          uint32_t rb[8];
+          tc::tmem_ld8(bq + c0, rb);
+          tc::tmem_ld_wait8(rb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[c0 + j] = __uint_as_float(rb[j]) * fmaf(gv[c0 + j], gA, gB);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[c0 + j] = 0.f;
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive_a(B_BFREE + 8 * b);   // GEMM1(n + NB) may overwrite the accumulator
+      if (more) load_gate(n0, n1);                // next step's gate values travel while the FMA block runs
+      // ---- acc[w'] += sum_w p[w] L'[w][w']
+      wait_a(B_LFULL + 8 * lb, (uint32_t)((n / NLB) & 1));   // every lane observes the phase: it reads the TMA-written bytes itself
+      const float4* Ls = reinterpret_cast<const float4*>(lsm + lb * RW * RW);
+      const int rq = mp >> 2;   // float4 per L' row
+      if (RW == 16) {
+        switch (mc) {
+          case 1: fma_rows<RW, 1>(acc, p, Ls, rq, mul); break;
+          case 2: fma_rows<RW, 2>(acc, p, Ls, rq, mul); break;
+          case 3: fma_rows<RW, 3>(acc, p, Ls, rq, mul); break;
+          default: fma_rows<RW, 4>(acc, p, Ls, rq, mul); break;
+        }
+      } else {
+        if (mc <= 6) fma_rows<RW, (RW >= 24 ? 6 : RW / 4)>(acc, p, Ls, rq, mul);
+        else fma_rows<RW, RW / 4>(acc, p, Ls, rq, mul);
+      }
+      __syncwarp();
+      if (lane == 0) arrive_a(B_LFREE + 8 * lb);
+      // ---- end of an m3 group: the registers go to C'[m3]
+      if (flags & 4) {
+        const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul);
+#pragma unroll
+        for (int j = 0; j < RW; ++j) {
+          if (j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));   // warp-uniform predicate
+          acc[j] = 0.f;
+        }
+        tc::tmem_st_wait();
+      }
+      cur_fm = n1.z;
+    }
+    tc::fence_before_sync();
+    tc::fence_after_sync();
+    {
+      const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
+      float* op = a.out + (live ? orow : 0) * a.plan.out_dim + ty.out_off;
+      const float* Dz = a.dw + (live ? e : 0) * a.dstride + a.doff[ty.l];
+      const uint32_t tc0 = tmem + lane_base + TC;
+      const bool atomic = a.out_index != nullptr;
+      switch (ty.l) {
+        case 0: rot::rot_epilogue<0>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 1: rot::rot_epilogue<1>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 2: rot::rot_epilogue<2>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 3: rot::rot_epilogue<3>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 4: rot::rot_epilogue<4>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 5: rot::rot_epilogue<5>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        default: rot::rot_epilogue<6>(tc0, mul, cmask, Dz, op, live, atomic); break;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
+}
+
+template <int RW, int NST>
+constexpr size_t rotf_smem_bytes() { return (size_t)(NST * (2 * KC * TILE + 2 * RW * KC) + NLB * RW * RW) * sizeof(float); }
+
+}  // namespace rotf

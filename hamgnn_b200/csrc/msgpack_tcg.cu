@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "msgpack_tcr_kernel.cuh"
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
+#include "msgpack_rotf_kernel.cuh"
 #include "msgpack_rot16_kernel.cuh"
 #include "msgpack_rot2_kernel.cuh"
 
@@ -694,6 +695,18 @@ int launch_rot_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
 }
 }  // namespace
 
+namespace {
+template <int RW, int NST>
+int launch_rotf_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
+  constexpr size_t smem = rotf::rotf_smem_bytes<RW, NST>();
+  static_assert(smem <= 113 * 1024, "msgpack_rotf_kernel shared memory (2 CTAs / SM)");
+  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rotf::msgpack_rotf_kernel<RW, NST><<<(unsigned)(n_tiles * ra.n_slots), rotf::NTHRF, smem, st>>>(ra);
+  HGB_LAUNCH_OK("msgpack_rotf_kernel");
+  return 0;
+}
+}  // namespace
+
 extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_rot_plan* rp, const float* const* src,
                                        const int64_t* const* src_rows, const float* dw, const float* rbf,
                                        const int32_t* w3_off, const int32_t* nch, const int32_t* w3img_off, int32_t gstride,
@@ -730,12 +743,22 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
   }
   int klass[32], order[32];
   double cost[32];
+  // slot classes 16 / 32 run msgpack_rotf_kernel (L' on the FMA pipes, four GEMM1 accumulators in TMEM) when every slot of the
+  // class fits its 256 TMEM columns and every step carries the un-split fp32 L' image; HGB_ROT_FMA = bit mask of the classes
+  // (default 3; 0 = msgpack_rot_kernel everywhere)
+  const int fma_env = getenv("HGB_ROT_FMA") ? atoi(getenv("HGB_ROT_FMA")) : 3;
+  bool fma_ok[3] = {(fma_env & 1) != 0, (fma_env & 2) != 0, false};
   for (int t = 0; t < plan->n_types; ++t) {
     const hgb_type_t& ty = plan->types_host[t];
     const int d3 = 2 * ty.l + 1;
     HGB_CHECK_ARG(ty.l >= 0 && ty.l <= rp->lmax && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
                   "hgb_msgpack_rot_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
     klass[t] = ty.mpad <= 16 ? 0 : (ty.mpad <= 32 ? 1 : 2);
+    if (klass[t] < 2) {
+      if (rotf::NB * ty.mpad + d3 * ty.mul > 256 || ty.mpad != (klass[t] == 0 ? 16 : 32)) fma_ok[klass[t]] = false;
+      for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si)
+        if (rp->steps_host[si].pad2 <= 0 || rp->steps_host[si].pad2 % 4 != 0) fma_ok[klass[t]] = false;
+    }
     {
       const int dbl = (klass[t] == 1) ? 0 : 1;   // TMEM: B0 B1 GL (GL) S (S) + d3 x mul
       HGB_CHECK_ARG((4 + 2 * dbl) * ty.mpad + d3 * ty.mul <= 512, "hgb_msgpack_rot_forward: slot %d needs more than 512 TMEM columns", t);
@@ -817,8 +840,8 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
-      if (k == 0) rc = launch_rot_class<16, 3>(cls[k], n_tiles, st);
-      else if (k == 1) rc = launch_rot_class<32, 2>(cls[k], n_tiles, st);
+      if (k == 0) rc = fma_ok[0] ? launch_rotf_class<16, 3>(cls[k], n_tiles, st) : launch_rot_class<16, 3>(cls[k], n_tiles, st);
+      else if (k == 1) rc = fma_ok[1] ? launch_rotf_class<32, 2>(cls[k], n_tiles, st) : launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }

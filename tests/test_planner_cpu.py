@@ -208,6 +208,16 @@ def test_rotated_frame_program_matches_oracle(small):
     with torch.no_grad():
         ref_emb = opre.pair_embedding(dd2)
     assert rel_err(got, ref_emb) < 2e-6
+    # ---- msgpack_rotf_kernel reads L' as the un-split fp32 row-major image at hgb_rot_step_t.pad2: same matrix as the (hi | lo) image
+    for op_, st_ in ((pb.conv_tp.op, pb.conv_tp.op.pack_tc(pb.conv_tp.weights(pb.skip_linear.weight))), (cb.op, cb.op.pack_tc(cb.weights()))):
+        wb = st_["tc_wbuf"].double()
+        for t in range(len(op_.irreps_out)):
+            mp = op_.tc_types_c[t].mpad
+            for si in range(op_.rot_step_begin[t], op_.rot_step_begin[t + 1]):
+                s_ = op_.rot_steps_c[si]
+                assert s_.pad2 > 0 and s_.pad2 % 4 == 0
+                plain = wb[s_.pad2:s_.pad2 + mp * mp].view(mp, mp)
+                assert torch.allclose(plain, EM._decode_image(wb, s_.lf_off, mp, mp), rtol=0, atol=1e-6 * float(plain.abs().max()) + 1e-30)
     # ---- the fp16 x 2 split program (rot16 tables, packed fp16 images with power-of-two scales): same bar
     st16 = pe.conv_tp.op.pack_rot16(pe.conv_tp.weights())
     got16 = EM.emulate_msgpack_rot16(pe.conv_tp.op, st16, [h], [None], vec, d["edge_embedding"])
