@@ -13,8 +13,13 @@
 // three steps ahead of the gate warps.  fp32 accuracy: GEMM1 as before (3xTF32, chains <= 48 MMAs), everything after it is
 // plain fp32 FMA (better than the split path).
 //
-// warps 0-3 gate + L' + accumulate (thread = edge = TMEM lane), 4 GEMM1 issuer, 5 TMA A chunks, 6 TMA W chunks,
+// NWG = 1: warps 0-3 gate + L' + accumulate (thread = edge = TMEM lane), 4 GEMM1 issuer, 5 TMA A chunks, 6 TMA W chunks,
 // 7 TMA L' images + gate L2 prefetch: 256 threads, 2 CTAs / SM (128 registers per thread).
+// NWG = 2: TWO gate warpgroups (warps 0-3 take the even steps, warps 4-7 the odd steps; warp w works on TMEM lane quadrant
+// w % 4), issuer / producers are warps 8-11: 384 threads, 2 CTAs / SM.  ncu of NWG = 1 (profiles/r05d): the gate warps execute
+// ~290 instructions per step at ~8 cycles per instruction (two gate warps per scheduler: no latency hiding) and wait on their
+// barriers only ~25 % of the time -- the step rate is the gate warps' own instruction stream, so the steps are dealt to twice
+// as many warps.  Each warpgroup keeps its own partial sums and its own C' region; the epilogue adds the two regions.
 #pragma once
 
 namespace rotf {
@@ -52,18 +57,63 @@ __device__ __forceinline__ void fma_rows(float (&acc)[RW], const float (&p)[RW],
   }
 }
 
-constexpr int NTHRF = 256;
 constexpr int NB = 4;    // GEMM1 accumulators in flight
 constexpr int NLB = 4;   // L' buffers in flight
 
-template <int RW, int NST>
-__global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_constant__ rot::RotArgs a) {
+// C[z][w][k] = sum_m3 D^{l3}_z[m3][k] (C'_A + C'_B)[z][m3][w] for the channel quads c_first, c_first + c_step, ...; C'_X[m3][w] is
+// TMEM column tcX + m3 * mul + w, bit m3 of cmX: region X holds that component (otherwise it counts as zero).
+template <int L3>
+__device__ __forceinline__ void rotf_epilogue(uint32_t tcA, uint32_t tcB, int mul, uint32_t cmA, uint32_t cmB, const float* __restrict__ Dz,
+                                              float* __restrict__ op, bool live, bool atomic, int c_first, int c_step) {
+  constexpr int d3 = 2 * L3 + 1;
+  for (int c0 = c_first; c0 < mul; c0 += c_step) {   // warp-uniform
+    float v[d3][4];
+#pragma unroll
+    for (int m = 0; m < d3; ++m) {
+      uint32_t ca[4], cb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ca[j] = 0u; cb[j] = 0u;
+        if (((cmA >> m) & 1u) && c0 + j < mul) rot::tmem_ld1(tcA + m * mul + c0 + j, ca[j]);
+        if (((cmB >> m) & 1u) && c0 + j < mul) rot::tmem_ld1(tcB + m * mul + c0 + j, cb[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { rot::tmem_ld_wait1(ca[j]); rot::tmem_ld_wait1(cb[j]); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[m][j] = __uint_as_float(ca[j]) + __uint_as_float(cb[j]);
+    }
+    if (!live) continue;
+#pragma unroll
+    for (int k = 0; k < d3; ++k) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < d3; ++m) {
+        const float dmk = (L3 == 0) ? 1.f : __ldg(Dz + m * d3 + k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(dmk, v[m][j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = c0 + j;
+        if (w < mul) {
+          if (atomic) atomicAdd(op + w * d3 + k, acc[j]);
+          else op[w * d3 + k] = acc[j];
+        }
+      }
+    }
+  }
+}
+
+template <int RW, int NST, int NWG>
+__global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const __grid_constant__ rot::RotArgs a) {
+  constexpr int W_MMA = 4 * NWG, W_A = W_MMA + 1, W_W = W_MMA + 2, W_L = W_MMA + 3;
   constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
   constexpr int NBAR = 2 * NST + 2 * NLB + 2 * NB;
   extern __shared__ __align__(128) float smem[];
   // barriers: full[NST] | empty[NST] | lfull[NLB] | lfree[NLB] | bfull[NB] | bfree[NB]
   __shared__ uint64_t bars[NBAR];
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t cm_sh[2];
   const uint32_t bar0 = tc::smem_u32(bars);
   const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_LFREE = B_LFULL + 8 * NLB,
                  B_BFULL = B_LFREE + 8 * NLB, B_BFREE = B_BFULL + 8 * NB;
@@ -77,10 +127,10 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
   const hgb_type_t ty = a.plan.types[t];
   const int d3 = 2 * ty.l + 1, mp = ty.mpad, mul = ty.mul;
   const int sb = a.step_begin[t], se = a.step_begin[t + 1];
-  // TMEM columns: B0 | B1 | B2 | B3 | C' (d3 x mul, exact stride)
+  // TMEM columns: B0 | B1 | B2 | B3 | C' of warpgroup 0 (d3 x mul, exact stride) (| C' of warpgroup 1)
   const uint32_t TC = (uint32_t)(NB * mp);
   uint32_t ncols = 32;
-  while (ncols < TC + (uint32_t)(d3 * mul)) ncols <<= 1;
+  while (ncols < TC + (uint32_t)(NWG * d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
     for (int i = 0; i < NBAR; ++i) {
@@ -89,7 +139,7 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
     }
     tc::mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc_dyn(&tmem_slot, ncols);
+  if (warp == W_MMA) tmem_alloc_dyn(&tmem_slot, ncols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -100,11 +150,11 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
   const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
   const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
 
-  if (warp >= 5) {
+  if (warp > W_MMA) {
     // =============================== TMA producers: A chunks | W chunks | L' images + gate prefetch ===============================
     if (lane == 0) {
       const float* xt = a.xp + (size_t)tile * a.tile_stride;
-      if (warp == 7) {
+      if (warp == W_L) {
         constexpr int GPF = 4;
         const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
         const float* gt = a.g + (size_t)tile * a.gstride * TILE;
@@ -126,7 +176,7 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
           bulk_g2s_a(sl0 + (uint32_t)(lb * RW * RW) * 4u, wbuf + st.pad2, lbytes, B_LFULL + 8 * lb);
         }
       } else {
-        const bool isA = warp == 5;
+        const bool isA = warp == W_A;
         int c_all = 0;
         for (int si = sb; si < se; ++si) {
           const hgb_rot_step_t st = a.steps[si];
@@ -148,7 +198,7 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     // =============================== GEMM1 issuer ===============================
     int n = 0, c_all = 0;
     int kpad = (sb < se) ? a.steps[sb].kpad : 0;
@@ -181,41 +231,53 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
     }
   } else {
     // =============================== gate, L', accumulate, final rotation (thread = edge = TMEM lane) ===============================
-    const int64_t el = (int64_t)tile * TILE + tid;
+    const int wg = warp >> 2, zt = (warp & 3) * 32 + lane;   // warpgroup (its steps: n = wg, wg + NWG, ...), edge inside the tile
+    const int64_t el = (int64_t)tile * TILE + zt;
     const bool live = el < a.n_chunk;
     const int64_t e = a.e_lo + el;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
-    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? tid : 0);
+    const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? zt : 0);
     const int mc = (mul + 3) >> 2;   // output quads that carry data
+    const int nsteps = se - sb;
+    const uint32_t tcw = tmem + lane_base + TC + (uint32_t)(wg * d3 * mul);   // this warpgroup's C'
     float gv[RW], acc[RW];
 #pragma unroll
     for (int j = 0; j < RW; ++j) { gv[j] = 0.f; acc[j] = 0.f; }
     float gA = 0.f, gB = 0.f;
     uint32_t cmask = 0;
-    const uint4* steps4 = reinterpret_cast<const uint4*>(a.steps);
+    const uint4* steps4 = reinterpret_cast<const uint4*>(a.steps) + 2 * sb;
+    // gate values of a step straight into registers (quads past the multiplicity are skipped by a branch); un-gated steps
+    // (branch < 0) use the factor (gA, gB) = (0, scale) instead of (scale, 0) on whatever the registers hold
     auto load_gate = [&](const uint4& w0, const uint4& w1) {
       const float sc = __uint_as_float(w1.x);
       const int br = (int)(int8_t)(w1.y >> 24);
       gA = (br < 0) ? 0.f : sc;
       gB = (br < 0) ? sc : 0.f;
-      const float* gp = grow + (size_t)max(br, 0) * g_bstride + (size_t)((br < 0) ? 0 : (int)w0.w) * TILE;
+      if (br >= 0) {   // warp-uniform
+        const float* gp = grow + (size_t)br * g_bstride + (size_t)(int)w0.w * TILE;
 #pragma unroll
-      for (int j = 0; j < RW; ++j)
-        if (j < mul) gv[j] = __ldg(gp + j * TILE);   // warp-uniform predicate; a warp reads 128 contiguous bytes
+        for (int q = 0; q < RW / 4; ++q) {
+          if (q >= mc) break;
+#pragma unroll
+          for (int j = 4 * q; j < 4 * q + 4; ++j) gv[j] = __ldg(gp + j * TILE);   // columns in [mul, 4 mc) exist (gstride % 4 == 0) and meet B == 0
+        }
+      }
     };
-    int n = 0;
     uint32_t cur_fm = 0;
-    if (se > sb) {
-      const uint4 w0 = __ldg(steps4 + 2 * sb), w1 = __ldg(steps4 + 2 * sb + 1);
+    if (wg < nsteps) {
+      const uint4 w0 = __ldg(steps4 + 2 * wg), w1 = __ldg(steps4 + 2 * wg + 1);
       cur_fm = w1.z;
       load_gate(w0, w1);
     }
-    for (int si = sb; si < se; ++si, ++n) {
+    for (int n = wg; n < nsteps; n += NWG) {
       uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-      const bool more = si + 1 < se;
-      if (more) { n0 = __ldg(steps4 + 2 * (si + 1)); n1 = __ldg(steps4 + 2 * (si + 1) + 1); }
-      const int m3 = (int)(cur_fm & 0xff), flags = (int)((cur_fm >> 8) & 0xff);
+      const bool more = n + NWG < nsteps;
+      if (more) { n0 = __ldg(steps4 + 2 * (n + NWG)); n1 = __ldg(steps4 + 2 * (n + NWG) + 1); }
+      uint32_t fm_other = 0;   // NWG == 2: the step in between belongs to the other warpgroup; it may close this m3 group
+      if (NWG == 2 && n + 1 < nsteps) fm_other = __ldg(reinterpret_cast<const uint32_t*>(steps4 + 2 * (n + 1) + 1) + 2);
+      const int m3 = (int)(cur_fm & 0xff);
+      const bool park = (((cur_fm | fm_other) >> 8) & 4u) != 0;
       cmask |= 1u << m3;
       const int b = n % NB, lb = n % NLB;
       // ---- B(n) -> registers, gated
@@ -225,21 +287,20 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
       float p[RW];
 #pragma unroll
       for (int c0 = 0; c0 < RW; c0 += 8) {
+        uint32_t rb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rb[j] = 0u;
         if (c0 < mul) {   // warp-uniform
-          uint32_t rb[8];
           tc::tmem_ld8(bq + c0, rb);
           tc::tmem_ld_wait8(rb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p[c0 + j] = __uint_as_float(rb[j]) * fmaf(gv[c0 + j], gA, gB);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p[c0 + j] = 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[c0 + j] = __uint_as_float(rb[j]) * fmaf(gv[c0 + j], gA, gB);
       }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) arrive_a(B_BFREE + 8 * b);   // GEMM1(n + NB) may overwrite the accumulator
-      if (more) load_gate(n0, n1);                // next step's gate values travel while the FMA block runs
+      if (more) load_gate(n0, n1);                // the gate values of this warpgroup's next step travel while the FMA block runs
       // ---- acc[w'] += sum_w p[w] L'[w][w']
       wait_a(B_LFULL + 8 * lb, (uint32_t)((n / NLB) & 1));   // every lane observes the phase: it reads the TMA-written bytes itself
       const float4* Ls = reinterpret_cast<const float4*>(lsm + lb * RW * RW);
@@ -257,9 +318,9 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
       }
       __syncwarp();
       if (lane == 0) arrive_a(B_LFREE + 8 * lb);
-      // ---- end of an m3 group: the registers go to C'[m3]
-      if (flags & 4) {
-        const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul);
+      // ---- this warpgroup's last step of an m3 group: the registers go to its C'[m3]
+      if (park) {
+        const uint32_t cc = tcw + (uint32_t)(m3 * mul);
 #pragma unroll
         for (int j = 0; j < RW; ++j) {
           if (j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));   // warp-uniform predicate
@@ -270,27 +331,34 @@ __global__ void __launch_bounds__(NTHRF, 2) msgpack_rotf_kernel(const __grid_con
       cur_fm = n1.z;
     }
     tc::fence_before_sync();
+    uint32_t cmA = cmask, cmB = 0;
+    if (NWG == 2) {
+      if ((warp & 3) == 0 && lane == 0) cm_sh[wg] = cmask;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // both warpgroups have parked their sums
+      cmA = cm_sh[0]; cmB = cm_sh[1];
+    }
     tc::fence_after_sync();
     {
       const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
       float* op = a.out + (live ? orow : 0) * a.plan.out_dim + ty.out_off;
       const float* Dz = a.dw + (live ? e : 0) * a.dstride + a.doff[ty.l];
-      const uint32_t tc0 = tmem + lane_base + TC;
+      const uint32_t tcA = tmem + lane_base + TC, tcB = tcA + (uint32_t)(d3 * mul);
       const bool atomic = a.out_index != nullptr;
+      const int cf = 4 * wg, cs = 4 * NWG;   // the warpgroups share the channel quads of the final rotation
       switch (ty.l) {
-        case 0: rot::rot_epilogue<0>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        case 1: rot::rot_epilogue<1>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        case 2: rot::rot_epilogue<2>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        case 3: rot::rot_epilogue<3>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        case 4: rot::rot_epilogue<4>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        case 5: rot::rot_epilogue<5>(tc0, mul, cmask, Dz, op, live, atomic); break;
-        default: rot::rot_epilogue<6>(tc0, mul, cmask, Dz, op, live, atomic); break;
+        case 0: rotf_epilogue<0>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        case 1: rotf_epilogue<1>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        case 2: rotf_epilogue<2>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        case 3: rotf_epilogue<3>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        case 4: rotf_epilogue<4>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        case 5: rotf_epilogue<5>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
+        default: rotf_epilogue<6>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
+  if (warp == W_MMA) tmem_dealloc_dyn(tmem, ncols);
 }
 
 template <int RW, int NST>

@@ -696,12 +696,12 @@ int launch_rot_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
 }  // namespace
 
 namespace {
-template <int RW, int NST>
+template <int RW, int NST, int NWG>
 int launch_rotf_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
   constexpr size_t smem = rotf::rotf_smem_bytes<RW, NST>();
   static_assert(smem <= 113 * 1024, "msgpack_rotf_kernel shared memory (2 CTAs / SM)");
-  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rotf::msgpack_rotf_kernel<RW, NST><<<(unsigned)(n_tiles * ra.n_slots), rotf::NTHRF, smem, st>>>(ra);
+  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rotf::msgpack_rotf_kernel<RW, NST, NWG><<<(unsigned)(n_tiles * ra.n_slots), 128 * NWG + 128, smem, st>>>(ra);
   HGB_LAUNCH_OK("msgpack_rotf_kernel");
   return 0;
 }
@@ -746,8 +746,9 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
   // slot classes 16 / 32 run msgpack_rotf_kernel (L' on the FMA pipes, four GEMM1 accumulators in TMEM) when every slot of the
   // class fits its 256 TMEM columns and every step carries the un-split fp32 L' image; HGB_ROT_FMA = bit mask of the classes
   // (default 3; 0 = msgpack_rot_kernel everywhere)
-  const int fma_env = getenv("HGB_ROT_FMA") ? atoi(getenv("HGB_ROT_FMA")) : 3;
+  const int fma_env = getenv("HGB_ROT_FMA") ? atoi(getenv("HGB_ROT_FMA")) : 3;   // bit 2 (4): two gate warpgroups for class 16
   bool fma_ok[3] = {(fma_env & 1) != 0, (fma_env & 2) != 0, false};
+  bool fma_wg2 = (fma_env & 4) != 0;
   for (int t = 0; t < plan->n_types; ++t) {
     const hgb_type_t& ty = plan->types_host[t];
     const int d3 = 2 * ty.l + 1;
@@ -756,6 +757,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     klass[t] = ty.mpad <= 16 ? 0 : (ty.mpad <= 32 ? 1 : 2);
     if (klass[t] < 2) {
       if (rotf::NB * ty.mpad + d3 * ty.mul > 256 || ty.mpad != (klass[t] == 0 ? 16 : 32)) fma_ok[klass[t]] = false;
+      if (klass[t] == 0 && rotf::NB * ty.mpad + 2 * d3 * ty.mul > 256) fma_wg2 = false;
       for (int si = rp->step_begin[t]; si < rp->step_begin[t + 1]; ++si)
         if (rp->steps_host[si].pad2 <= 0 || rp->steps_host[si].pad2 % 4 != 0) fma_ok[klass[t]] = false;
     }
@@ -840,8 +842,9 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
-      if (k == 0) rc = fma_ok[0] ? launch_rotf_class<16, 3>(cls[k], n_tiles, st) : launch_rot_class<16, 3>(cls[k], n_tiles, st);
-      else if (k == 1) rc = fma_ok[1] ? launch_rotf_class<32, 2>(cls[k], n_tiles, st) : launch_rot_class<32, 2>(cls[k], n_tiles, st);
+      if (k == 0) rc = !fma_ok[0] ? launch_rot_class<16, 3>(cls[k], n_tiles, st)
+                       : fma_wg2 ? launch_rotf_class<16, 3, 2>(cls[k], n_tiles, st) : launch_rotf_class<16, 3, 1>(cls[k], n_tiles, st);
+      else if (k == 1) rc = fma_ok[1] ? launch_rotf_class<32, 2, 1>(cls[k], n_tiles, st) : launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }

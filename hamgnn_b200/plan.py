@@ -1543,7 +1543,8 @@ class MessagePackOp:
                 out_index = None
             chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
-            g_ws = workspace("gate", nb * chunk * gstride, out.device)   # [nb][tile][gstride][128]
+            # [nb][tile][gstride][128] (+ one quad of columns: msgpack_rotf_kernel loads whole 4-column groups)
+            g_ws = workspace("gate", nb * chunk * gstride + 4 * self.ROT_TILE, out.device)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
             nch = (C.c_int32 * 2)(*(list(self.n_channels) + [0] * (2 - nb)))
             w3i = None
