@@ -414,8 +414,9 @@ def main():
         b_alg_launch = alg["msgpack_rot2"][0] * steps / cnt_d
         roof = {"kernel": ("msgpack_rot2_kernel (A-stationary edge-aligned MessagePackBlock: TMA ring + tcgen05 3xTF32, FMA-pipe L' for multiplicity <= 16)"
                            if dom_name == "msgpack_rot2" else
-                           "msgpack_rot_kernel<16,3> + <32,2> + <64,2> (edge-aligned MessagePackBlock, one launch per slot class and edge chunk, timed "
-                           "together: TMA ring + tcgen05 3xTF32, 2 CTAs / SM)"),
+                           "msgpack_rotf_kernel<16,2,2> (slot class 16: GEMM1 on tcgen05 3xTF32, gate + L' on the fp32 FMA pipes, two gate warpgroups) + "
+                           "msgpack_rot_kernel<32,2> + <64,2> (edge-aligned MessagePackBlock, one launch per slot class and edge chunk, timed "
+                           "together: TMA ring + tcgen05, 2 CTAs / SM)"),
                 "bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                 "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_note,
                 "traffic_over_algorithmic_bytes": (traffic / b_alg_launch) if traffic else None,

@@ -104,9 +104,18 @@ __device__ __forceinline__ void rotf_epilogue(uint32_t tcA, uint32_t tcB, int mu
   }
 }
 
-template <int RW, int NST, int NWG>
-__global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const __grid_constant__ rot::RotArgs a) {
-  constexpr int W_MMA = 4 * NWG, W_A = W_MMA + 1, W_W = W_MMA + 2, W_L = W_MMA + 3;
+template <bool F16> struct ArgsOf { using type = rot::RotArgs; };
+template <> struct ArgsOf<true> { using type = rot16::Rot16Args; };
+
+// F16 = true: GEMM1 on fp16 x 2 split operands (the rot16 packing: rotate_pack16_kernel images with a power-of-two scale per
+// (edge, input block), W images with a scale per image, kind::f16 MMAs with K = 16 per instruction, offsets / kpad in 32-bit
+// words) -- half the tensor-core instructions and half the operand bytes of the tf32 form; the inverse scales are folded
+// into the gate factor.  The step's lf_off is then the offset of the un-split fp32 L' image in plan.wbuf.
+template <int RW, int NST, int NWG, int NMW, bool F16>
+__global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const __grid_constant__ typename ArgsOf<F16>::type a) {
+  // NMW = GEMM1 issuer warps; the CTA always has four non-gate warps: NMW = 1: issuer | A | W | L' + gate prefetch,
+  // NMW = 2: issuer 0 | issuer 1 | A + gate prefetch | W + L'
+  constexpr int W_MMA = 4 * NWG, W_A = W_MMA + NMW, W_W = W_A + 1, W_L = (NMW == 2) ? W_W : W_A + 2;
   constexpr int STG = 2 * KC * TILE + 2 * RW * KC;   // floats per ring stage: A chunk (hi | lo) + W chunk (hi | lo)
   constexpr int NBAR = 2 * NST + 2 * NLB + 2 * NB;
   extern __shared__ __align__(128) float smem[];
@@ -114,6 +123,7 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
   __shared__ uint64_t bars[NBAR];
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t cm_sh[2];
+  __shared__ volatile int full_turn;   // NMW == 2: chunks whose ring-stage "full" wait has been passed, in chunk order
   const uint32_t bar0 = tc::smem_u32(bars);
   const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * NST, B_LFULL = bar0 + 16 * NST, B_LFREE = B_LFULL + 8 * NLB,
                  B_BFULL = B_LFREE + 8 * NLB, B_BFREE = B_BFULL + 8 * NB;
@@ -133,6 +143,7 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
   while (ncols < TC + (uint32_t)(NWG * d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
+    full_turn = 0;
     for (int i = 0; i < NBAR; ++i) {
       const bool four = (i >= 2 * NST + NLB && i < 2 * NST + 2 * NLB) || i >= 2 * NST + 2 * NLB + NB;   // lfree, bfree: one arrival per gate warp
       tc::mbar_init(&bars[i], four ? 4 : (i < NST ? 2 : 1));                                           // full: A + W producers
@@ -144,72 +155,101 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const float* __restrict__ wbuf = a.plan.wbuf;
-  const uint32_t idesc = tc::idesc_tf32_m128(mp);
+  const float* __restrict__ wbuf = a.plan.wbuf;   // un-split fp32 L' images (and the tf32 W images)
+  const float* __restrict__ wimg = wbuf;          // GEMM1 W images
+  if constexpr (F16) wimg = a.wbuf16;
+  const uint32_t idesc = F16 ? rot16::idesc_f16_m128(mp) : tc::idesc_tf32_m128(mp);
   const uint32_t dhi = tc::smem_desc_hi(128);
   const uint32_t lbo_a = TILE * 16, lbo_n = (uint32_t)mp * 16;
   const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_n) >> 4;
 
-  if (warp > W_MMA) {
-    // =============================== TMA producers: A chunks | W chunks | L' images + gate prefetch ===============================
+  if (warp >= W_A) {
+    // =============================== TMA producers ===============================
     if (lane == 0) {
-      const float* xt = a.xp + (size_t)tile * a.tile_stride;
-      if (warp == W_L) {
-        constexpr int GPF = 4;
-        const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
-        const float* gt = a.g + (size_t)tile * a.gstride * TILE;
-        auto prefetch_gate = [&](int sj) {
-          if (sj < se) {
-            const hgb_rot_step_t* ps = a.steps + sj;
-            if (ps->branch >= 0) bulk_prefetch_l2(gt + (size_t)ps->branch * g_bstride + (size_t)ps->g_off * TILE, (uint32_t)(mul * TILE) * 4u);
-          }
-        };
-        for (int j = 0; j < GPF; ++j) prefetch_gate(sb + j);
-        int n = 0;
-        const uint32_t lbytes = (uint32_t)(mp * mp) * 4u;
-        for (int si = sb; si < se; ++si, ++n) {
-          const hgb_rot_step_t st = a.steps[si];
-          prefetch_gate(si + GPF);
-          const int lb = n % NLB;
-          if (n >= NLB) wait_a(B_LFREE + 8 * lb, (uint32_t)(((n / NLB) - 1) & 1));   // the gate warps have read L'(n - NLB)
-          expect_tx_a(B_LFULL + 8 * lb, lbytes);
-          bulk_g2s_a(sl0 + (uint32_t)(lb * RW * RW) * 4u, wbuf + st.pad2, lbytes, B_LFULL + 8 * lb);
-        }
-      } else {
-        const bool isA = warp == W_A;
-        int c_all = 0;
-        for (int si = sb; si < se; ++si) {
-          const hgb_rot_step_t st = a.steps[si];
-          const int kpad = st.kpad;
+      const bool doA = warp == W_A, doW = warp == W_W, doL = warp == W_L, doG = (NMW == 2) ? doA : doL;
+      const float* xt = reinterpret_cast<const float*>(a.xp) + (size_t)tile * a.tile_stride;
+      constexpr int GPF = 4;
+      const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+      const float* gt = a.g + (size_t)tile * a.gstride * TILE;
+      // The step records are read one iteration ahead (and the record of the gate block to prefetch one more): a dependent
+      // global load at the top of every iteration would put an L2 round trip (~700 cycles) into this thread's per-step time
+      const uint4* rec4 = reinterpret_cast<const uint4*>(a.steps);
+      auto gate_block = [&](const uint4& w0, const uint4& w1) {   // L2 prefetch of the gate block of a step
+        const int br = (int)(int8_t)(w1.y >> 24);
+        if (br >= 0) bulk_prefetch_l2(gt + (size_t)br * g_bstride + (size_t)(int)w0.w * TILE, (uint32_t)(mul * TILE) * 4u);
+      };
+      if (doG)
+        for (int j = 0; j < GPF && sb + j < se; ++j) gate_block(__ldg(rec4 + 2 * (sb + j)), __ldg(rec4 + 2 * (sb + j) + 1));
+      const uint32_t lbytes = (uint32_t)(mp * mp) * 4u;
+      int n = 0, c_all = 0;
+      uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, g0 = c0, g1 = c0;
+      if (sb < se) { c0 = __ldg(rec4 + 2 * sb); c1 = __ldg(rec4 + 2 * sb + 1); }
+      if (doG && sb + GPF < se) { g0 = __ldg(rec4 + 2 * (sb + GPF)); g1 = __ldg(rec4 + 2 * (sb + GPF) + 1); }
+      for (int si = sb; si < se; ++si, ++n) {
+        uint4 n0 = c0, n1 = c1, h0 = g0, h1 = g1;
+        if (si + 1 < se) { n0 = __ldg(rec4 + 2 * (si + 1)); n1 = __ldg(rec4 + 2 * (si + 1) + 1); }
+        if (doG && si + 1 + GPF < se) { h0 = __ldg(rec4 + 2 * (si + 1 + GPF)); h1 = __ldg(rec4 + 2 * (si + 1 + GPF) + 1); }
+        if (doG && si + GPF < se) gate_block(g0, g1);
+        const int st_a_off = (int)c0.x, st_w_off = (int)c0.y, st_lf_off = (int)c0.z, st_kpad = (int)(int16_t)(c1.y & 0xffffu), st_pad2 = (int)c1.w;
+        if (doA || doW) {
+          const int kpad = st_kpad;
           for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
             const int kc = min(KC, kpad - u0), s = c_all % NST;
             if (c_all >= NST) wait_a(B_EMPTY + 8 * s, (uint32_t)(((c_all / NST) - 1) & 1));
             const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
             const uint32_t ab = (uint32_t)(kc * TILE * 2) * 4u, wb = (uint32_t)(2 * mp * kc) * 4u;
-            if (isA) {
+            if (doA) {
               expect_tx_a(B_FULL + 8 * s, ab);
-              bulk_g2s_a(sa, xt + st.a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
+              bulk_g2s_a(sa, xt + st_a_off + (size_t)c * (2 * KC * TILE), ab, B_FULL + 8 * s);
             } else {
               expect_tx_a(B_FULL + 8 * s, wb);
-              bulk_g2s_a(sa + 2 * KC * TILE * 4, wbuf + st.w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
+              bulk_g2s_a(sa + 2 * KC * TILE * 4, wimg + st_w_off + (size_t)c * (2 * mp * KC), wb, B_FULL + 8 * s);
             }
           }
         }
+        if (doL) {
+          const int lb = n % NLB;
+          if (n >= NLB) wait_a(B_LFREE + 8 * lb, (uint32_t)(((n / NLB) - 1) & 1));   // the gate warps have read L'(n - NLB)
+          expect_tx_a(B_LFULL + 8 * lb, lbytes);
+          bulk_g2s_a(sl0 + (uint32_t)(lb * RW * RW) * 4u, wbuf + (F16 ? st_lf_off : st_pad2), lbytes, B_LFULL + 8 * lb);
+        }
+        c0 = n0; c1 = n1; g0 = h0; g1 = h1;
       }
     }
     __syncwarp();
-  } else if (warp == W_MMA) {
-    // =============================== GEMM1 issuer ===============================
+  } else if (warp >= W_MMA) {
+    // =============================== GEMM1 issuer(s) ===============================
+    // NWG = 2: two issuer warps take alternate steps (ncu r05f: the single issuer's ~190 scalar instructions per step at ~8 cycles
+    // each paced the CTA once the gate work was dealt to two warpgroups); both walk all steps to keep the ring's chunk count
+    const int mw = warp - W_MMA;
     int n = 0, c_all = 0;
     int kpad = (sb < se) ? a.steps[sb].kpad : 0;
     for (int si = sb; si < se; ++si, ++n) {
       const int kpad_next = (si + 1 < se) ? a.steps[si + 1].kpad : 0;
+      if (NMW == 2 && (n & 1) != mw) {   // the other issuer's step
+        c_all += (kpad + KC - 1) / KC;
+        kpad = kpad_next;
+        continue;
+      }
       const int b = n % NB;
       if (n >= NB) warp_wait_a(B_BFREE + 8 * b, (uint32_t)(((n / NB) - 1) & 1));   // the gate warps have read B(n - NB)
       const uint32_t dcol = tmem + (uint32_t)(b * mp);
       for (int u0 = 0, c = 0; u0 < kpad; u0 += KC, ++c, ++c_all) {
         const int kc = min(KC, kpad - u0), s = c_all % NST;
-        warp_wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
+        if (NMW == 2) {
+          // a parity wait is only valid one phase ahead: the two issuers pass the ring's "full" waits strictly in chunk order
+          // (without this the issuer of step n + 1 could test a stage two uses early and see the phase of use u - 2)
+          if (lane == 0) {
+            uint32_t spins = 0;
+            while (full_turn != c_all)
+              if (++spins > 0x4000000u) __trap();
+            wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
+            full_turn = c_all + 1;
+          }
+          __syncwarp();
+        } else {
+          warp_wait_a(B_FULL + 8 * s, (uint32_t)((c_all / NST) & 1));
+        }
         tc::fence_after_sync();
         if (elect_one()) {
           const uint32_t sa = stage0 + (uint32_t)(s * STG) * 4u;
@@ -218,9 +258,15 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
           for (int k8 = 0; k8 < (kc >> 3); ++k8) {
             const uint64_t dah = tc::desc64(ah + k8 * astep, dhi), dal = tc::desc64(al + k8 * astep, dhi);
             const uint64_t dbh = tc::desc64(wh + k8 * bstep, dhi), dbl_ = tc::desc64(wl + k8 * bstep, dhi);
-            tc::mma_tf32(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
-            tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
-            tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+            if constexpr (F16) {
+              rot16::mma_f16(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+              rot16::mma_f16(dcol, dah, dbl_, idesc, 1);
+              rot16::mma_f16(dcol, dah, dbh, idesc, 1);
+            } else {
+              tc::mma_tf32(dcol, dal, dbh, idesc, (uint32_t)(c > 0) | (uint32_t)(k8 > 0));
+              tc::mma_tf32(dcol, dah, dbl_, idesc, 1);
+              tc::mma_tf32(dcol, dah, dbh, idesc, 1);
+            }
           }
           commit_a(B_EMPTY + 8 * s);
           if (u0 + KC >= kpad) commit_a(B_BFULL + 8 * b);
@@ -250,8 +296,10 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
     // gate values of a step straight into registers (quads past the multiplicity are skipped by a branch); un-gated steps
     // (branch < 0) use the factor (gA, gB) = (0, scale) instead of (scale, 0) on whatever the registers hold
     auto load_gate = [&](const uint4& w0, const uint4& w1) {
-      const float sc = __uint_as_float(w1.x);
+      float sc = __uint_as_float(w1.x);
       const int br = (int)(int8_t)(w1.y >> 24);
+      if constexpr (F16)   // inverse scales of the W image and of this edge's rows of the input block
+        sc *= __ldg(a.img_inv + (w1.w & 0xffffu)) * __ldg(a.sx + ((size_t)tile * a.n_blocks + (w1.z >> 16)) * TILE + zt);
       gA = (br < 0) ? 0.f : sc;
       gB = (br < 0) ? sc : 0.f;
       if (br >= 0) {   // warp-uniform

@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(256, 3) radial_gate_kernel(const __grid_consta
 #include "msgpack_tcr_kernel.cuh"
 #include "radial_gate_tc_kernel.cuh"
 #include "msgpack_rot_kernel.cuh"
-#include "msgpack_rotf_kernel.cuh"
 #include "msgpack_rot16_kernel.cuh"
+#include "msgpack_rotf_kernel.cuh"
 #include "msgpack_rot2_kernel.cuh"
 
 // Radial gate pre-pass: the tcgen05 kernel when the host supplies the packed W3 tiles (w3img_off != NULL) and the
@@ -696,12 +696,12 @@ int launch_rot_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
 }  // namespace
 
 namespace {
-template <int RW, int NST, int NWG>
-int launch_rotf_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
+template <int RW, int NST, int NWG, int NMW = 1, bool F16 = false>
+int launch_rotf_class(const typename rotf::ArgsOf<F16>::type& ra, int n_tiles, cudaStream_t st) {
   constexpr size_t smem = rotf::rotf_smem_bytes<RW, NST>();
   static_assert(smem <= 113 * 1024, "msgpack_rotf_kernel shared memory (2 CTAs / SM)");
-  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rotf::msgpack_rotf_kernel<RW, NST, NWG><<<(unsigned)(n_tiles * ra.n_slots), 128 * NWG + 128, smem, st>>>(ra);
+  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16><<<(unsigned)(n_tiles * ra.n_slots), 128 * NWG + 128, smem, st>>>(ra);
   HGB_LAUNCH_OK("msgpack_rotf_kernel");
   return 0;
 }
@@ -746,7 +746,10 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
   // slot classes 16 / 32 run msgpack_rotf_kernel (L' on the FMA pipes, four GEMM1 accumulators in TMEM) when every slot of the
   // class fits its 256 TMEM columns and every step carries the un-split fp32 L' image; HGB_ROT_FMA = bit mask of the classes
   // (default 3; 0 = msgpack_rot_kernel everywhere)
-  const int fma_env = getenv("HGB_ROT_FMA") ? atoi(getenv("HGB_ROT_FMA")) : 3;   // bit 2 (4): two gate warpgroups for class 16
+  // bit 0 / 1: classes 16 / 32 on msgpack_rotf_kernel; bit 2: two gate warpgroups for class 16; bit 3: two GEMM1 issuer warps;
+  // bit 4: two ring stages instead of three.  Measured on tbg_m8 (profiles/README.md r05): message kernels 57.5 ms with 0,
+  // 50.0 with 1, 68.4 with 2 (class 32 on the FMA pipes spills at 128 registers), 47.4 with 5, 48.8 with 13, 46.2 with 21.
+  const int fma_env = getenv("HGB_ROT_FMA") ? atoi(getenv("HGB_ROT_FMA")) : 21;
   bool fma_ok[3] = {(fma_env & 1) != 0, (fma_env & 2) != 0, false};
   bool fma_wg2 = (fma_env & 4) != 0;
   for (int t = 0; t < plan->n_types; ++t) {
@@ -843,7 +846,10 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
       if (k == 0) rc = !fma_ok[0] ? launch_rot_class<16, 3>(cls[k], n_tiles, st)
-                       : fma_wg2 ? launch_rotf_class<16, 3, 2>(cls[k], n_tiles, st) : launch_rotf_class<16, 3, 1>(cls[k], n_tiles, st);
+                       : !fma_wg2 ? launch_rotf_class<16, 3, 1>(cls[k], n_tiles, st)
+                       : (fma_env & 16) ? launch_rotf_class<16, 2, 2>(cls[k], n_tiles, st)      // experiment: two ring stages
+                       : (fma_env & 8) ? launch_rotf_class<16, 3, 2, 2>(cls[k], n_tiles, st)    // experiment: two GEMM1 issuer warps
+                                       : launch_rotf_class<16, 3, 2>(cls[k], n_tiles, st);
       else if (k == 1) rc = fma_ok[1] ? launch_rotf_class<32, 2, 1>(cls[k], n_tiles, st) : launch_rot_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
@@ -910,7 +916,9 @@ extern "C" int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan, const hgb
     HGB_CHECK_ARG(ty.l >= 0 && ty.l <= rp->lmax && ty.mpad % 16 == 0 && ty.mpad >= ty.mul && ty.mpad <= NMAX,
                   "hgb_msgpack_rot16_forward: slot %d (mul %d, padded %d, l %d) unsupported", t, ty.mul, ty.mpad, ty.l);
     klass[t] = ty.mpad <= 16 ? 0 : (ty.mpad <= 32 ? 1 : 2);
-    {
+    if (klass[t] == 0) {   // msgpack_rotf_kernel<16, 3, 2, 1, F16>: four GEMM1 accumulators + one C' per gate warpgroup
+      HGB_CHECK_ARG(rotf::NB * ty.mpad + 2 * d3 * ty.mul <= 256, "hgb_msgpack_rot16_forward: slot %d needs more than 256 TMEM columns", t);
+    } else {
       const int dbl = (klass[t] == 1) ? 0 : 1;
       HGB_CHECK_ARG((4 + 2 * dbl) * ty.mpad + d3 * ty.mul <= 512, "hgb_msgpack_rot16_forward: slot %d needs more than 512 TMEM columns", t);
     }
@@ -923,7 +931,7 @@ extern "C" int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan, const hgb
       HGB_CHECK_ARG(s.kpad >= 8 && s.kpad % 8 == 0 && s.m3 >= 0 && s.m3 < d3 && s.kind == 0 && s.a_off >= 0 && s.a_off % 4 == 0 &&
                         (int64_t)s.a_off + (int64_t)2 * s.kpad * rot::TILE <= rp->tile_stride && s.w_off >= 0 && s.w_off % 4 == 0 &&
                         (int64_t)s.w_off + (int64_t)2 * ty.mpad * s.kpad <= wbuf16_words && s.lf_off >= 0 && s.lf_off % 4 == 0 &&
-                        (int64_t)s.lf_off + (int64_t)ty.mpad * ty.mpad <= wbuf16_words && (s.new_path & 1) && s.pad >= 0 &&
+                        (klass[t] == 0 || (int64_t)s.lf_off + (int64_t)ty.mpad * ty.mpad <= wbuf16_words) && (s.new_path & 1) && s.pad >= 0 &&
                         s.pad < rp->n_blocks && (int)wimg < n_images && (int)limg < n_images,
                     "hgb_msgpack_rot16_forward: bad step %d", si);
       HGB_CHECK_ARG(s.branch < plan->n_branches && (s.branch < 0 || (s.g_off >= 0 && s.g_off + ty.mul <= nch[s.branch])),
@@ -994,7 +1002,7 @@ extern "C" int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan, const hgb
       if (cls[k].n_slots == 0) continue;
       cls[k].e_lo = e_lo; cls[k].n_chunk = n;
       int rc = 0;
-      if (k == 0) rc = launch_rot16_class<16, 3>(cls[k], n_tiles, st);
+      if (k == 0) rc = launch_rotf_class<16, 3, 2, 1, true>(cls[k], n_tiles, st);   // steps of these slots carry the fp32 L' offset
       else if (k == 1) rc = launch_rot16_class<32, 2>(cls[k], n_tiles, st);
       else rc = launch_rot16_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;

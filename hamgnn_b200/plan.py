@@ -968,10 +968,14 @@ class MessagePackOp:
                         c = float(w[l1 + m1, pa.l2, l3 + m3]) * math.sqrt(2 * pa.l2 + 1)
                         if c == 0.0:
                             continue
-                        group.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, w_img[p][0], l_img[p][0], pa.pad0, c, blk.kpad // 2, 0,
+                        # slots of padded multiplicity 16 run msgpack_rotf_kernel<F16> (L' on the FMA pipes): lf_off = the un-split
+                        # fp32 L' image in the tensor-core wbuf; wider slots run msgpack_rot16_kernel: lf_off = the fp16 image
+                        lf = self.tc_lplain_off[int(pa.lf_off)] if mp == 16 else l_img[p][0]
+                        group.append(L.RotStepT(blk.xoff + (l1 + m1) * per_m, w_img[p][0], lf, pa.pad0, c, blk.kpad // 2, 0,
                                                 pa.branch, l3 + m3, 1, bi, w_img[p][1] | (l_img[p][1] << 16)))
                     else:
-                        group.append(L.RotStepT(blk.xoff + (l1 + m3) * per_m, w_img[p][0], ident[mp][0], 0, 1.0, blk.kpad // 2, 0,
+                        lf = self.tc_lplain_off[int(self.tc_ident_off[mp])] if mp == 16 else ident[mp][0]
+                        group.append(L.RotStepT(blk.xoff + (l1 + m3) * per_m, w_img[p][0], lf, 0, 1.0, blk.kpad // 2, 0,
                                                 -1, l3 + m3, 1, bi, w_img[p][1] | (ident[mp][1] << 16)))
                 if group:
                     group[-1].new_path |= 4

@@ -645,6 +645,9 @@ def emulate_msgpack_rot16(op: MessagePackOp, st: dict, sources, rows, vec, rbf, 
             else:
                 gv[:, :ty.mul] = sc[:, None]
             P = B * gv
+            if mp == 16:   # msgpack_rotf_kernel<F16>: L' on the fp32 FMA pipes from the un-split image at lf_off of the tensor-core wbuf
+                Cacc[:, s_.m3, :] += P @ wbuf[s_.lf_off:s_.lf_off + mp * mp].view(mp, mp)
+                continue
             ps, pinv = _pow2_scale(P.abs().amax(dim=1), 0)
             ph, pl = _split16(P * ps[:, None])
             lh, ll = _decode_image16(buf16, s_.lf_off, mp, mp // 2)
