@@ -60,6 +60,24 @@ __device__ __forceinline__ void fma_rows(float (&acc)[RW], const float (&p)[RW],
 constexpr int NB = 4;    // GEMM1 accumulators in flight
 constexpr int NLB = 4;   // L' buffers in flight
 
+// acc[0 .. 4 MC) += sum_{j < nw} p[j] L'[j][0 .. 4 MC) with Ls already advanced to the first of the nw rows
+template <int HW, int RW, int MC>
+__device__ __forceinline__ void fma_rows_part(float (&acc)[RW], const float (&p)[HW], const float4* __restrict__ Ls, int rq, int nw) {
+#pragma unroll
+  for (int j = 0; j < HW; ++j) {
+    if (j >= nw) break;   // warp-uniform
+    const float pw = p[j];
+#pragma unroll
+    for (int q = 0; q < MC; ++q) {
+      const float4 l = Ls[j * rq + q];
+      acc[4 * q + 0] = fmaf(pw, l.x, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(pw, l.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(pw, l.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(pw, l.w, acc[4 * q + 3]);
+    }
+  }
+}
+
 // C[z][w][k] = sum_m3 D^{l3}_z[m3][k] (C'_A + C'_B)[z][m3][w] for the channel quads c_first, c_first + c_step, ...; C'_X[m3][w] is
 // TMEM column tcX + m3 * mul + w, bit m3 of cmX: region X holds that component (otherwise it counts as zero).
 template <int L3>
@@ -111,8 +129,13 @@ template <> struct ArgsOf<true> { using type = rot16::Rot16Args; };
 // (edge, input block), W images with a scale per image, kind::f16 MMAs with K = 16 per instruction, offsets / kpad in 32-bit
 // words) -- half the tensor-core instructions and half the operand bytes of the tf32 form; the inverse scales are folded
 // into the gate factor.  The step's lf_off is then the offset of the un-split fp32 L' image in plan.wbuf.
-template <int RW, int NST, int NWG, int NMW, bool F16>
+// SPLIT = true (NWG = 2, slot class 32): both gate warpgroups work on EVERY step, each on half of the mid channels w (rows of
+// L'): 16 gate values, 16 gated products and 32 partial sums per thread instead of 32 / 32 / 32 -- the class-32 form of the
+// kernel with one warpgroup spilled at 128 registers and ran 1.7x slower than msgpack_rot_kernel<32,2>.  At the end of an m3
+// group warpgroup 0 parks its partial sums in C', warpgroup 1 adds its own (one named barrier per group).
+template <int RW, int NST, int NWG, int NMW, bool F16, bool SPLIT = false>
 __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const __grid_constant__ typename ArgsOf<F16>::type a) {
+  static_assert(!SPLIT || (NWG == 2 && RW == 32), "SPLIT: two gate warpgroups, slot class 32");
   // NMW = GEMM1 issuer warps; the CTA always has four non-gate warps: NMW = 1: issuer | A | W | L' + gate prefetch,
   // NMW = 2: issuer 0 | issuer 1 | A + gate prefetch | W + L'
   constexpr int W_MMA = 4 * NWG, W_A = W_MMA + NMW, W_W = W_A + 1, W_L = (NMW == 2) ? W_W : W_A + 2;
@@ -140,13 +163,13 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
   // TMEM columns: B0 | B1 | B2 | B3 | C' of warpgroup 0 (d3 x mul, exact stride) (| C' of warpgroup 1)
   const uint32_t TC = (uint32_t)(NB * mp);
   uint32_t ncols = 32;
-  while (ncols < TC + (uint32_t)(NWG * d3 * mul)) ncols <<= 1;
+  while (ncols < TC + (uint32_t)((SPLIT ? 1 : NWG) * d3 * mul)) ncols <<= 1;
 
   if (tid == 0) {
     full_turn = 0;
     for (int i = 0; i < NBAR; ++i) {
       const bool four = (i >= 2 * NST + NLB && i < 2 * NST + 2 * NLB) || i >= 2 * NST + 2 * NLB + NB;   // lfree, bfree: one arrival per gate warp
-      tc::mbar_init(&bars[i], four ? 4 : (i < NST ? 2 : 1));                                           // full: A + W producers
+      tc::mbar_init(&bars[i], four ? (SPLIT ? 8 : 4) : (i < NST ? 2 : 1));                                           // full: A + W producers
     }
     tc::mbar_fence_init();
   }
@@ -276,6 +299,134 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
       kpad = kpad_next;
     }
   } else {
+    if constexpr (SPLIT) {
+      // =============================== gate halves (both warpgroups on every step) ===============================
+      constexpr int HW = RW / 2;
+      const int wg = warp >> 2, zt = (warp & 3) * 32 + lane;
+      const int64_t el = (int64_t)tile * TILE + zt;
+      const bool live = el < a.n_chunk;
+      const int64_t e = a.e_lo + el;
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const size_t g_bstride = (size_t)((a.n_chunk + TILE - 1) / TILE) * a.gstride * TILE;
+      const float* grow = a.g + (size_t)tile * a.gstride * TILE + (live ? zt : 0);
+      const int mc = (mul + 3) >> 2;
+      const int h0 = min(mul, ((mul >> 1) + 3) & ~3);        // mid channels [0, h0) -> warpgroup 0, [h0, mul) -> warpgroup 1
+      const int w0 = wg ? h0 : 0, nw = wg ? mul - h0 : h0;   // this warpgroup's rows of L' (nw <= 16)
+      const int nq = (nw + 3) >> 2;
+      const int nsteps = se - sb;
+      float gv[HW], acc[RW];
+#pragma unroll
+      for (int j = 0; j < HW; ++j) gv[j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < RW; ++j) acc[j] = 0.f;
+      float gA = 0.f, gB = 0.f;
+      uint32_t cmask = 0;
+      const uint4* steps4 = reinterpret_cast<const uint4*>(a.steps) + 2 * sb;
+      auto load_gate = [&](const uint4& r0, const uint4& r1) {
+        float sc = __uint_as_float(r1.x);
+        const int br = (int)(int8_t)(r1.y >> 24);
+        gA = (br < 0) ? 0.f : sc;
+        gB = (br < 0) ? sc : 0.f;
+        if (br >= 0) {   // warp-uniform
+          const float* gp = grow + (size_t)br * g_bstride + (size_t)((int)r0.w + w0) * TILE;
+#pragma unroll
+          for (int q = 0; q < HW / 4; ++q) {
+            if (q >= nq) break;
+#pragma unroll
+            for (int j = 4 * q; j < 4 * q + 4; ++j) gv[j] = __ldg(gp + j * TILE);   // columns past the multiplicity meet B == 0 / unused rows
+          }
+        }
+      };
+      uint32_t cur_fm = 0;
+      if (nsteps > 0) {
+        const uint4 r0 = __ldg(steps4), r1 = __ldg(steps4 + 1);
+        cur_fm = r1.z;
+        load_gate(r0, r1);
+      }
+      for (int n = 0; n < nsteps; ++n) {
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        const bool more = n + 1 < nsteps;
+        if (more) { n0 = __ldg(steps4 + 2 * (n + 1)); n1 = __ldg(steps4 + 2 * (n + 1) + 1); }
+        const int m3 = (int)(cur_fm & 0xff);
+        const bool park = ((cur_fm >> 8) & 4u) != 0;
+        cmask |= 1u << m3;
+        const int b = n % NB, lb = n % NLB;
+        warp_wait_a(B_BFULL + 8 * b, (uint32_t)((n / NB) & 1));
+        tc::fence_after_sync();
+        const uint32_t bq = tmem + lane_base + (uint32_t)(b * mp + w0);
+        float p[HW];
+#pragma unroll
+        for (int c0 = 0; c0 < HW; c0 += 8) {
+          uint32_t rb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rb[j] = 0u;
+          if (c0 < nw) {   // warp-uniform; w0 + c0 + 7 <= 31 < mp
+            tc::tmem_ld8(bq + c0, rb);
+            tc::tmem_ld_wait8(rb);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[c0 + j] = __uint_as_float(rb[j]) * fmaf(gv[c0 + j], gA, gB);
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) arrive_a(B_BFREE + 8 * b);
+        if (more) load_gate(n0, n1);
+        wait_a(B_LFULL + 8 * lb, (uint32_t)((n / NLB) & 1));
+        const int rq = mp >> 2;
+        const float4* Ls = reinterpret_cast<const float4*>(lsm + lb * RW * RW) + w0 * rq;
+        if (mc <= 6) fma_rows_part<HW, RW, 6>(acc, p, Ls, rq, nw);
+        else fma_rows_part<HW, RW, RW / 4>(acc, p, Ls, rq, nw);
+        __syncwarp();
+        if (lane == 0) arrive_a(B_LFREE + 8 * lb);
+        if (park) {   // warp-uniform, the same decision in both warpgroups
+          const uint32_t cc = tmem + lane_base + TC + (uint32_t)(m3 * mul);
+          if (wg == 0) {
+#pragma unroll
+            for (int j = 0; j < RW; ++j)
+              if (j < mul) tmem_st1(cc + j, __float_as_uint(acc[j]));
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (wg == 1) {
+            tc::fence_after_sync();
+#pragma unroll
+            for (int j = 0; j < RW; ++j) {
+              if (j < mul) {
+                uint32_t c = 0u;
+                rot::tmem_ld1(cc + j, c);
+                rot::tmem_ld_wait1(c);
+                tmem_st1(cc + j, __float_as_uint(acc[j] + __uint_as_float(c)));
+              }
+            }
+            tc::tmem_st_wait();
+          }
+#pragma unroll
+          for (int j = 0; j < RW; ++j) acc[j] = 0.f;
+        }
+        cur_fm = n1.z;
+      }
+      tc::fence_before_sync();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // warpgroup 1 has added its last partial sums
+      tc::fence_after_sync();
+      {
+        const int64_t orow = (live && a.out_index) ? a.out_index[e] : e;
+        float* op = a.out + (live ? orow : 0) * a.plan.out_dim + ty.out_off;
+        const float* Dz = a.dw + (live ? e : 0) * a.dstride + a.doff[ty.l];
+        const uint32_t tcA = tmem + lane_base + TC;
+        const bool atomic = a.out_index != nullptr;
+        const int cf = 4 * wg, cs = 8;
+        switch (ty.l) {
+          case 0: rotf_epilogue<0>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          case 1: rotf_epilogue<1>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          case 2: rotf_epilogue<2>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          case 3: rotf_epilogue<3>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          case 4: rotf_epilogue<4>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          case 5: rotf_epilogue<5>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+          default: rotf_epilogue<6>(tcA, tcA, mul, cmask, 0u, Dz, op, live, atomic, cf, cs); break;
+        }
+      }
+    } else {
     // =============================== gate, L', accumulate, final rotation (thread = edge = TMEM lane) ===============================
     const int wg = warp >> 2, zt = (warp & 3) * 32 + lane;   // warpgroup (its steps: n = wg, wg + NWG, ...), edge inside the tile
     const int64_t el = (int64_t)tile * TILE + zt;
@@ -402,6 +553,7 @@ __global__ void __launch_bounds__(128 * NWG + 128, 2) msgpack_rotf_kernel(const 
         case 5: rotf_epilogue<5>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
         default: rotf_epilogue<6>(tcA, tcB, mul, cmA, cmB, Dz, op, live, atomic, cf, cs); break;
       }
+    }
     }
   }
   tc::fence_before_sync();

@@ -696,12 +696,12 @@ int launch_rot_class(const rot::RotArgs& ra, int n_tiles, cudaStream_t st) {
 }  // namespace
 
 namespace {
-template <int RW, int NST, int NWG, int NMW = 1, bool F16 = false>
+template <int RW, int NST, int NWG, int NMW = 1, bool F16 = false, bool SPLIT = false>
 int launch_rotf_class(const typename rotf::ArgsOf<F16>::type& ra, int n_tiles, cudaStream_t st) {
   constexpr size_t smem = rotf::rotf_smem_bytes<RW, NST>();
   static_assert(smem <= 113 * 1024, "msgpack_rotf_kernel shared memory (2 CTAs / SM)");
-  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16><<<(unsigned)(n_tiles * ra.n_slots), 128 * NWG + 128, smem, st>>>(ra);
+  HGB_CUDA_OK(cudaFuncSetAttribute(rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rotf::msgpack_rotf_kernel<RW, NST, NWG, NMW, F16, SPLIT><<<(unsigned)(n_tiles * ra.n_slots), 128 * NWG + 128, smem, st>>>(ra);
   HGB_LAUNCH_OK("msgpack_rotf_kernel");
   return 0;
 }
@@ -850,7 +850,9 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
                        : (fma_env & 16) ? launch_rotf_class<16, 2, 2>(cls[k], n_tiles, st)      // experiment: two ring stages
                        : (fma_env & 8) ? launch_rotf_class<16, 3, 2, 2>(cls[k], n_tiles, st)    // experiment: two GEMM1 issuer warps
                                        : launch_rotf_class<16, 3, 2>(cls[k], n_tiles, st);
-      else if (k == 1) rc = fma_ok[1] ? launch_rotf_class<32, 2, 1>(cls[k], n_tiles, st) : launch_rot_class<32, 2>(cls[k], n_tiles, st);
+      else if (k == 1) rc = !fma_ok[1] ? launch_rot_class<32, 2>(cls[k], n_tiles, st)
+                            : (fma_env & 64) ? launch_rotf_class<32, 2, 1>(cls[k], n_tiles, st)   // experiment: one warpgroup, 128 registers
+                                             : launch_rotf_class<32, 2, 2, 1, false, true>(cls[k], n_tiles, st);
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }
