@@ -7,9 +7,11 @@
 //   * prologue (warps 0-3, thread = edge row): layers 1 and 2 in fp32 FMA from shared memory (weights broadcast,
 //     inputs in a stride-65 tile), the activated h2 row is split hi/lo (3xTF32) and written as the A operand
 //     images [h2/4][128][4] (K-major, no swizzle) -- A stays resident for the whole CTA.
-//   * warp 4: streams the host-packed W3 tiles (64 gate columns each, hi | lo images [h2/4][64][4], L2 resident)
-//     through a ring of 3 with cp.async one tile ahead, issues 3 x h2/8 tcgen05.mma.kind::tf32 (M 128, N 64) per tile
-//     into one of two TMEM accumulators and commits to the tile's barriers.
+//   * warp 5 (one thread): streams the host-packed W3 tiles (64 gate columns each, hi | lo images [h2/4][64][4], L2 resident,
+//     32 KB contiguous) through a ring of 3 with ONE cp.async.bulk per tile (r05: the per-lane cp.async loop of rounds 1-2 --
+//     64 x 16 B per lane and tile, issued by the MMA warp itself -- was ~1 500 cycles of the issuing warp per tile).
+//   * warp 4: issues 3 x h2/8 tcgen05.mma.kind::tf32 (M 128, N 64) per tile into one of two TMEM accumulators and commits
+//     to the tile's barriers.
 //   * warps 0-3: drain the other accumulator (tcgen05.ld, 32 columns per wait) and store 256 contiguous bytes per
 //     row and tile; every 32-byte sector of g is written by one thread in two back-to-back stores.
 //
@@ -20,7 +22,7 @@
 namespace gtc {
 using namespace tcmsg;
 
-constexpr int NT = 160;
+constexpr int NT = 192;   // warps 0-3 prologue + epilogue, warp 4 MMA issuer, warp 5 W3-tile loader (one cp.async.bulk per tile)
 constexpr int TN = 64;     // gate columns per MMA tile
 constexpr int KMAX = 64;   // h2 <= 64
 constexpr int WRING = 3;
@@ -105,7 +107,7 @@ __device__ __forceinline__ void layer16(const float* __restrict__ xin, const flo
 
 __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t dfull[2], dempty[2], wdone[WRING];
+  __shared__ uint64_t dfull[2], dempty[2], wdone[WRING], wfull[WRING];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
   if (tid == 0) {
     tc::mbar_init(&dfull[0], 1); tc::mbar_init(&dfull[1], 1);
     tc::mbar_init(&dempty[0], 4); tc::mbar_init(&dempty[1], 4);
-    for (int i = 0; i < WRING; ++i) tc::mbar_init(&wdone[i], 1);
+    for (int i = 0; i < WRING; ++i) { tc::mbar_init(&wdone[i], 1); tc::mbar_init(&wfull[i], 1); }
     tc::mbar_fence_init();
   }
   if (warp == 4) tc::tmem_alloc<2 * TN>(&tmem_slot);
@@ -171,30 +173,39 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
   __syncthreads();           // from here on the scratch region belongs to the W3 ring
 
   const int img = K * TN;    // floats per operand image of one tile
-  if (warp == 4) {
-    // =============================== loader + MMA warp ===============================
+  if (warp == 5) {
+    // =============================== W3-tile loader ===============================
+    if (lane == 0) {
+      const float* wsrc = a.w3img[b];
+      const uint32_t bytes = (uint32_t)(2 * img) * 4u;
+      for (int t = 0; t < ntiles; ++t) {
+        const int slot = t % WRING;
+        if (t >= WRING) {   // the MMAs of tile t - WRING have read the slot
+          const uint32_t addr = tc::smem_u32(&wdone[slot]), parity = (uint32_t)(((t / WRING) - 1) & 1);
+          uint32_t ok = 0, spins = 0;
+          while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            if (++spins > 0x4000000u) __trap();
+          }
+        }
+        const uint32_t mb = tc::smem_u32(&wfull[slot]);
+        const uint32_t dst = tc::smem_u32(smem + Sm::RING + slot * Sm::TILE);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(wsrc + (size_t)t * 2 * img), "r"(bytes), "r"(mb)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // =============================== MMA warp ===============================
     const uint32_t idesc = tc::idesc_tf32_m128(TN);
     const uint32_t dhi = tc::smem_desc_hi(128);
     const uint32_t lbo_a = ROWS * 16, lbo_b = TN * 16;
     const uint32_t astep = (2 * lbo_a) >> 4, bstep = (2 * lbo_b) >> 4;
-    const float* wsrc = a.w3img[b];
-    auto load_tile = [&](int t) {
-      const float* src = wsrc + (size_t)t * 2 * img;
-      float* dst = smem + Sm::RING + (t % WRING) * Sm::TILE;
-      for (int i = lane; i < (2 * img) / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
-    };
-    if (ntiles > 0) load_tile(0);
-    cp_async_commit();
     for (int t = 0; t < ntiles; ++t) {
-      if (t + 1 < ntiles) {
-        // slot (t + 1) % 3 was last read by the MMAs of tile t - 2
-        if (t >= 2) spin_wait(&wdone[(t - 2) % WRING], (uint32_t)(((t - 2) / WRING) & 1));
-        load_tile(t + 1);
-      }
-      cp_async_commit();
-      cp_async_wait_group<1>();   // tile t has landed
-      tc::fence_proxy_async();
-      __syncwarp();
+      spin_wait(&wfull[t % WRING], (uint32_t)((t / WRING) & 1));                 // tile t has landed (async-proxy writes)
       if (t >= 2) spin_wait(&dempty[t & 1], (uint32_t)(((t >> 1) - 1) & 1));   // accumulator drained (tile t - 2)
       if (lane == 0) {
         tc::fence_after_sync();
