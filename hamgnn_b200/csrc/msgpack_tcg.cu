@@ -812,6 +812,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
     }
     a.n_slots = ns;
     a.dbl = (k == 1) ? 0 : 1;
+    if (k == 0 && getenv("HGB_ROT_DBL0") && atoi(getenv("HGB_ROT_DBL0"))) a.dbl = 0;   // experiment: single-buffered GL / S for class 16
   }
   rot::RpArgs pa;
   memset(&pa, 0, sizeof(pa));

@@ -23,9 +23,9 @@ namespace gtc {
 using namespace tcmsg;
 
 constexpr int NT = 192;   // warps 0-3 prologue + epilogue, warp 4 MMA issuer, warp 5 W3-tile loader (one cp.async.bulk per tile)
-constexpr int TN = 64;     // gate columns per MMA tile
+constexpr int TN = 128;    // gate columns per MMA tile = MMA N (plan.MessagePackOp.GATE_TILE_COLS); r05: 64 -> 128 halves the MMAs per column
 constexpr int KMAX = 64;   // h2 <= 64
-constexpr int WRING = 3;
+constexpr int WRING = 2;   // two 64 KB tiles (hi | lo images of 128 columns)
 
 // Barrier wait of this kernel: a plain try_wait loop (try_wait itself parks the thread for a hardware time slice).  The
 // tcr::warp_wait it used in round 1 adds a try_wait suspend hint of 10 us and a nanosleep back-off: 36 % of this kernel's
@@ -55,6 +55,18 @@ __device__ __forceinline__ void spin_wait(uint64_t* mbar, uint32_t parity) {
     if (!ok) __trap();
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ bool elect_lane() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 struct Sm {
@@ -207,8 +219,8 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
     for (int t = 0; t < ntiles; ++t) {
       spin_wait(&wfull[t % WRING], (uint32_t)((t / WRING) & 1));                 // tile t has landed (async-proxy writes)
       if (t >= 2) spin_wait(&dempty[t & 1], (uint32_t)(((t >> 1) - 1) & 1));   // accumulator drained (tile t - 2)
-      if (lane == 0) {
-        tc::fence_after_sync();
+      tc::fence_after_sync();
+      if (elect_lane()) {   // convergent warp + elect.sync: descriptors stay in uniform registers, the UTCHMMA issue back to back
         const float* wt = smem + Sm::RING + (t % WRING) * Sm::TILE;
         const uint32_t ah = tc::smem_desc_lo(tc::smem_u32(sAhi), lbo_a), al = tc::smem_desc_lo(tc::smem_u32(sAlo), lbo_a);
         const uint32_t wh = tc::smem_desc_lo(tc::smem_u32(wt), lbo_b), wl = tc::smem_desc_lo(tc::smem_u32(wt + img), lbo_b);
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) radial_gate_tc_kernel(const __grid_cons
       tc::fence_after_sync();
       const int n0 = t * TN;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < TN / 32; ++h) {
         uint32_t r[4][8];
         const uint32_t col = tmem + lane_base + (uint32_t)((t & 1) * TN + h * 32);
         tc::tmem_ld8(col, r[0]); tc::tmem_ld8(col + 8, r[1]); tc::tmem_ld8(col + 16, r[2]); tc::tmem_ld8(col + 24, r[3]);

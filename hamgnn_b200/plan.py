@@ -658,10 +658,10 @@ class MessagePackOp:
             add(wcur + np.arange(n3), base[("fc2", b)] + np.arange(n3), 1.0 / math.sqrt(self.h2), 2)
             wcur += (n3 + 3) // 4 * 4
         # the same layer as tensor-core tiles for radial_gate_tc_kernel: per tile of 64 gate columns a (hi | lo) pair of
-        # K-major images [h2/4][64][4]
+        # K-major images [h2/4][GATE_TILE_COLS][4]
         self.tc_w3img_off = None
         if self.h2 % 8 == 0 and self.h1 % 4 == 0:
-            TNG = 64
+            TNG = self.GATE_TILE_COLS
             self.tc_w3img_off = []
             for b in range(len(self.branches)):
                 nchb = self.n_channels[b]
@@ -790,6 +790,7 @@ class MessagePackOp:
 
     # -------------------------------------------------------------------------------- rotated-frame program
     ROT_TILE = 128    # edges per tile = MMA rows
+    GATE_TILE_COLS = 128   # gate columns per W3 tile of radial_gate_tc_kernel (= gtc::TN, the MMA N)
     ROT_KC = 32       # channels per operand chunk
 
     def _build_rot_program(self):

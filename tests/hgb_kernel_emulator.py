@@ -255,7 +255,7 @@ def emulate_finalize_so3(nao, hns, ksi, lmat, partner, h0_re, h0_im, symmetrize=
 
 def emulate_radial_gate_tc(op: MessagePackOp, wbuf: torch.Tensor, rbf: torch.Tensor):
     """radial_gate_tc_kernel from the tensor-core packing: layers 1-2 from the plain copies, the last layer from the
-    (hi | lo) tiles of 64 gate columns.  Returns [n_branches, E, max n_channels]."""
+    (hi | lo) tiles of GATE_TILE_COLS gate columns.  Returns [n_branches, E, max n_channels]."""
     from hamgnn_b200 import so3
     act = so3.normalize2mom_const("silu")
     out = torch.zeros(len(op.branches), rbf.shape[0], max(op.n_channels), dtype=wbuf.dtype)
@@ -264,11 +264,12 @@ def emulate_radial_gate_tc(op: MessagePackOp, wbuf: torch.Tensor, rbf: torch.Ten
         w2 = wbuf[op.tc_fc2_off[b]:op.tc_fc2_off[b] + op.h1 * op.h2].view(op.h1, op.h2)
         h2 = _silu(_silu(rbf @ w1) * act @ w2) * act
         assert op.tc_w3img_off[b] % 4 == 0
-        for t, n0 in enumerate(range(0, op.n_channels[b], 64)):
-            W = _decode_image(wbuf, op.tc_w3img_off[b] + t * 2 * op.h2 * 64, 64, op.h2)      # [h2, 64]
-            n1 = min(n0 + 64, op.n_channels[b])
+        TN = op.GATE_TILE_COLS
+        for t, n0 in enumerate(range(0, op.n_channels[b], TN)):
+            W = _decode_image(wbuf, op.tc_w3img_off[b] + t * 2 * op.h2 * TN, TN, op.h2)      # [h2, TN]
+            n1 = min(n0 + TN, op.n_channels[b])
             out[b, :, n0:n1] = (h2 @ W)[:, :n1 - n0]
-            assert float(W[:, n1 - n0:].abs().max()) == 0 if n1 - n0 < 64 else True            # zero padding
+            assert float(W[:, n1 - n0:].abs().max()) == 0 if n1 - n0 < TN else True            # zero padding
     return out
 
 
