@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhamgnn_b200.so")
-SOURCES = ["capi.cu", "edge_embed.cu", "msgpack.cu", "rowops.cu", "ham.cu", "tc_gemm_test.cu", "msgpack_tc.cu", "msgpack_tcg.cu", "mma_probe.cu", "neighbor.cu"]
+SOURCES = ["capi.cu", "edge_embed.cu", "msgpack.cu", "rowops.cu", "ham.cu", "tc_gemm_test.cu", "msgpack_tc.cu", "msgpack_tcg.cu", "mma_probe.cu", "neighbor.cu", "band.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

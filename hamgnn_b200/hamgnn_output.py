@@ -18,6 +18,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -124,6 +125,11 @@ class HamGNNPlusPlusOut(nn.Module):
         self.soc_switch, self.spin_constrained, self.collinear_spin = soc_switch, spin_constrained, collinear_spin
         self.zero_point_shift, self.calculate_sparsity = zero_point_shift, calculate_sparsity
         self.calculate_band_energy = calculate_band_energy
+        self.num_k = int(num_k)
+        # reference _configure_band_num_control (hamgnn_output.py:812-830): dict keys -> int, ignored when reciprocal values are exported
+        self.band_num_control = ({int(k): v for k, v in band_num_control.items()} if isinstance(band_num_control, dict)
+                                 else band_num_control if isinstance(band_num_control, int) and not isinstance(band_num_control, bool)
+                                 else None)
         self.get_nonzero_mask_tensor = get_nonzero_mask_tensor
         if self.ham_type != "openmx":
             if self.ham_type in ("siesta", "abacus", "pasp"):
@@ -131,7 +137,10 @@ class HamGNNPlusPlusOut(nn.Module):
             raise NotImplementedError(f"Hamiltonian type '{self.ham_type}' is not supported.")
         self.soc_basis, self.add_H_nonsoc = soc_basis.lower(), add_H_nonsoc
         for flag, name in ((spin_constrained, "spin_constrained"), (collinear_spin, "collinear_spin"),
-                           (calculate_band_energy, "calculate_band_energy"), (return_forces, "return_forces"),
+                           (calculate_band_energy and soc_switch, "calculate_band_energy with soc_switch"),
+                           (calculate_band_energy and not ham_only, "calculate_band_energy with ham_only=False"),
+                           (calculate_band_energy and isinstance(k_path, (list, tuple, str)), "k_path (pass data.k_vecs instead)"),
+                           (return_forces, "return_forces"),
                            (nonlinearity_type != "gate", "nonlinearity_type!='gate'"),
                            (export_reciprocal_values, "export_reciprocal_values")):
             if flag:
@@ -335,6 +344,8 @@ class HamGNNPlusPlusOut(nn.Module):
                 shift = ((H - data["hamiltonian"]) * sel).sum() / (S * sel).sum()
                 H = H - shift * S
             result = {"hamiltonian": H, "band_energy": None, "wavefunction": None, "band_gap": None, "H_sym": None}
+            if self.calculate_band_energy:
+                self._band_energies(data, H, on_row, off_row, result)
             if self.get_nonzero_mask_tensor:
                 result["mask"] = self.build_interaction_masks(data)
         if overlap is not None:
@@ -342,6 +353,27 @@ class HamGNNPlusPlusOut(nn.Module):
         if self.calculate_sparsity:
             result["sparsity_ratio"] = self.calculate_sparsity_ratio(data)
         return result
+
+    # ---------------------------------------------------------------------------------------------
+    def _band_energies(self, data, H, on_row, off_row, result):
+        """Band-energy head (hamgnn_output.py:3802-3880): k points from data.k_vecs [n_crystals, num_k, 3] if present, otherwise
+        num_k random points in (-1, 1)^3 mapped with inv(cell)^T like the reference's default branch; predicted bands into the
+        result, reference bands (from data.Hon / data.Hoff, when present) into data.band_energy / wavefunction / band_gap / H_sym."""
+        from .band import BandEnergyHead, OPENMX_NUM_VALENCE
+        if getattr(self, "_band_head", None) is None:
+            self._band_head = BandEnergyHead(self.nao_max, self.basis_def, OPENMX_NUM_VALENCE, self.num_k, self.band_num_control)
+        dev = H.device
+        if "k_vecs" not in data:
+            cells = data["cell"].detach().float().cpu().numpy().reshape(-1, 3, 3)
+            ks = [(2.0 * np.random.rand(self.num_k, 3) - 1.0).dot(np.linalg.inv(c).T) for c in cells]
+            data["k_vecs"] = torch.tensor(np.stack(ks), dtype=torch.float32, device=dev)
+        hon, hoff = H[on_row], H[off_row]
+        be, wf, gap, hsym = self._band_head(hon, hoff, data)
+        result.update({"band_energy": be, "wavefunction": wf, "band_gap": gap, "H_sym": hsym})
+        if "Hon" in data and "Hoff" in data:
+            with torch.no_grad():
+                data["band_energy"], data["wavefunction"], data["band_gap"], data["H_sym"] = self._band_head(
+                    L.f32c(data["Hon"]), L.f32c(data["Hoff"]), data)
 
     # ---------------------------------------------------------------------------------------------
     def _forward_soc(self, data, node_attr, edge_attr, spinless, on_row, off_row, inv, src, dst, z):

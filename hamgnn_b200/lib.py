@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("HGB_LIB", os.path.join(_HERE, "libhamgnn_b200.so"))
 EXPORTS = ["hgb_abi_version", "hgb_last_error", "hgb_launch_count", "hgb_edge_embed", "hgb_msgpack_forward",
            "hgb_linear_forward", "hgb_resblock_forward", "hgb_ham_assemble", "hgb_ham_finalize", "hgb_tc_gemm_selftest", "hgb_msgpack_tc_forward", "hgb_msgpack_tcg_forward",
            "hgb_linear_forward_ld", "hgb_csr_rows", "hgb_ham_finalize_su2", "hgb_ksi_shell_average", "hgb_ham_finalize_so3",
-           "hgb_msgpack_tcg_forward_v2", "hgb_radial_gate", "hgb_wigner", "hgb_msgpack_rot_forward", "hgb_msgpack_rot2_forward", "hgb_msgpack_rot16_forward", "hgb_timing_enable", "hgb_timing_collect", "hgb_mma_probe", "hgb_tma_probe", "hgb_segment_sum", "hgb_neighbor_list", "hgb_edge_lookup"]
+           "hgb_msgpack_tcg_forward_v2", "hgb_radial_gate", "hgb_wigner", "hgb_msgpack_rot_forward", "hgb_msgpack_rot2_forward", "hgb_msgpack_rot16_forward", "hgb_timing_enable", "hgb_timing_collect", "hgb_mma_probe", "hgb_tma_probe", "hgb_segment_sum", "hgb_neighbor_list", "hgb_edge_lookup", "hgb_band_kspace"]
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -167,6 +167,7 @@ def load() -> C.CDLL:
     lib.hgb_msgpack_rot16_forward.argtypes = [C.POINTER(MsgpackPlan), C.POINTER(RotPlan), C.POINTER(vp), C.POINTER(vp), vp, vp,
                                               C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, vp, vp, vp, vp, i64, vp, i32,
                                               i64, i64, vp, vp, i32, vp]
+    lib.hgb_band_kspace.argtypes = [vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp]
     lib.hgb_timing_enable.argtypes = [i32]
     lib.hgb_timing_collect.argtypes = [C.POINTER(f32), C.POINTER(i64)]
     lib.hgb_mma_probe.argtypes = [i32, i32, i32, i32, i32, vp, vp]

@@ -224,6 +224,22 @@ int hgb_msgpack_rot16_forward(const hgb_msgpack_plan* plan_host, const hgb_rot_p
                               int64_t n_edges, float* out, const int64_t* out_index, int32_t flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f3: band-energy head, reciprocal-space assembly.  Replaces the dense per-k scatter of calculate_band_energies
+ * (hamgnn/models/hamgnn_output.py:1775-1909: phase factors exp(2 pi i k.R), index_put_ accumulate into
+ * [num_k, Na, Na, nao, nao], swapaxes, masked_select of the defined orbitals) for ONE crystal:
+ *   hk / sk [n_k][n_orb][n_orb] complex64 (interleaved re, im), rows / columns = the defined orbitals of the crystal's atoms in
+ *   atom-major order, orb_index[atom][o] = compact index of orbital o of that atom or -1.
+ * hon / son [n_atoms][nao^2], hoff / soff [E][nao^2] fp32; src / dst: atom indices LOCAL to the crystal per edge; nbr_shift
+ * [E][3] and kvec [n_k][3] in reciprocal units of each other (phase = 2 pi k.R).  seg_edge lists the edges grouped by (src, dst)
+ * (any fixed order inside a group), seg_ptr[n_segs + 1] the group boundaries: one CTA adds the images of a pair in list order
+ * (no atomics, bit-reproducible).  The generalized eigenproblem is solved by the caller (hamgnn_b200/band.py, cuSOLVER via
+ * torch.linalg). */
+int hgb_band_kspace(const float* hon, const float* hoff, const float* son, const float* soff, int64_t n_atoms, int32_t nao,
+                    const int64_t* seg_ptr, int64_t n_segs, const int64_t* seg_edge, const int64_t* src, const int64_t* dst,
+                    const float* nbr_shift, const float* kvec, int32_t n_k, const int32_t* orb_index, int32_t n_orb, float* hk,
+                    float* sk, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f4: graph construction on the device.  hgb_neighbor_list replaces neighbor_list_and_relative_vec
  * (hamgnn/models/base_model.py:87-178: ASE primitive_neighbor_list on the CPU with per-atom cutoffs) for one crystal:
  * directed edges i -> (j, S), S in [-reps, reps]^3, iff 0 < |pos_j + S.cell - pos_i| < radius_i + radius_j (fp64), sorted by
