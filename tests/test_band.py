@@ -22,7 +22,7 @@ def _global_inverse(batch):
     return batch.inv_edge_idx + off[eb]
 
 
-def _pd_overlap(batch, nao, seed=0, eps=0.04):
+def _pd_overlap(batch, nao, seed=0, eps=0.01):
     """Synthetic overlap blocks: Son = 1 + small symmetric, Soff[e] = eps * A with Soff[inv e] = Soff[e]^T (S(k) Hermitian, PD)."""
     g = torch.Generator().manual_seed(seed)
     N, E = batch.num_nodes, batch.edge_index.shape[1]
