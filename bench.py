@@ -463,7 +463,7 @@ def main():
                             + (", SOC su2" if kw["out_kw"].get("soc_switch") else "") + (", legacy_edge_update" if kw["cfg"].get("legacy_edge_update") else ""),
                    "messages_per_edge": MSG,
                    "parallelism": (f"edge-shard x{world}" if single_graph else f"graphs over {world} ranks") if world > 1 else "single GPU",
-                   "message_kernel": P.BACKEND, "edge_chunk": P.ROT_CHUNK_EDGES,
+                   "message_kernel": P.BACKEND, "edge_chunk": (P.ROT_CHUNK_EDGES or P._AUTO_CHUNK.get(str(dev), 0)),
                    "l2": "inputs larger than L2 (edge features 2.7 GB per tensor)" if E_total * D * 4 > 2.0e8 else
                          f"working set {E_total * D * 4 / 1e6:.0f} MB per edge tensor; workspaces of GBs are rewritten between uses"},
         "clocks": clk,

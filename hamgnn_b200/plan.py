@@ -269,14 +269,32 @@ GATE_BACKEND = os.environ.get("HGB_GATE", "tc" if BACKEND in ("rot", "rot2", "ro
 ROT16_FLAGS = int(os.environ.get("HGB_ROT16_FLAGS", "0"))   # bit 0: debug, swapped halves of the packed TMEM words
 
 
-# edges per chunk of the 'rot' backend (bounds its workspaces: packed rotated input 25 KB/edge + gate 29 KB/edge)
+# Edges per chunk of the rotated-frame paths (bounds their workspaces: packed rotated input ~25 KB/edge + gate ~29 KB/edge).
+# HGB_ROT_CHUNK fixes it (rounded up to the 128-edge tile); otherwise (0 = auto) it is derived once per device from the free memory:
+# a fifth of it for the two workspaces, between 16 384 and 524 288 edges.  Measured on tbg_m28: 65 536 edges 4.90e6, 131 072 5.07e6,
+# 524 288 5.16e6 messages/s (profiles/README.md r01w: fewer launches, fewer partially filled last waves).
 def _rot_chunk_edges() -> int:
-    """Edges per chunk of the rotated-frame paths: a multiple of the 128-edge tile (HGB_ROT_CHUNK is rounded up)."""
-    v = int(os.environ.get("HGB_ROT_CHUNK", str(128 * 1024)))
-    return max(128, (v + 127) // 128 * 128)
+    v = int(os.environ.get("HGB_ROT_CHUNK", "0"))
+    return 0 if v <= 0 else max(128, (v + 127) // 128 * 128)
 
 
 ROT_CHUNK_EDGES = _rot_chunk_edges()
+_AUTO_CHUNK: Dict[str, int] = {}
+
+
+def rot_chunk(device, floats_per_edge: int) -> int:
+    """The chunk size in effect on `device` for workspaces of `floats_per_edge` fp32 values per edge."""
+    if ROT_CHUNK_EDGES > 0:
+        return ROT_CHUNK_EDGES
+    key = str(device)
+    if key not in _AUTO_CHUNK:
+        free, _total = torch.cuda.mem_get_info(device)
+        # sized for the widest caller of a forward (the first call may be the one-branch embedding block): >= 64 KB per edge
+        edges = int(0.2 * free / (4.0 * max(16384, floats_per_edge)))
+        _AUTO_CHUNK[key] = max(16384, min(524288, edges // 128 * 128))
+    return _AUTO_CHUNK[key]
+
+
 _WIGNER_CACHE: Dict[Tuple, torch.Tensor] = {}
 _WORKSPACES: Dict[Tuple[str, str], torch.Tensor] = {}
 _SEGMENT_CACHE: Dict[str, tuple] = {}
@@ -1513,7 +1531,7 @@ class MessagePackOp:
             E = int(n_edges)
             dev = out.device
             dw = wigner_for(self, edge_vec)
-            chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
+            chunk = min(rot_chunk(dev, nb * self.rot2_gstride + self.rot_tile_stride // self.ROT_TILE), (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = self.rot2_gstride
             # [tile][nb][gstride][128]; zero-initialised once: the kernel reads whole 4-column blocks, the columns past a
             # branch's width are never written and multiply B columns that are exactly zero
@@ -1546,8 +1564,8 @@ class MessagePackOp:
                 seg_out, seg_index = out, out_index
                 out = workspace("msg_rows", max(1, E) * self.irreps_out.dim, out.device)[:E * self.irreps_out.dim].view(E, self.irreps_out.dim)
                 out_index = None
-            chunk = min(ROT_CHUNK_EDGES, (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             gstride = (max(self.n_channels) + 3) // 4 * 4
+            chunk = min(rot_chunk(out.device, nb * gstride + self.rot_tile_stride // self.ROT_TILE), (E + self.ROT_TILE - 1) // self.ROT_TILE * self.ROT_TILE)
             # [nb][tile][gstride][128] (+ one quad of columns: msgpack_rotf_kernel loads whole 4-column groups)
             g_ws = workspace("gate", nb * chunk * gstride + 4 * self.ROT_TILE, out.device)
             w3o = (C.c_int32 * 2)(*(list(self.tc_w3_off) + [0] * (2 - nb)))
