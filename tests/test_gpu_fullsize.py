@@ -39,9 +39,9 @@ def test_message_call_at_full_size():
     try:
         P.BACKEND = "rot"
         assert cb.op.rot_supported()
-        chunk_a = P.ROT_CHUNK_EDGES
         msg = torch.empty(E, D, device=dev)
         cb.op.forward(cb.weights(), [x, x, e], [sd, rd, None], sh, rbf, E, msg, edge_vec=vec)
+        chunk_a = P.ROT_CHUNK_EDGES or P._AUTO_CHUNK[str(msg.device)]   # HGB_ROT_CHUNK, or the size derived from free memory
         agg = torch.zeros(N, D, device=dev)
         cb.op.forward(cb.weights(), [x, x, e], [sd, rd, None], sh, rbf, E, agg, out_index=rd, edge_vec=vec)
         chunk_b = 65536 if chunk_a != 65536 else 131072
