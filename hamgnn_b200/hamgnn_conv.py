@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 from . import lib as L
+from . import plan as P
 from .irreps import Ir, Irreps, MulIr
 from .plan import Branch, GateLayout, LinearOp, MessagePackOp, linear_forward
 
@@ -356,7 +357,11 @@ class HamGNNConvE3(nn.Module):
         rbf = torch.empty(E, self.num_radial, device=dev, dtype=torch.float32)
         vec = torch.empty(E, 3, device=dev, dtype=torch.float32)
         ln = torch.empty(E, device=dev, dtype=torch.float32)
-        freqs = self.radial_basis_functions.freqs.detach().float().cpu().contiguous()
+        fb = self.radial_basis_functions.freqs
+        fkey = (fb.data_ptr(), fb._version, str(fb.device))
+        if getattr(self, "_freqs_host", (None, None))[0] != fkey:     # host copy of the Bessel frequencies: one sync per change, not per forward
+            self._freqs_host = (fkey, fb.detach().float().cpu().contiguous())
+        freqs = self._freqs_host[1]
         fptr = C.cast(freqs.data_ptr(), C.POINTER(C.c_float))
         rc = L.load().hgb_edge_embed(pos.data_ptr(), shift.data_ptr(), ei.data_ptr(), E, self._sh_ls, len(self._sh_ls),
                                      self.cutoff, fptr,
@@ -400,4 +405,5 @@ class HamGNNConvE3(nn.Module):
             self.convolutions[i](data)
             self.pair_interactions[i](data)
         edge_attr = data["edge_features"] if matching is None else data["edge_features"][matching]
+        P._WIGNER_CACHE.clear()      # the per-edge Wigner matrices ([E, 476] fp32) served the seven message ops of this forward
         return AttrDict(node_attr=data["node_features"], edge_attr=edge_attr)
