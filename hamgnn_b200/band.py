@@ -41,24 +41,32 @@ class BandEnergyHead:
             nv[z] = c
         self._nv = nv
 
-    def kspace(self, hon, hoff, son, soff, src_local, dst_local, nbr_shift, kvec, z):
-        """H(k), S(k) [num_k, n_orb, n_orb] complex64 of one crystal (device tensors; src / dst local atom indices)."""
-        dev = hon.device
-        na, nao = hon.shape[0], self.nao_max
+    def kspace_tables(self, src_local, dst_local, z):
+        """Host side of hgb_band_kspace for one crystal: (orb_index [na * nao] int32, n_orb, seg_ptr, seg_edge, n_segs) -- the compact
+        index of every defined orbital and the edges grouped by (i, j) (stable sort: the images of a pair keep their input order)."""
+        dev = z.device
+        na = z.shape[0]
         defined = self._orb_mask.to(dev)[z]                                        # [na, nao]
         flat = defined.reshape(-1)
         orb_index = torch.where(flat, torch.cumsum(flat.to(torch.int32), 0, dtype=torch.int32) - 1,
                                 torch.full_like(flat, -1, dtype=torch.int32)).to(torch.int32).contiguous()
         n_orb = int(flat.sum())
-        E = hoff.shape[0]
+        E = src_local.shape[0]
         key = src_local * na + dst_local
-        order = torch.sort(key, stable=True).indices.contiguous()                   # edges grouped by (i, j), original order inside
+        order = torch.sort(key, stable=True).indices.contiguous()
         ks = key[order]
         starts = torch.ones(E, dtype=torch.bool, device=dev)
         if E > 1:
             starts[1:] = ks[1:] != ks[:-1]
         seg_ptr = torch.cat([torch.nonzero(starts).reshape(-1), torch.tensor([E], device=dev)]).to(torch.int64).contiguous()
         n_segs = int(seg_ptr.numel() - 1) if E > 0 else 0
+        return orb_index, n_orb, seg_ptr, order, n_segs
+
+    def kspace(self, hon, hoff, son, soff, src_local, dst_local, nbr_shift, kvec, z):
+        """H(k), S(k) [num_k, n_orb, n_orb] complex64 of one crystal (device tensors; src / dst local atom indices)."""
+        dev = hon.device
+        na, nao = hon.shape[0], self.nao_max
+        orb_index, n_orb, seg_ptr, order, n_segs = self.kspace_tables(src_local, dst_local, z)
         nk = kvec.shape[0]
         hk = torch.empty(nk, n_orb, n_orb, 2, device=dev, dtype=torch.float32)
         sk = torch.empty(nk, n_orb, n_orb, 2, device=dev, dtype=torch.float32)

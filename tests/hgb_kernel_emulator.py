@@ -660,3 +660,35 @@ def emulate_msgpack_rot16(op: MessagePackOp, st: dict, sources, rows, vec, rbf, 
     if out_rows is None:
         return msg
     return torch.zeros(n_out, D, dtype=dt).index_add_(0, out_rows, msg)
+
+
+# ------------------------------------------------------------------------------------------------ band-energy head
+def emulate_band_kspace(hon, hoff, son, soff, nao, seg_ptr, seg_edge, src, dst, shift, kvec, orb_index, n_orb):
+    """band_onsite_kernel + band_offsite_kernel (csrc/band.cu) from the very arguments of hgb_band_kspace: one (i, j) segment at a
+    time, the images of the pair added in list order; returns (hk, sk) complex [n_k, n_orb, n_orb]."""
+    nk = kvec.shape[0]
+    hk = np.zeros((nk, n_orb, n_orb), dtype=np.complex128)
+    sk = np.zeros_like(hk)
+    oi = np.asarray(orb_index).reshape(-1, nao)
+    hon, hoff, son, soff = (np.asarray(t, np.float64) for t in (hon, hoff, son, soff))
+    for a in range(oi.shape[0]):
+        v = oi[a] >= 0
+        r = oi[a][v]
+        hk[:, r[:, None], r[None, :]] = hon[a].reshape(nao, nao)[np.ix_(v, v)]
+        sk[:, r[:, None], r[None, :]] = son[a].reshape(nao, nao)[np.ix_(v, v)]
+    for s in range(len(seg_ptr) - 1):
+        e0, e1 = int(seg_ptr[s]), int(seg_ptr[s + 1])
+        first = int(seg_edge[e0])
+        i, j = int(src[first]), int(dst[first])
+        vi, vj = oi[i] >= 0, oi[j] >= 0
+        acc_h = np.zeros((nk, int(vi.sum()), int(vj.sum())), dtype=np.complex128)
+        acc_s = np.zeros_like(acc_h)
+        for q in range(e0, e1):
+            e = int(seg_edge[q])
+            assert int(src[e]) == i and int(dst[e]) == j, "a segment holds the images of ONE atom pair"
+            ph = np.exp(2j * np.pi * (np.asarray(kvec, np.float64) @ np.asarray(shift[e], np.float64)))
+            acc_h += ph[:, None, None] * hoff[e].reshape(nao, nao)[np.ix_(vi, vj)]
+            acc_s += ph[:, None, None] * soff[e].reshape(nao, nao)[np.ix_(vi, vj)]
+        hk[:, oi[i][vi][:, None], oi[j][vj][None, :]] += acc_h
+        sk[:, oi[i][vi][:, None], oi[j][vj][None, :]] += acc_s
+    return hk, sk

@@ -82,6 +82,47 @@ def test_oracle_identity_overlap_and_edge_order():
     assert np.allclose(be, be2, atol=1e-10)
 
 
+def test_band_host_tables_cpu():
+    """The host side of hgb_band_kspace (compact orbital index, edges grouped by atom pair) drives a CPU emulation of the two
+    kernels to the oracle's H(k), S(k) -- on shuffled edges, so that the stable (i, j) grouping is exercised."""
+    import hgb_kernel_emulator as EM
+    from hamgnn_b200.band import BandEnergyHead, OPENMX_NUM_VALENCE
+    from hamgnn_b200.hamgnn_output import openmx_basis
+    nao = 19
+    _, _, basis = openmx_basis(nao)
+    g = gd.Batch.from_data_list([gd.mos2_monolayer(seed=2)])      # Mo (19 orbitals) and S (13): the mask matters
+    N, E = g.num_nodes, g.edge_index.shape[1]
+    gen = torch.Generator().manual_seed(9)
+    perm = torch.randperm(E, generator=gen)
+    src, dst, shift = g.edge_index[0][perm], g.edge_index[1][perm], g.nbr_shift[perm]
+    hon, hoff = torch.randn(N, nao * nao, generator=gen), torch.randn(E, nao * nao, generator=gen)
+    son, soff = torch.randn(N, nao * nao, generator=gen), torch.randn(E, nao * nao, generator=gen)
+    kv = torch.rand(5, 3, generator=gen) - 0.5
+    head = BandEnergyHead(nao, basis, OPENMX_NUM_VALENCE, 5)
+    orb_index, n_orb, seg_ptr, order, n_segs = head.kspace_tables(src, dst, g.z)
+    assert n_orb == sum(len(basis[int(z)]) for z in g.z) and n_segs == len(set(zip(src.tolist(), dst.tolist())))
+    hk, sk = EM.emulate_band_kspace(hon, hoff, son, soff, nao, seg_ptr.numpy(), order.numpy(), src.numpy(), dst.numpy(),
+                                    shift.numpy(), kv.numpy(), orb_index.numpy(), n_orb)
+    # the oracle's dense scatter + orbital selection, without its eigen-solve (a random S is not positive definite)
+    nk = kv.shape[0]
+    dh = np.zeros((nk, N, N, nao, nao), dtype=np.complex128)
+    ds = np.zeros_like(dh)
+    for a in range(N):
+        dh[:, a, a] += hon[a].double().numpy().reshape(nao, nao)
+        ds[:, a, a] += son[a].double().numpy().reshape(nao, nao)
+    for e in range(E):
+        ph = np.exp(2j * np.pi * (kv.double().numpy() @ shift[e].double().numpy()))
+        dh[:, int(src[e]), int(dst[e])] += ph[:, None, None] * hoff[e].double().numpy().reshape(nao, nao)
+        ds[:, int(src[e]), int(dst[e])] += ph[:, None, None] * soff[e].double().numpy().reshape(nao, nao)
+    keep = np.zeros((99, nao), dtype=bool)
+    for z, idx in basis.items():
+        keep[z, idx] = True
+    keep = keep[g.z.numpy()].reshape(-1)
+    dh = np.swapaxes(dh, -2, -3).reshape(nk, N * nao, N * nao)[:, keep][:, :, keep]
+    ds = np.swapaxes(ds, -2, -3).reshape(nk, N * nao, N * nao)[:, keep][:, :, keep]
+    assert np.abs(hk - dh).max() < 1e-10 and np.abs(sk - ds).max() < 1e-10
+
+
 @pytest.mark.gpu
 def test_band_head_matches_oracle_gpu():
     from hamgnn_b200.band import BandEnergyHead, OPENMX_NUM_VALENCE
