@@ -852,8 +852,7 @@ extern "C" int hgb_msgpack_rot_forward(const hgb_msgpack_plan* plan, const hgb_r
                        : (fma_env & 8) ? launch_rotf_class<16, 3, 2, 2>(cls[k], n_tiles, st)    // experiment: two GEMM1 issuer warps
                                        : launch_rotf_class<16, 3, 2>(cls[k], n_tiles, st);
       else if (k == 1) rc = !fma_ok[1] ? launch_rot_class<32, 2>(cls[k], n_tiles, st)
-                            : (fma_env & 64) ? launch_rotf_class<32, 2, 1>(cls[k], n_tiles, st)   // experiment: one warpgroup, 128 registers
-                                             : launch_rotf_class<32, 2, 2, 1, false, true>(cls[k], n_tiles, st);
+                                       : launch_rotf_class<32, 2, 2, 1, false, true>(cls[k], n_tiles, st);   // both warpgroups on every step
       else rc = launch_rot_class<64, 2>(cls[k], n_tiles, st);
       if (rc != 0) return rc;
     }

@@ -3,6 +3,8 @@ csrc/msgpack_rot16_kernel.cuh) through the C ABI (hgb_msgpack_rot16_forward): th
 module (hamgnn/nn/message_passing.py:26-231 restated in oracle/), edge chunking, bit-reproducibility of the receiver
 reduction, and the full forward vs the oracle.  Tolerance 1e-5 relative (north-star bar), oracle in fp64 on the same fp32
 weights."""
+import os
+
 import pytest
 import torch
 
@@ -116,4 +118,35 @@ def test_full_forward_rot16_backend(cfg_name, gname):
     errs = (rel_err(r["node_attr"].cpu(), rep["node_attr"]), rel_err(r["edge_attr"].cpu(), rep["edge_attr"]),
             rel_err(o["hamiltonian"].cpu(), res["hamiltonian"]))
     print(f"[{cfg_name} {gname} rot16] rel err node {errs[0]:.2e} edge {errs[1]:.2e} H {errs[2]:.2e}")
+    assert max(errs) < TOL, errs
+
+
+@pytest.mark.parametrize("fma", ["0", "1", "5", "13", "23"])
+def test_rot_path_variants(setup, fma):
+    """Every variant of the default backend that ships in the library (HGB_ROT_FMA bit mask, read per call by
+    hgb_msgpack_rot_forward): 0 = msgpack_rot_kernel for every slot class, 1 = class 16 on msgpack_rotf_kernel with one gate
+    warpgroup, 5 = two gate warpgroups, 13 = + two GEMM1 issuer warps, 23 = class 32 on the FMA pipes as well (both warpgroups on
+    every step); the default (21 = two ring stages) is what every other test runs.  Same bar as the default: 1e-5."""
+    cfg_name, pre, out, opre, oout, batch, d, rep, res, dev = setup
+    torch.manual_seed(11)
+    E, N, D = batch.edge_index.shape[1], batch.num_nodes, pre.irreps_node_features.dim
+    x, e = torch.randn(N, D), torch.randn(E, D)
+    s, r = batch.edge_index
+    dd = {"edge_index": batch.edge_index, "node_features": x.double(), "edge_features": e.double(),
+          "edge_attrs": d["edge_attrs"], "edge_embedding": d["edge_embedding"]}
+    with torch.no_grad():
+        ref_pair = opre.pair_interactions[1](dict(dd))
+        ref_msg = opre.convolutions[0].conv_tp(x.double()[s], x.double()[r], e.double(), d["edge_attrs"], d["edge_embedding"])
+        ref_agg = torch.zeros(N, D, dtype=torch.float64).index_add_(0, r, ref_msg)
+    old = os.environ.get("HGB_ROT_FMA")
+    try:
+        os.environ["HGB_ROT_FMA"] = fma
+        got = _single_calls(pre, batch, d, dev, x, e, "rot", 0, None)
+    finally:
+        if old is None:
+            os.environ.pop("HGB_ROT_FMA", None)
+        else:
+            os.environ["HGB_ROT_FMA"] = old
+    errs = (rel_err(got[0], ref_msg), rel_err(got[1], ref_agg), rel_err(got[2], ref_pair))
+    print(f"[{cfg_name} rot HGB_ROT_FMA={fma}] rel err message {errs[0]:.2e} scatter {errs[1]:.2e} edge update {errs[2]:.2e}")
     assert max(errs) < TOL, errs
