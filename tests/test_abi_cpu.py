@@ -81,3 +81,13 @@ def test_product_refuses_to_run_without_the_library(monkeypatch):
     for mod in ("hamgnn_b200.plan", "hamgnn_b200.hamgnn_conv", "hamgnn_b200.hamgnn_output", "hamgnn_b200.lib", "hamgnn_b200.dist"):
         src = open(os.path.join(ROOT, *mod.split(".")) + ".py").read()
         assert "oracle" not in re.sub(r"#.*", "", src).replace('"""', ""), f"{mod} must not reference the oracle"
+
+
+def test_streamed_forward_refuses_cpu():
+    """hamgnn_b200.pipeline.streamed_forward is a CUDA-only caller like everything else on the product path."""
+    import torch
+    from hamgnn_b200 import lib as L
+    from hamgnn_b200.pipeline import streamed_forward
+    lin = torch.nn.Linear(2, 2)
+    with pytest.raises(L.HgbError):
+        next(streamed_forward(lin, lin, [], device="cpu"))
